@@ -1,0 +1,694 @@
+// C ABI of libocp_b200 (declared in include/ocp_b200.h).  Context set-up, device tables, the Newton loop,
+// the adjoint solve and the host-buffer entry points.  Every compute entry point launches CUDA kernels;
+// there is no CPU fallback (ocp_create fails with OCP_ERR_NO_DEVICE when no GPU is usable).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ocp_b200.h"
+#include "element_math.cuh"
+#include "host_lu.hpp"
+#include "kernels.cuh"
+#include "sparse_solver.cuh"
+
+using namespace ocp;
+
+struct ocp_ctx {
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int nv = 0, nn = 0, nc = 0, ndofs = 0, nnz = 0, n_dir = 0, n_g1 = 0, nt = 0;
+    double nu = 1.0, dt = 0.0, cx = 0.0, cy = 0.0;
+    DeviceTables tab{};
+    // device tables
+    double *d_geom = nullptr, *d_g1_len = nullptr, *d_g1_normal = nullptr;
+    int *d_cell_nodes = nullptr, *d_cell_dofs = nullptr, *d_cell_slots = nullptr;
+    int *d_dof_ux = nullptr, *d_dof_uy = nullptr, *d_dof_p = nullptr;
+    int *d_rowptr = nullptr, *d_col = nullptr, *d_dir = nullptr;
+    int *d_g1_nodes = nullptr, *d_g1_dofs = nullptr, *d_g1_slots = nullptr;
+    int *d_bin_ptr = nullptr, *d_bin_cells = nullptr;
+    int *d_m_rowptr = nullptr, *d_m_col = nullptr;   // P1 mass matrix
+    double *d_m_vals = nullptr;
+    int m_nnz = 0;
+    // work space
+    double *d_vals = nullptr, *d_res = nullptr, *d_rhs = nullptr, *d_tmp = nullptr, *d_rhs4 = nullptr;
+    double *d_scalar = nullptr, *d_scratch = nullptr;
+    size_t scratch_len = 0;
+    unsigned *d_counter = nullptr;
+    double *h_pinned = nullptr;    // 8 doubles
+    // host-entry staging (grown on demand)
+    double *d_stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stage_len[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint8_t *d_parked = nullptr;
+    size_t parked_len = 0;
+    SparseLU lu_fwd, lu_adj, lu_mass;
+    bool mass_factored = false;
+    int adj_refine = 1;
+    ocp_solver_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+#define CUDA_OK(ctx, call)                                                         \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) {                                                   \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);       \
+            return OCP_ERR_CUDA;                                                   \
+        }                                                                          \
+    } while (0)
+
+template <class T>
+int upload(ocp_ctx *c, T **dst, const T *src, size_t n) {
+    CUDA_OK(c, cudaMalloc((void **)dst, sizeof(T) * std::max<size_t>(n, 1)));
+    if (n) CUDA_OK(c, cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+    return OCP_OK;
+}
+
+int ensure_scratch(ocp_ctx *c, size_t n) {
+    if (n <= c->scratch_len) return OCP_OK;
+    cudaFree(c->d_scratch);
+    c->d_scratch = nullptr;
+    c->scratch_len = 0;
+    CUDA_OK(c, cudaMalloc((void **)&c->d_scratch, sizeof(double) * n));
+    c->scratch_len = n;
+    return OCP_OK;
+}
+
+int ensure_stage(ocp_ctx *c, int i, size_t n) {
+    if (n <= c->stage_len[i]) return OCP_OK;
+    cudaFree(c->d_stage[i]);
+    c->d_stage[i] = nullptr;
+    c->stage_len[i] = 0;
+    CUDA_OK(c, cudaMalloc((void **)&c->d_stage[i], sizeof(double) * n));
+    c->stage_len[i] = n;
+    return OCP_OK;
+}
+
+int ensure_parked(ocp_ctx *c, size_t n) {
+    if (n <= c->parked_len) return OCP_OK;
+    cudaFree(c->d_parked);
+    c->d_parked = nullptr;
+    c->parked_len = 0;
+    CUDA_OK(c, cudaMalloc((void **)&c->d_parked, n));
+    c->parked_len = n;
+    return OCP_OK;
+}
+
+int find_slot(const int *rowptr, const int *col, int r, int cidx) {
+    const int *b = col + rowptr[r], *e = col + rowptr[r + 1];
+    const int *p = std::lower_bound(b, e, cidx);
+    return (p != e && *p == cidx) ? (int)(p - col) : -1;
+}
+
+struct PhaseTimer {
+    ocp_ctx *c;
+    double *acc;
+    PhaseTimer(ocp_ctx *ctx, double *a) : c(ctx), acc(a) { cudaEventRecord(c->ev0, c->stream); }
+    ~PhaseTimer() {
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        *acc += ms;
+    }
+};
+
+// forward residual / matrix assembly on the context's work arrays
+int assemble_forward(ocp_ctx *c, const double *d_w, const double *d_f, double *d_vals, double *d_res, bool bc) {
+    cudaStream_t s = c->stream;
+    if (d_vals) CUDA_OK(c, cudaMemsetAsync(d_vals, 0, sizeof(double) * c->nnz, s));
+    if (d_res) CUDA_OK(c, cudaMemsetAsync(d_res, 0, sizeof(double) * c->ndofs, s));
+    launch_assemble_cells(c->nc, c->d_geom, c->d_cell_dofs, c->d_cell_slots, d_w, c->nu, false, d_vals, d_res, s);
+    launch_assemble_facets(c->n_g1, c->d_g1_nodes, c->d_g1_dofs, c->d_g1_slots, c->d_g1_len, c->d_g1_normal,
+                           c->d_dof_ux, c->d_dof_uy, d_w, d_f, false, d_vals, d_res, s);
+    if (bc) launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, d_vals, d_res, d_w, s);
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+int assemble_adjoint(ocp_ctx *c, const double *d_w, double *d_vals, bool bc) {
+    cudaStream_t s = c->stream;
+    CUDA_OK(c, cudaMemsetAsync(d_vals, 0, sizeof(double) * c->nnz, s));
+    // the adjoint form carries no viscosity factor (OCP_dolfin.py:344): nu := 1
+    launch_assemble_cells(c->nc, c->d_geom, c->d_cell_dofs, c->d_cell_slots, d_w, 1.0, true, d_vals, nullptr, s);
+    launch_assemble_facets(c->n_g1, c->d_g1_nodes, c->d_g1_dofs, c->d_g1_slots, c->d_g1_len, c->d_g1_normal,
+                           c->d_dof_ux, c->d_dof_uy, d_w, nullptr, true, d_vals, nullptr, s);
+    if (bc) launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, d_vals, nullptr, nullptr, s);
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+int read_scalar(ocp_ctx *c, const double *d, int n, double *h) {
+    CUDA_OK(c, cudaMemcpyAsync(c->h_pinned, d, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) h[i] = c->h_pinned[i];
+    return OCP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ocp_version(void) { return 100; }
+
+int ocp_device_available(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return OCP_ERR_NO_DEVICE;
+    }
+    return OCP_OK;
+}
+
+const char *ocp_last_error(const ocp_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void ocp_get_solver_stats(const ocp_ctx *ctx, ocp_solver_stats *out) {
+    if (ctx && out) *out = ctx->stats;
+}
+
+void ocp_reset_solver_stats(ocp_ctx *ctx) {
+    if (ctx) {
+        double keep = ctx->stats.analyse_ms;
+        ctx->stats = ocp_solver_stats{};
+        ctx->stats.analyse_ms = keep;
+    }
+}
+
+void ocp_set_viscosity(ocp_ctx *ctx, double viscosity) {
+    if (ctx) ctx->nu = viscosity;
+}
+
+int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
+    if (!d || !out) return OCP_ERR_INVALID;
+    *out = nullptr;
+    if (ocp_device_available() != OCP_OK) return OCP_ERR_NO_DEVICE;
+    if (d->ndofs != 2 * d->nn + d->nv || d->nt < 2 || d->nc <= 0) return OCP_ERR_INVALID;
+    ocp_ctx *c = new ocp_ctx();
+    *out = c;   // returned even on failure so that the caller can read ocp_last_error, then destroy
+    c->stream = (cudaStream_t)stream;
+    c->nv = d->nv; c->nn = d->nn; c->nc = d->nc; c->ndofs = d->ndofs; c->nnz = d->nnz;
+    c->n_dir = d->n_dirichlet; c->n_g1 = d->n_g1; c->nt = d->nt;
+    c->nu = d->viscosity; c->dt = d->dt; c->cx = d->center_x; c->cy = d->center_y;
+    const int nc = d->nc, nn = d->nn, nv = d->nv, n = d->ndofs;
+
+    // derived host tables: cell dofs, CSR slots of every element / facet entry
+    std::vector<int> cell_dofs((size_t)nc * 15), slots((size_t)nc * 225);
+    for (int e = 0; e < nc; ++e) {
+        const int *cn = d->cell_nodes + 6 * (size_t)e;
+        int *cd = cell_dofs.data() + 15 * (size_t)e;
+        for (int a = 0; a < 6; ++a) {
+            if (cn[a] < 0 || cn[a] >= nn) { c->err = "cell_nodes out of range"; return OCP_ERR_INVALID; }
+            cd[a] = d->dof_ux[cn[a]];
+            cd[6 + a] = d->dof_uy[cn[a]];
+        }
+        for (int a = 0; a < 3; ++a) {
+            if (cn[a] >= nv) { c->err = "cell vertex index >= nv"; return OCP_ERR_INVALID; }
+            cd[12 + a] = d->dof_p[cn[a]];
+        }
+        for (int i = 0; i < 15; ++i)
+            for (int j = 0; j < 15; ++j) {
+                int sl = find_slot(d->csr_rowptr, d->csr_col, cd[i], cd[j]);
+                if (sl < 0) { c->err = "CSR pattern misses an element entry"; return OCP_ERR_INVALID; }
+                slots[(size_t)e * 225 + i * 15 + j] = sl;
+            }
+    }
+    std::vector<int> g1_dofs((size_t)d->n_g1 * 6), g1_slots((size_t)d->n_g1 * 36);
+    for (int f = 0; f < d->n_g1; ++f) {
+        int *gd = g1_dofs.data() + 6 * (size_t)f;
+        for (int a = 0; a < 3; ++a) {
+            gd[a] = d->dof_ux[d->g1_nodes[3 * f + a]];
+            gd[3 + a] = d->dof_uy[d->g1_nodes[3 * f + a]];
+        }
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) {
+                int sl = find_slot(d->csr_rowptr, d->csr_col, gd[i], gd[j]);
+                if (sl < 0) { c->err = "CSR pattern misses a facet entry"; return OCP_ERR_INVALID; }
+                g1_slots[(size_t)f * 36 + i * 6 + j] = sl;
+            }
+    }
+    // P1 mass matrix (constant): pattern + values, area/12 (1 + delta_ab)
+    std::vector<std::vector<std::pair<int, double>>> rows(nv);
+    for (int e = 0; e < nc; ++e) {
+        const double *g = d->cell_geom + 6 * (size_t)e;
+        const double area = 0.5 / std::fabs(g[2] * g[5] - g[4] * g[3]);
+        const int *cn = d->cell_nodes + 6 * (size_t)e;
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) rows[cn[a]].push_back({cn[b], area / 12.0 * (a == b ? 2.0 : 1.0)});
+    }
+    std::vector<int> m_rowptr(nv + 1, 0), m_col;
+    std::vector<double> m_val;
+    for (int i = 0; i < nv; ++i) {
+        auto &r = rows[i];
+        std::sort(r.begin(), r.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) {
+            return a.first < b.first;
+        });
+        for (size_t k = 0; k < r.size(); ++k) {
+            if (k > 0 && r[k].first == r[k - 1].first)
+                m_val.back() += r[k].second;
+            else {
+                m_col.push_back(r[k].first);
+                m_val.push_back(r[k].second);
+            }
+        }
+        m_rowptr[i + 1] = (int)m_col.size();
+    }
+    c->m_nnz = (int)m_col.size();
+
+#define UP(dst, src, cnt)                                        \
+    do {                                                         \
+        int rc_ = upload(c, &c->dst, src, (size_t)(cnt));        \
+        if (rc_ != OCP_OK) return rc_;                           \
+    } while (0)
+    UP(d_geom, d->cell_geom, (size_t)nc * 6);
+    UP(d_cell_nodes, d->cell_nodes, (size_t)nc * 6);
+    UP(d_cell_dofs, cell_dofs.data(), cell_dofs.size());
+    UP(d_cell_slots, slots.data(), slots.size());
+    UP(d_dof_ux, d->dof_ux, nn);
+    UP(d_dof_uy, d->dof_uy, nn);
+    UP(d_dof_p, d->dof_p, nv);
+    UP(d_rowptr, d->csr_rowptr, n + 1);
+    UP(d_col, d->csr_col, d->nnz);
+    UP(d_dir, d->dirichlet_dofs, d->n_dirichlet);
+    UP(d_g1_nodes, d->g1_nodes, (size_t)d->n_g1 * 3);
+    UP(d_g1_dofs, g1_dofs.data(), g1_dofs.size());
+    UP(d_g1_slots, g1_slots.data(), g1_slots.size());
+    UP(d_g1_len, d->g1_len, d->n_g1);
+    UP(d_g1_normal, d->g1_normal, (size_t)d->n_g1 * 2);
+    UP(d_bin_ptr, d->bin_ptr, (size_t)d->nbx * d->nby + 1);
+    UP(d_bin_cells, d->bin_cells, d->bin_ptr[(size_t)d->nbx * d->nby]);
+    UP(d_m_rowptr, m_rowptr.data(), m_rowptr.size());
+    UP(d_m_col, m_col.data(), m_col.size());
+    UP(d_m_vals, m_val.data(), m_val.size());
+#undef UP
+    CUDA_OK(c, cudaMalloc((void **)&c->d_vals, sizeof(double) * d->nnz));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_res, sizeof(double) * n));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_rhs, sizeof(double) * n));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_tmp, sizeof(double) * n));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_rhs4, sizeof(double) * 4 * nv));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_scalar, sizeof(double) * 8));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_counter, sizeof(unsigned)));
+    CUDA_OK(c, cudaMemset(c->d_counter, 0, sizeof(unsigned)));
+    CUDA_OK(c, cudaMallocHost((void **)&c->h_pinned, sizeof(double) * 8));
+    CUDA_OK(c, cudaEventCreate(&c->ev0));
+    CUDA_OK(c, cudaEventCreate(&c->ev1));
+    int rc = ensure_scratch(c, 3 * (size_t)((nc + 127) / 128) + 1024);
+    if (rc != OCP_OK) return rc;
+
+    c->tab.nc = nc; c->tab.nn = nn; c->tab.nv = nv;
+    c->tab.geom = c->d_geom; c->tab.cell_nodes = c->d_cell_nodes;
+    c->tab.ox = d->bin_ox; c->tab.oy = d->bin_oy; c->tab.ihx = d->bin_ihx; c->tab.ihy = d->bin_ihy;
+    c->tab.nbx = d->nbx; c->tab.nby = d->nby;
+    c->tab.bin_ptr = c->d_bin_ptr; c->tab.bin_cells = c->d_bin_cells;
+
+    // solver configuration: dof coordinates and kinds for the nested-dissection order
+    std::vector<double> xy(2 * (size_t)n);
+    std::vector<unsigned char> kind(n, 0);
+    for (int i = 0; i < nn; ++i) {
+        for (int k = 0; k < 2; ++k) {
+            xy[2 * (size_t)d->dof_ux[i] + k] = d->node_coords[2 * (size_t)i + k];
+            xy[2 * (size_t)d->dof_uy[i] + k] = d->node_coords[2 * (size_t)i + k];
+        }
+    }
+    for (int i = 0; i < nv; ++i) {
+        xy[2 * (size_t)d->dof_p[i]] = d->node_coords[2 * (size_t)i];
+        xy[2 * (size_t)d->dof_p[i] + 1] = d->node_coords[2 * (size_t)i + 1];
+        kind[d->dof_p[i]] = 1;
+    }
+    c->lu_fwd.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data());
+    c->lu_adj.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data());
+    std::vector<unsigned char> kind0(nv, 0);
+    c->lu_mass.configure(nv, c->m_nnz, m_rowptr.data(), m_col.data(), c->d_m_rowptr, c->d_m_col, d->node_coords,
+                         kind0.data());
+    return OCP_OK;
+}
+
+void ocp_destroy(ocp_ctx *c) {
+    if (!c) return;
+    void *ptrs[] = {c->d_geom, c->d_g1_len, c->d_g1_normal, c->d_cell_nodes, c->d_cell_dofs, c->d_cell_slots,
+                    c->d_dof_ux, c->d_dof_uy, c->d_dof_p, c->d_rowptr, c->d_col, c->d_dir, c->d_g1_nodes,
+                    c->d_g1_dofs, c->d_g1_slots, c->d_bin_ptr, c->d_bin_cells, c->d_m_rowptr, c->d_m_col,
+                    c->d_m_vals, c->d_vals, c->d_res, c->d_rhs, c->d_tmp, c->d_rhs4, c->d_scalar, c->d_scratch,
+                    c->d_counter, c->d_parked};
+    for (void *p : ptrs) cudaFree(p);
+    for (int i = 0; i < 8; ++i) cudaFree(c->d_stage[i]);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+}
+
+int ocp_assemble_forward(ocp_ctx *c, const double *d_w, const double *d_f, double *d_vals, double *d_res,
+                         int apply_bc) {
+    if (!c || !d_w) return OCP_ERR_INVALID;
+    int rc = assemble_forward(c, d_w, d_f, d_vals, d_res, apply_bc != 0);
+    if (rc != OCP_OK) return rc;
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return OCP_OK;
+}
+
+int ocp_assemble_adjoint(ocp_ctx *c, const double *d_w, double *d_vals, int apply_bc) {
+    if (!c || !d_w || !d_vals) return OCP_ERR_INVALID;
+    int rc = assemble_adjoint(c, d_w, d_vals, apply_bc != 0);
+    if (rc != OCP_OK) return rc;
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return OCP_OK;
+}
+
+int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init, int *newton_its,
+                      double *h_res_hist) {
+    if (!c || !d_f || !d_w) return OCP_ERR_INVALID;
+    cudaStream_t s = c->stream;
+    const int n = c->ndofs;
+    const double atol = 1e-10, rtol = 1e-9;
+    const int maxit = 50;
+    if (zero_init) CUDA_OK(c, cudaMemsetAsync(d_w, 0, sizeof(double) * n, s));
+    double r0 = 0.0, r = 0.0;
+    int it = 0;
+    for (;;) {
+        {
+            PhaseTimer t(c, &c->stats.assemble_ms);
+            // residual and Newton matrix at the current iterate in one pass over the cells
+            int rc = assemble_forward(c, d_w, d_f, c->d_vals, c->d_res, true);
+            if (rc != OCP_OK) return rc;
+            launch_sumsq(n, c->d_res, c->d_scalar, c->d_scratch, c->d_counter, s);
+        }
+        double ss;
+        int rc = read_scalar(c, c->d_scalar, 1, &ss);
+        if (rc != OCP_OK) return rc;
+        r = std::sqrt(ss);
+        if (it == 0) r0 = r;
+        if (h_res_hist) h_res_hist[it] = r;
+        if (!(r == r)) {
+            c->err = "Newton residual is NaN";
+            if (newton_its) *newton_its = it;
+            return OCP_ERR_NOT_CONVERGED;
+        }
+        if (r < atol || (r0 > 0.0 && r / r0 < rtol)) break;
+        if (it >= maxit) {
+            c->err = "Newton solver did not converge in 50 iterations";
+            if (newton_its) *newton_its = it;
+            return OCP_ERR_NOT_CONVERGED;
+        }
+        {
+            PhaseTimer t(c, &c->stats.factor_ms);
+            bool first = !c->lu_fwd.analysed();
+            if (!c->lu_fwd.factor(c->d_vals, s, c->err)) return OCP_ERR_SOLVER;
+            if (first) c->stats.analyse_ms += c->lu_fwd.analyse_ms;
+            c->stats.n_factor++;
+        }
+        {
+            PhaseTimer t(c, &c->stats.solve_ms);
+            if (!c->lu_fwd.solve(c->d_res, s, c->err)) return OCP_ERR_SOLVER;   // d_res <- dx
+            launch_axpy(n, -1.0, c->d_res, d_w, s);
+            c->stats.n_solve++;
+        }
+        ++it;
+    }
+    if (newton_its) *newton_its = it;
+    return OCP_OK;
+}
+
+int ocp_velocity_nodal(ocp_ctx *c, const double *d_w, double *d_vel) {
+    if (!c || !d_w || !d_vel) return OCP_ERR_INVALID;
+    launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, d_w, d_vel, c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+int ocp_project_grad(ocp_ctx *c, const double *d_w, double *d_g) {
+    if (!c || !d_w || !d_g) return OCP_ERR_INVALID;
+    cudaStream_t s = c->stream;
+    const int nv = c->nv;
+    {
+        PhaseTimer t(c, &c->stats.assemble_ms);
+        CUDA_OK(c, cudaMemsetAsync(c->d_rhs4, 0, sizeof(double) * 4 * nv, s));
+        launch_gradproj_rhs(c->nc, nv, c->d_geom, c->d_cell_nodes, c->d_cell_dofs, d_w, c->d_rhs4, s);
+        CUDA_OK(c, cudaGetLastError());
+    }
+    if (!c->mass_factored) {
+        PhaseTimer t(c, &c->stats.factor_ms);
+        if (!c->lu_mass.factor(c->d_m_vals, s, c->err)) return OCP_ERR_SOLVER;
+        c->stats.analyse_ms += c->lu_mass.analyse_ms;
+        c->mass_factored = true;
+    }
+    {
+        PhaseTimer t(c, &c->stats.solve_ms);
+        for (int j = 0; j < 4; ++j) {
+            if (!c->lu_mass.solve(c->d_rhs4 + (size_t)j * nv, s, c->err)) return OCP_ERR_SOLVER;
+            c->stats.n_solve++;
+        }
+        launch_transpose4(nv, c->d_rhs4, d_g, s);
+        CUDA_OK(c, cudaGetLastError());
+    }
+    return OCP_OK;
+}
+
+int ocp_buoy_forward(ocp_ctx *c, const double *d_vel, const double *d_x0, int K, double *d_x, double *d_u,
+                     int32_t *d_cell, double *d_mask, uint8_t *d_parked) {
+    if (!c || !d_vel || !d_x0 || !d_x || !d_u || !d_mask || !d_parked || K < 0) return OCP_ERR_INVALID;
+    launch_buoy_forward(c->tab, d_vel, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_cell, d_mask, d_parked,
+                        c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+int ocp_buoy_adjoint_scatter(ocp_ctx *c, const double *d_vel, const double *d_g, int K, const double *d_x,
+                             const double *d_u, const double *d_ud, const double *d_mask, const uint8_t *d_parked,
+                             double *d_mu, double *d_acc) {
+    if (!c || !d_vel || !d_g || !d_x || !d_u || !d_ud || !d_mask || !d_parked || !d_acc || K < 0)
+        return OCP_ERR_INVALID;
+    int rc = ensure_scratch(c, 2 * (size_t)buoy_max_blocks(K) + 2);
+    if (rc != OCP_OK) return rc;
+    launch_buoy_adjoint_scatter(c->tab, d_vel, d_g, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_ud, d_mask, d_parked,
+                                d_mu, d_acc, c->d_scratch, c->d_counter, c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+int ocp_misfit(ocp_ctx *c, int K, const double *d_u, const double *d_ud, double *d_out) {
+    if (!c || !d_u || !d_ud || !d_out || K < 0) return OCP_ERR_INVALID;
+    int rc = ensure_scratch(c, 2 * 148 * 8 + 2);
+    if (rc != OCP_OK) return rc;
+    launch_misfit(K, c->nt, c->dt, d_u, d_ud, d_out, c->d_scratch, c->d_counter, c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+int ocp_adjoint_solve(ocp_ctx *c, const double *d_w, const double *d_bnode, double *d_z) {
+    if (!c || !d_w || !d_bnode || !d_z) return OCP_ERR_INVALID;
+    cudaStream_t s = c->stream;
+    const int n = c->ndofs;
+    {
+        PhaseTimer t(c, &c->stats.assemble_ms);
+        int rc = assemble_adjoint(c, d_w, c->d_vals, true);
+        if (rc != OCP_OK) return rc;
+        launch_rhs_from_nodal(c->nn, c->nv, c->d_dof_ux, c->d_dof_uy, c->d_dof_p, d_bnode, c->d_rhs, s);
+        launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, nullptr, c->d_rhs, nullptr, s);   // b[d] = 0
+        CUDA_OK(c, cudaGetLastError());
+    }
+    {
+        PhaseTimer t(c, &c->stats.factor_ms);
+        bool first = !c->lu_adj.analysed();
+        if (!c->lu_adj.factor(c->d_vals, s, c->err)) return OCP_ERR_SOLVER;
+        if (first) c->stats.analyse_ms += c->lu_adj.analyse_ms;
+        c->stats.n_factor++;
+    }
+    {
+        PhaseTimer t(c, &c->stats.solve_ms);
+        CUDA_OK(c, cudaMemcpyAsync(d_z, c->d_rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        if (!c->lu_adj.solve(d_z, s, c->err)) return OCP_ERR_SOLVER;
+        c->stats.n_solve++;
+        for (int k = 0; k < c->adj_refine; ++k) {   // one step of iterative refinement on the same factors
+            launch_spmv_residual(n, c->d_rowptr, c->d_col, c->d_vals, d_z, c->d_rhs, c->d_tmp, s);
+            if (!c->lu_adj.solve(c->d_tmp, s, c->err)) return OCP_ERR_SOLVER;
+            launch_axpy(n, 1.0, c->d_tmp, d_z, s);
+            c->stats.n_solve++;
+        }
+        CUDA_OK(c, cudaGetLastError());
+    }
+    return OCP_OK;
+}
+
+int ocp_boundary_inner(ocp_ctx *c, const double *d_a, const double *d_b, double *d_out) {
+    if (!c || !d_a || !d_b || !d_out) return OCP_ERR_INVALID;
+    launch_boundary_inner(c->n_g1, c->d_g1_nodes, c->d_g1_len, d_a, d_b, d_out, c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+int ocp_nodal_axpby(ocp_ctx *c, double ca, const double *d_a, double cb, const double *d_b, double *d_out) {
+    if (!c || !d_a || !d_b || !d_out) return OCP_ERR_INVALID;
+    launch_axpby(2 * c->nn, ca, d_a, cb, d_b, d_out, c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+int ocp_field_norms(ocp_ctx *c, const double *d_w, double *d_out) {
+    if (!c || !d_w || !d_out) return OCP_ERR_INVALID;
+    int rc = ensure_scratch(c, 3 * (size_t)((c->nc + 127) / 128) + 8);
+    if (rc != OCP_OK) return rc;
+    launch_field_norms(c->nc, c->d_geom, c->d_cell_dofs, d_w, d_out, c->d_scratch, c->d_counter, c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+int ocp_traj_transpose(ocp_ctx *c, const double *d_src, double *d_dst, int K, int to_time_major) {
+    if (!c || !d_src || !d_dst || K < 0) return OCP_ERR_INVALID;
+    launch_traj_transpose(d_src, d_dst, K, c->nt, to_time_major, c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------------------------
+
+int ocp_solve_primal_ode_host(ocp_ctx *c, const double *h_w, const double *h_x0, int K, double *h_x, double *h_u,
+                              double *h_mask) {
+    if (!c || !h_w || !h_x0 || !h_x || !h_u || !h_mask || K < 0) return OCP_ERR_INVALID;
+    cudaStream_t s = c->stream;
+    const size_t tr = (size_t)K * c->nt * 2;
+    int rc;
+    if ((rc = ensure_stage(c, 0, c->ndofs)) || (rc = ensure_stage(c, 1, 2 * (size_t)c->nn)) ||
+        (rc = ensure_stage(c, 2, 2 * (size_t)K + 2)) || (rc = ensure_stage(c, 3, tr)) ||
+        (rc = ensure_stage(c, 4, tr)) || (rc = ensure_stage(c, 5, tr)) || (rc = ensure_stage(c, 6, (size_t)K + 1)) ||
+        (rc = ensure_parked(c, (size_t)K + 1)))
+        return rc;
+    double *d_w = c->d_stage[0], *d_vel = c->d_stage[1], *d_x0 = c->d_stage[2], *d_x = c->d_stage[3],
+           *d_u = c->d_stage[4], *d_t = c->d_stage[5], *d_mask = c->d_stage[6];
+    CUDA_OK(c, cudaMemcpyAsync(d_w, h_w, sizeof(double) * c->ndofs, cudaMemcpyHostToDevice, s));
+    CUDA_OK(c, cudaMemcpyAsync(d_x0, h_x0, sizeof(double) * 2 * K, cudaMemcpyHostToDevice, s));
+    CUDA_OK(c, cudaMemcpyAsync(d_mask, h_mask, sizeof(double) * K, cudaMemcpyHostToDevice, s));
+    launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, d_w, d_vel, s);
+    launch_buoy_forward(c->tab, d_vel, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, nullptr, d_mask, c->d_parked, s);
+    launch_traj_transpose(d_x, d_t, K, c->nt, 0, s);
+    CUDA_OK(c, cudaMemcpyAsync(h_x, d_t, sizeof(double) * tr, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(c, cudaStreamSynchronize(s));   // d_t is reused for u
+    launch_traj_transpose(d_u, d_t, K, c->nt, 0, s);
+    CUDA_OK(c, cudaMemcpyAsync(h_u, d_t, sizeof(double) * tr, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(c, cudaMemcpyAsync(h_mask, d_mask, sizeof(double) * K, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(c, cudaStreamSynchronize(s));
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+int ocp_solve_adjoint_ode_host(ocp_ctx *c, const double *h_g, const double *h_x, const double *h_u,
+                               const double *h_ud, const double *h_mask, int K, double *h_mu) {
+    if (!c || !h_g || !h_x || !h_u || !h_ud || !h_mask || !h_mu || K < 0) return OCP_ERR_INVALID;
+    cudaStream_t s = c->stream;
+    const size_t tr = (size_t)K * c->nt * 2;
+    const size_t nacc = 2 * (size_t)c->nn + 2;
+    int rc;
+    if ((rc = ensure_stage(c, 0, 4 * (size_t)c->nv)) || (rc = ensure_stage(c, 1, nacc)) ||
+        (rc = ensure_stage(c, 2, tr)) || (rc = ensure_stage(c, 3, tr)) || (rc = ensure_stage(c, 4, tr)) ||
+        (rc = ensure_stage(c, 5, tr)) || (rc = ensure_stage(c, 6, (size_t)K + 1)) ||
+        (rc = ensure_stage(c, 7, 2 * (size_t)c->nn)) || (rc = ensure_parked(c, (size_t)K + 1)) ||
+        (rc = ensure_scratch(c, 2 * (size_t)buoy_max_blocks(K) + 2)))
+        return rc;
+    double *d_g = c->d_stage[0], *d_acc = c->d_stage[1], *d_x = c->d_stage[2], *d_u = c->d_stage[3],
+           *d_ud = c->d_stage[4], *d_t = c->d_stage[5], *d_mask = c->d_stage[6], *d_vel = c->d_stage[7];
+    CUDA_OK(c, cudaMemcpyAsync(d_g, h_g, sizeof(double) * 4 * c->nv, cudaMemcpyHostToDevice, s));
+    CUDA_OK(c, cudaMemcpyAsync(d_mask, h_mask, sizeof(double) * K, cudaMemcpyHostToDevice, s));
+    const double *src[3] = {h_x, h_u, h_ud};
+    double *dst[3] = {d_x, d_u, d_ud};
+    for (int i = 0; i < 3; ++i) {
+        CUDA_OK(c, cudaMemcpyAsync(d_t, src[i], sizeof(double) * tr, cudaMemcpyHostToDevice, s));
+        launch_traj_transpose(d_t, dst[i], K, c->nt, 1, s);
+    }
+    // the adjoint ODE alone needs neither the velocity field nor the parked flags: zero them
+    CUDA_OK(c, cudaMemsetAsync(d_vel, 0, sizeof(double) * 2 * c->nn, s));
+    CUDA_OK(c, cudaMemsetAsync(c->d_parked, 0, (size_t)K + 1, s));
+    CUDA_OK(c, cudaMemsetAsync(d_acc, 0, sizeof(double) * nacc, s));
+    launch_buoy_adjoint_scatter(c->tab, d_vel, d_g, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_ud, d_mask,
+                                c->d_parked, d_t, d_acc, c->d_scratch, c->d_counter, s);
+    launch_traj_transpose(d_t, d_x, K, c->nt, 0, s);
+    CUDA_OK(c, cudaMemcpyAsync(h_mu, d_x, sizeof(double) * tr, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(c, cudaStreamSynchronize(s));
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+int ocp_gradient_host(ocp_ctx *c, const double *h_f, const double *h_x0, const double *h_ud, int K, double *h_w,
+                      double *h_z, double *h_mask, double *h_scalars) {
+    if (!c || !h_f || !h_x0 || !h_ud || !h_w || !h_z || !h_mask || !h_scalars || K < 0) return OCP_ERR_INVALID;
+    cudaStream_t s = c->stream;
+    const size_t tr = (size_t)K * c->nt * 2;
+    const size_t nacc = 2 * (size_t)c->nn + 2;
+    const int n = c->ndofs;
+    int rc;
+    if ((rc = ensure_stage(c, 0, 2 * (size_t)n + 4 + 4 * (size_t)c->nv)) || (rc = ensure_stage(c, 1, nacc + 2 * (size_t)c->nn)) ||
+        (rc = ensure_stage(c, 2, tr)) || (rc = ensure_stage(c, 3, tr)) || (rc = ensure_stage(c, 4, tr)) ||
+        (rc = ensure_stage(c, 5, tr)) || (rc = ensure_stage(c, 6, 3 * (size_t)K + 4)) ||
+        (rc = ensure_stage(c, 7, 2 * (size_t)c->nn)) || (rc = ensure_parked(c, (size_t)K + 1)))
+        return rc;
+    const size_t npad = ((size_t)n + 1) & ~(size_t)1, kpad = ((size_t)K + 1) & ~(size_t)1;   // keep 16-byte alignment
+    double *d_w = c->d_stage[0], *d_z = d_w + npad, *d_g = d_z + npad;
+    double *d_acc = c->d_stage[1], *d_f = d_acc + nacc;
+    double *d_x = c->d_stage[2], *d_u = c->d_stage[3], *d_ud = c->d_stage[4], *d_t = c->d_stage[5];
+    double *d_mask = c->d_stage[6], *d_x0 = d_mask + kpad;
+    double *d_vel = c->d_stage[7];
+    CUDA_OK(c, cudaMemcpyAsync(d_f, h_f, sizeof(double) * 2 * c->nn, cudaMemcpyHostToDevice, s));
+    CUDA_OK(c, cudaMemcpyAsync(d_x0, h_x0, sizeof(double) * 2 * K, cudaMemcpyHostToDevice, s));
+    CUDA_OK(c, cudaMemcpyAsync(d_t, h_ud, sizeof(double) * tr, cudaMemcpyHostToDevice, s));
+    launch_traj_transpose(d_t, d_ud, K, c->nt, 1, s);
+    CUDA_OK(c, cudaMemsetAsync(d_mask, 0, sizeof(double) * K, s));
+    CUDA_OK(c, cudaMemsetAsync(d_acc, 0, sizeof(double) * nacc, s));
+    int its = 0;
+    if ((rc = ocp_forward_solve(c, d_f, d_w, 1, &its, nullptr))) return rc;
+    if ((rc = ocp_project_grad(c, d_w, d_g))) return rc;
+    launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, d_w, d_vel, s);
+    launch_buoy_forward(c->tab, d_vel, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, nullptr, d_mask, c->d_parked, s);
+    if ((rc = ocp_buoy_adjoint_scatter(c, d_vel, d_g, K, d_x, d_u, d_ud, d_mask, c->d_parked, nullptr, d_acc))) return rc;
+    if ((rc = ocp_adjoint_solve(c, d_w, d_acc, d_z))) return rc;
+    launch_boundary_inner(c->n_g1, c->d_g1_nodes, c->d_g1_len, d_f, d_f, c->d_scalar, s);
+    CUDA_OK(c, cudaMemcpyAsync(h_w, d_w, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(c, cudaMemcpyAsync(h_z, d_z, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(c, cudaMemcpyAsync(h_mask, d_mask, sizeof(double) * K, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(c, cudaMemcpyAsync(c->h_pinned, d_acc + 2 * (size_t)c->nn, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(c, cudaMemcpyAsync(c->h_pinned + 2, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(c, cudaStreamSynchronize(s));
+    h_scalars[0] = c->h_pinned[0];
+    h_scalars[1] = c->h_pinned[2];
+    h_scalars[2] = c->h_pinned[1];
+    h_scalars[3] = (double)its;
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+// ---- element-level self-tests: the same __host__ __device__ arithmetic the kernels run, evaluated on the
+// host for ONE element so that CPU-only unit tests can check it against the oracle.  Not a compute path.
+void ocp_selftest_cell_matrix(const double *geom6, const double *coef15, double nu, double *A225, double *R15) {
+    for (int r = 0; r < 15; ++r) cell_row(geom6, coef15, coef15 + 6, coef15 + 12, nu, r, A225 + 15 * r, R15[r]);
+}
+
+void ocp_selftest_facet_matrix(double len, double nx, double ny, const double *uv6, const double *f6, double *A36,
+                               double *R6) {
+    for (int r = 0; r < 6; ++r) facet_row(len, nx, ny, uv6, uv6 + 3, f6, f6 + 3, r, A36 + 6 * r, R6[r]);
+}
+
+int64_t ocp_host_lu_probe(int32_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *xy,
+                          double *rhs_inout, int32_t *p, int32_t *q) {
+    if (n <= 0 || !rowptr || !col || !val || !xy) return OCP_ERR_INVALID;
+    std::vector<unsigned char> kind(n, 0);
+    // structural-zero diagonal => pressure-like dof (ordered after its neighbours)
+    for (int i = 0; i < n; ++i) {
+        bool nz = false;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+            if (col[k] == i && val[k] != 0.0) nz = true;
+        kind[i] = nz ? 0 : 1;
+    }
+    std::vector<int> qq;
+    nested_dissection_order(n, rowptr, col, xy, kind.data(), qq);
+    HostLU lu;
+    if (!sparse_lu(n, rowptr, col, val, qq, 1.0e-3, lu)) return OCP_ERR_SOLVER;
+    if (rhs_inout) host_lu_solve(lu, rhs_inout);
+    if (p) std::copy(lu.P.begin(), lu.P.end(), p);
+    if (q) std::copy(lu.Q.begin(), lu.Q.end(), q);
+    return (int64_t)lu.Lx.size() + (int64_t)lu.Ux.size();
+}
+
+}  // extern "C"

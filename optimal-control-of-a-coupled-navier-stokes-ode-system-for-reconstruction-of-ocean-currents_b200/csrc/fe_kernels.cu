@@ -1,0 +1,389 @@
+// Finite-element kernels: cell-parallel assembly of the Taylor-Hood Newton matrix / residual and of the
+// adjoint operator (atomic fp64 scatter into the precomputed CSR pattern through per-cell slot tables),
+// Gamma_1 facet blocks, Dirichlet rows, the grad(u) projection right-hand side, boundary forms and norms.
+#include "element_math.cuh"
+#include "kernels.cuh"
+
+namespace ocp {
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic grid reduction of up to three values (see buoy_kernels.cu for the two-value variant)
+__device__ __forceinline__ void block_finish3(double a, double b, double c, double *scratch, unsigned *counter,
+                                              double *out, int nout, bool accumulate) {
+    __shared__ double sm[3][32];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    c = warp_sum(c);
+    if (lane == 0) {
+        sm[0][wid] = a;
+        sm[1][wid] = b;
+        sm[2][wid] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[3] = {0.0, 0.0, 0.0};
+        for (int i = 0; i < nw; ++i)
+            for (int j = 0; j < 3; ++j) t[j] += sm[j][i];
+        for (int j = 0; j < 3; ++j) scratch[3 * blockIdx.x + j] = t[j];
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 32) {
+        __threadfence();
+        double t[3] = {0.0, 0.0, 0.0};
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 32)
+            for (int j = 0; j < 3; ++j) t[j] += __ldcg(scratch + 3 * i + j);
+        for (int j = 0; j < 3; ++j) t[j] = warp_sum(t[j]);
+        if (threadIdx.x == 0) {
+            for (int j = 0; j < nout; ++j) out[j] = accumulate ? out[j] + t[j] : t[j];
+            *counter = 0u;
+        }
+    }
+}
+
+// 16 lanes per cell, lane r < 15 owns row r of the 15x15 element matrix.
+template <bool kTranspose>
+__global__ void __launch_bounds__(256)
+assemble_cells_kernel(int nc, const double *__restrict__ geom, const int *__restrict__ cell_dofs,
+                      const int *__restrict__ slots, const double *__restrict__ w, double nu,
+                      double *__restrict__ vals, double *__restrict__ res) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cell = t >> 4, row = t & 15;
+    if (cell >= nc || row == 15) return;
+    double g[6], U[6], V[6], P[3];
+    const double2 *gp = reinterpret_cast<const double2 *>(geom) + 3 * (size_t)cell;
+    const double2 ga = __ldg(gp), gb = __ldg(gp + 1), gc = __ldg(gp + 2);
+    g[0] = ga.x; g[1] = ga.y; g[2] = gb.x; g[3] = gb.y; g[4] = gc.x; g[5] = gc.y;
+    const int *dofs = cell_dofs + 15 * (size_t)cell;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        U[i] = __ldg(w + __ldg(dofs + i));
+        V[i] = __ldg(w + __ldg(dofs + 6 + i));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) P[i] = __ldg(w + __ldg(dofs + 12 + i));
+    double A[15], R;
+    cell_row(g, U, V, P, nu, row, A, R);
+    if (vals) {
+        const int *sl = slots + 225 * (size_t)cell;
+        const int ncol = row < 12 ? 15 : 12;       // the p-p block is structurally present but zero
+#pragma unroll
+        for (int j = 0; j < 15; ++j)
+            if (j < ncol) atomicAdd(vals + __ldg(sl + (kTranspose ? j * 15 + row : row * 15 + j)), A[j]);
+    }
+    if (res) atomicAdd(res + __ldg(dofs + row), R);
+}
+
+// 8 lanes per facet, lane r < 6 owns row r of the 6x6 facet block.
+template <bool kTranspose>
+__global__ void __launch_bounds__(128)
+assemble_facets_kernel(int n_g1, const int *__restrict__ g1_nodes, const int *__restrict__ g1_dofs,
+                       const int *__restrict__ g1_slots, const double *__restrict__ g1_len,
+                       const double *__restrict__ g1_normal, const int *__restrict__ dof_ux,
+                       const int *__restrict__ dof_uy, const double *__restrict__ w, const double *__restrict__ f,
+                       double *__restrict__ vals, double *__restrict__ res) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int fct = t >> 3, r = t & 7;
+    if (fct >= n_g1 || r >= 6) return;
+    double U[3], V[3], Fx[3] = {0.0, 0.0, 0.0}, Fy[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int n = __ldg(g1_nodes + 3 * fct + a);
+        U[a] = __ldg(w + __ldg(dof_ux + n));
+        V[a] = __ldg(w + __ldg(dof_uy + n));
+        if (f) {
+            Fx[a] = __ldg(f + 2 * (size_t)n);
+            Fy[a] = __ldg(f + 2 * (size_t)n + 1);
+        }
+    }
+    double A[6], R;
+    facet_row(__ldg(g1_len + fct), __ldg(g1_normal + 2 * fct), __ldg(g1_normal + 2 * fct + 1), U, V, Fx, Fy, r, A, R);
+    if (vals) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+            atomicAdd(vals + __ldg(g1_slots + 36 * fct + (kTranspose ? j * 6 + r : r * 6 + j)), A[j]);
+    }
+    if (res) atomicAdd(res + __ldg(g1_dofs + 6 * fct + r), R);
+}
+
+__global__ void dirichlet_kernel(int n_dir, const int *__restrict__ dir, const int *__restrict__ rowptr,
+                                 const int *__restrict__ col, double *__restrict__ vals, double *__restrict__ res,
+                                 const double *__restrict__ w) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_dir) return;
+    const int d = dir[warp];
+    if (vals)
+        for (int p = rowptr[d] + lane; p < rowptr[d + 1]; p += 32) vals[p] = (col[p] == d) ? 1.0 : 0.0;
+    if (res && lane == 0) res[d] = w ? w[d] : 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(int n, const double *__restrict__ v, double *out, double *scratch, unsigned *counter) {
+    double s = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += v[i] * v[i];
+    block_finish3(s, 0.0, 0.0, scratch, counter, out, 1, false);
+}
+
+__global__ void axpy_kernel(int n, double a, const double *__restrict__ x, double *__restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += a * x[i];
+}
+
+__global__ void axpby_kernel(int n, double a, const double *x, double b, const double *y, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a * x[i] + b * y[i];
+}
+
+__global__ void velocity_nodal_kernel(int nn, const int *__restrict__ dof_ux, const int *__restrict__ dof_uy,
+                                      const double *__restrict__ w, double2 *__restrict__ vel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nn) vel[i] = make_double2(w[dof_ux[i]], w[dof_uy[i]]);
+}
+
+__global__ void rhs_from_nodal_kernel(int nn, int nv, const int *__restrict__ dof_ux, const int *__restrict__ dof_uy,
+                                      const int *__restrict__ dof_p, const double2 *__restrict__ bnode,
+                                      double *__restrict__ b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nn) {
+        const double2 v = bnode[i];
+        b[dof_ux[i]] = v.x;
+        b[dof_uy[i]] = v.y;
+        if (i < nv) b[dof_p[i]] = 0.0;
+    }
+}
+
+// Right-hand side of the L2 projection of grad(u) onto continuous P1 (OCP_dolfin.py:328-329):
+// grad(u) is linear per cell, so int (du_i/dx_j) psi_a = area/12 (sum_b D_b + D_a) with D_b its vertex values.
+__global__ void __launch_bounds__(128)
+gradproj_rhs_kernel(int nc, int nv, const double *__restrict__ geom, const int *__restrict__ cell_nodes,
+                    const int *__restrict__ cell_dofs, const double *__restrict__ w, double *__restrict__ rhs4) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= nc) return;
+    const double *g = geom + 6 * (size_t)cell;
+    const double g1x = g[2], g1y = g[3], g2x = g[4], g2y = g[5];
+    const double g0x = -(g1x + g2x), g0y = -(g1y + g2y);
+    const double area = 0.5 / fabs(g1x * g2y - g2x * g1y);
+    const int *dofs = cell_dofs + 15 * (size_t)cell;
+    double U[6], V[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        U[i] = w[dofs[i]];
+        V[i] = w[dofs[6 + i]];
+    }
+    double D[3][4];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const double l0 = b == 0 ? 1.0 : 0.0, l1 = b == 1 ? 1.0 : 0.0, l2 = b == 2 ? 1.0 : 0.0;
+        const double d0 = 4.0 * l0 - 1.0, d1 = 4.0 * l1 - 1.0, d2 = 4.0 * l2 - 1.0;
+        double gx[6], gy[6];
+        gx[0] = d0 * g0x; gy[0] = d0 * g0y;
+        gx[1] = d1 * g1x; gy[1] = d1 * g1y;
+        gx[2] = d2 * g2x; gy[2] = d2 * g2y;
+        gx[3] = 4.0 * (l2 * g1x + l1 * g2x); gy[3] = 4.0 * (l2 * g1y + l1 * g2y);
+        gx[4] = 4.0 * (l2 * g0x + l0 * g2x); gy[4] = 4.0 * (l2 * g0y + l0 * g2y);
+        gx[5] = 4.0 * (l1 * g0x + l0 * g1x); gy[5] = 4.0 * (l1 * g0y + l0 * g1y);
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            a0 += U[k] * gx[k];
+            a1 += U[k] * gy[k];
+            a2 += V[k] * gx[k];
+            a3 += V[k] * gy[k];
+        }
+        D[b][0] = a0; D[b][1] = a1; D[b][2] = a2; D[b][3] = a3;
+    }
+    const double s = area / 12.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double tot = D[0][j] + D[1][j] + D[2][j];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            atomicAdd(rhs4 + (size_t)j * nv + cell_nodes[6 * (size_t)cell + a], s * (tot + D[a][j]));
+    }
+}
+
+__global__ void transpose4_kernel(int nv, const double *__restrict__ src4, double *__restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nv) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[4 * (size_t)i + j] = src4[(size_t)j * nv + i];
+    }
+}
+
+// int_{Gamma_1} a.b ds, exact P2 x P2 facet mass  L/30 [[4,-1,2],[-1,4,2],[2,2,16]]  (single block, deterministic)
+__global__ void __launch_bounds__(256)
+boundary_inner_kernel(int n_g1, const int *__restrict__ g1_nodes, const double *__restrict__ g1_len,
+                      const double2 *__restrict__ a, const double2 *__restrict__ b, double *out) {
+    double s = 0.0;
+    for (int f = threadIdx.x; f < n_g1; f += blockDim.x) {
+        const int n0 = g1_nodes[3 * f], n1 = g1_nodes[3 * f + 1], n2 = g1_nodes[3 * f + 2];
+        const double2 a0 = a[n0], a1 = a[n1], a2 = a[n2], b0 = b[n0], b1 = b[n1], b2 = b[n2];
+        const double mx = a0.x * (4.0 * b0.x - b1.x + 2.0 * b2.x) + a1.x * (-b0.x + 4.0 * b1.x + 2.0 * b2.x) +
+                          a2.x * (2.0 * b0.x + 2.0 * b1.x + 16.0 * b2.x);
+        const double my = a0.y * (4.0 * b0.y - b1.y + 2.0 * b2.y) + a1.y * (-b0.y + 4.0 * b1.y + 2.0 * b2.y) +
+                          a2.y * (2.0 * b0.y + 2.0 * b1.y + 16.0 * b2.y);
+        s += g1_len[f] * (mx + my) / 30.0;
+    }
+    __shared__ double sm[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += sm[i];
+        out[0] = t;
+    }
+}
+
+// ||div u||^2, ||u||^2_{L2}, |u|^2_{H1} (OCP_dolfin.py:430, Pipeline_limits.py:433-443)
+__global__ void __launch_bounds__(128)
+field_norms_kernel(int nc, const double *__restrict__ geom, const int *__restrict__ cell_dofs,
+                   const double *__restrict__ w, double *out3, double *scratch, unsigned *counter) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    double sdiv = 0.0, sl2 = 0.0, sh1 = 0.0;
+    if (cell < nc) {
+        const double *g = geom + 6 * (size_t)cell;
+        const double g1x = g[2], g1y = g[3], g2x = g[4], g2y = g[5];
+        const double g0x = -(g1x + g2x), g0y = -(g1y + g2y);
+        const double area = 0.5 / fabs(g1x * g2y - g2x * g1y);
+        const int *dofs = cell_dofs + 15 * (size_t)cell;
+        double U[6], V[6];
+        for (int i = 0; i < 6; ++i) {
+            U[i] = w[dofs[i]];
+            V[i] = w[dofs[6 + i]];
+        }
+        for (int q = 0; q < 7; ++q) {
+            double l0, l1, l2, wq;
+            tri_qpoint(q, l0, l1, l2, wq);
+            double phi[6], gx[6], gy[6];
+            phi[0] = l0 * (2.0 * l0 - 1.0); phi[1] = l1 * (2.0 * l1 - 1.0); phi[2] = l2 * (2.0 * l2 - 1.0);
+            phi[3] = 4.0 * l1 * l2; phi[4] = 4.0 * l0 * l2; phi[5] = 4.0 * l0 * l1;
+            const double d0 = 4.0 * l0 - 1.0, d1 = 4.0 * l1 - 1.0, d2 = 4.0 * l2 - 1.0;
+            gx[0] = d0 * g0x; gy[0] = d0 * g0y;
+            gx[1] = d1 * g1x; gy[1] = d1 * g1y;
+            gx[2] = d2 * g2x; gy[2] = d2 * g2y;
+            gx[3] = 4.0 * (l2 * g1x + l1 * g2x); gy[3] = 4.0 * (l2 * g1y + l1 * g2y);
+            gx[4] = 4.0 * (l2 * g0x + l0 * g2x); gy[4] = 4.0 * (l2 * g0y + l0 * g2y);
+            gx[5] = 4.0 * (l1 * g0x + l0 * g1x); gy[5] = 4.0 * (l1 * g0y + l0 * g1y);
+            double ux = 0, uy = 0, uxx = 0, uxy = 0, uyx = 0, uyy = 0;
+            for (int b = 0; b < 6; ++b) {
+                ux += U[b] * phi[b]; uy += V[b] * phi[b];
+                uxx += U[b] * gx[b]; uxy += U[b] * gy[b];
+                uyx += V[b] * gx[b]; uyy += V[b] * gy[b];
+            }
+            const double wa = wq * area;
+            sdiv += wa * (uxx + uyy) * (uxx + uyy);
+            sl2 += wa * (ux * ux + uy * uy);
+            sh1 += wa * (uxx * uxx + uxy * uxy + uyx * uyx + uyy * uyy);
+        }
+    }
+    block_finish3(sdiv, sl2, sh1, scratch, counter, out3, 3, false);
+}
+
+// r = b - A x, one warp per row
+__global__ void __launch_bounds__(256)
+spmv_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restrict__ col,
+                     const double *__restrict__ vals, const double *__restrict__ x, const double *__restrict__ b,
+                     double *__restrict__ r) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double s = 0.0;
+    for (int p = rowptr[row] + lane; p < rowptr[row + 1]; p += 32) s += vals[p] * x[col[p]];
+    s = warp_sum(s);
+    if (lane == 0) r[row] = b[row] - s;
+}
+
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+void launch_assemble_cells(int nc, const double *geom, const int *cell_dofs, const int *slots, const double *w,
+                           double nu, bool transpose, double *vals, double *res, cudaStream_t s) {
+    const int blocks = cdiv((long long)nc * 16, 256);
+    if (transpose)
+        assemble_cells_kernel<true><<<blocks, 256, 0, s>>>(nc, geom, cell_dofs, slots, w, nu, vals, res);
+    else
+        assemble_cells_kernel<false><<<blocks, 256, 0, s>>>(nc, geom, cell_dofs, slots, w, nu, vals, res);
+}
+
+void launch_assemble_facets(int n_g1, const int *g1_nodes, const int *g1_dofs, const int *g1_slots,
+                            const double *g1_len, const double *g1_normal, const int *dof_ux, const int *dof_uy,
+                            const double *w, const double *f, bool transpose, double *vals, double *res,
+                            cudaStream_t s) {
+    if (n_g1 <= 0) return;
+    const int blocks = cdiv((long long)n_g1 * 8, 128);
+    if (transpose)
+        assemble_facets_kernel<true><<<blocks, 128, 0, s>>>(n_g1, g1_nodes, g1_dofs, g1_slots, g1_len, g1_normal,
+                                                            dof_ux, dof_uy, w, f, vals, res);
+    else
+        assemble_facets_kernel<false><<<blocks, 128, 0, s>>>(n_g1, g1_nodes, g1_dofs, g1_slots, g1_len, g1_normal,
+                                                             dof_ux, dof_uy, w, f, vals, res);
+}
+
+void launch_dirichlet(int n_dir, const int *dir, const int *rowptr, const int *col, double *vals, double *res,
+                      const double *w, cudaStream_t s) {
+    if (n_dir <= 0) return;
+    dirichlet_kernel<<<cdiv((long long)n_dir * 32, 256), 256, 0, s>>>(n_dir, dir, rowptr, col, vals, res, w);
+}
+
+void launch_sumsq(int n, const double *v, double *out, double *scratch, unsigned *counter, cudaStream_t s) {
+    int blocks = cdiv(n, 256);
+    if (blocks > 296) blocks = 296;
+    sumsq_kernel<<<blocks, 256, 0, s>>>(n, v, out, scratch, counter);
+}
+
+void launch_axpy(int n, double a, const double *x, double *y, cudaStream_t s) {
+    axpy_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, a, x, y);
+}
+
+void launch_axpby(int n, double a, const double *x, double b, const double *y, double *out, cudaStream_t s) {
+    axpby_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, a, x, b, y, out);
+}
+
+void launch_velocity_nodal(int nn, const int *dof_ux, const int *dof_uy, const double *w, double *vel,
+                           cudaStream_t s) {
+    velocity_nodal_kernel<<<cdiv(nn, 256), 256, 0, s>>>(nn, dof_ux, dof_uy, w, reinterpret_cast<double2 *>(vel));
+}
+
+void launch_rhs_from_nodal(int nn, int nv, const int *dof_ux, const int *dof_uy, const int *dof_p,
+                           const double *bnode, double *b, cudaStream_t s) {
+    rhs_from_nodal_kernel<<<cdiv(nn, 256), 256, 0, s>>>(nn, nv, dof_ux, dof_uy, dof_p,
+                                                        reinterpret_cast<const double2 *>(bnode), b);
+}
+
+void launch_gradproj_rhs(int nc, int nv, const double *geom, const int *cell_nodes, const int *cell_dofs,
+                         const double *w, double *rhs4, cudaStream_t s) {
+    gradproj_rhs_kernel<<<cdiv(nc, 128), 128, 0, s>>>(nc, nv, geom, cell_nodes, cell_dofs, w, rhs4);
+}
+
+void launch_transpose4(int nv, const double *src4, double *dst, cudaStream_t s) {
+    transpose4_kernel<<<cdiv(nv, 256), 256, 0, s>>>(nv, src4, dst);
+}
+
+void launch_boundary_inner(int n_g1, const int *g1_nodes, const double *g1_len, const double *a, const double *b,
+                           double *out, cudaStream_t s) {
+    boundary_inner_kernel<<<1, 256, 0, s>>>(n_g1, g1_nodes, g1_len, reinterpret_cast<const double2 *>(a),
+                                            reinterpret_cast<const double2 *>(b), out);
+}
+
+void launch_field_norms(int nc, const double *geom, const int *cell_dofs, const double *w, double *out3,
+                        double *scratch, unsigned *counter, cudaStream_t s) {
+    field_norms_kernel<<<cdiv(nc, 128), 128, 0, s>>>(nc, geom, cell_dofs, w, out3, scratch, counter);
+}
+
+void launch_spmv_residual(int n, const int *rowptr, const int *col, const double *vals, const double *x,
+                          const double *b, double *r, cudaStream_t s) {
+    spmv_residual_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(n, rowptr, col, vals, x, b, r);
+}
+
+}  // namespace ocp

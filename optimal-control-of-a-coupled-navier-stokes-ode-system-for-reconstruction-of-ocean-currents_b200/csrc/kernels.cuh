@@ -1,0 +1,57 @@
+// Kernel launchers of libocp_b200 (sm_100a).  All launches go to the stream passed in.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ocp {
+
+struct DeviceTables {
+    int nc, nn, nv;
+    const double *geom;        // (nc,6)
+    const int *cell_nodes;     // (nc,6)
+    double ox, oy, ihx, ihy;
+    int nbx, nby;
+    const int *bin_ptr, *bin_cells;
+};
+
+// ---- buoy sweeps (buoy_kernels.cu) ---------------------------------------------------------------------------
+void launch_buoy_forward(const DeviceTables &t, const double *vel, const double *x0, int K, int nt, double h,
+                         double cx, double cy, double *x, double *u, int *cell, double *mask, uint8_t *parked,
+                         cudaStream_t s);
+// scratch: >= 2*max_blocks+2 doubles, counter: 1 unsigned (zero on entry, left zero)
+void launch_buoy_adjoint_scatter(const DeviceTables &t, const double *vel, const double *g, int K, int nt, double h,
+                                 double cx, double cy, const double *x, const double *u, const double *ud,
+                                 const double *mask, const uint8_t *parked, double *mu, double *acc,
+                                 double *scratch, unsigned *counter, cudaStream_t s);
+void launch_misfit(int K, int nt, double h, const double *u, const double *ud, double *out, double *scratch,
+                   unsigned *counter, cudaStream_t s);
+void launch_traj_transpose(const double *src, double *dst, int K, int nt, int to_time_major, cudaStream_t s);
+int buoy_max_blocks(int K);
+
+// ---- FE kernels (fe_kernels.cu) -------------------------------------------------------------------------------
+void launch_assemble_cells(int nc, const double *geom, const int *cell_dofs, const int *slots, const double *w,
+                           double nu, bool transpose, double *vals, double *res, cudaStream_t s);
+void launch_assemble_facets(int n_g1, const int *g1_nodes, const int *g1_dofs, const int *g1_slots,
+                            const double *g1_len, const double *g1_normal, const int *dof_ux, const int *dof_uy,
+                            const double *w, const double *f, bool transpose, double *vals, double *res,
+                            cudaStream_t s);
+// rows -> identity on the CSR values; res[d] = w[d] (w may be null -> res[d] = 0)
+void launch_dirichlet(int n_dir, const int *dir, const int *rowptr, const int *col, double *vals, double *res,
+                      const double *w, cudaStream_t s);
+void launch_sumsq(int n, const double *v, double *out, double *scratch, unsigned *counter, cudaStream_t s);
+void launch_axpy(int n, double a, const double *x, double *y, cudaStream_t s);           // y += a x
+void launch_axpby(int n, double a, const double *x, double b, const double *y, double *out, cudaStream_t s);
+void launch_velocity_nodal(int nn, const int *dof_ux, const int *dof_uy, const double *w, double *vel, cudaStream_t s);
+void launch_rhs_from_nodal(int nn, int nv, const int *dof_ux, const int *dof_uy, const int *dof_p,
+                           const double *bnode, double *b, cudaStream_t s);
+void launch_gradproj_rhs(int nc, int nv, const double *geom, const int *cell_nodes, const int *cell_dofs,
+                         const double *w, double *rhs4, cudaStream_t s);
+void launch_transpose4(int nv, const double *src4, double *dst, cudaStream_t s);         // (4,nv) -> (nv,4)
+void launch_boundary_inner(int n_g1, const int *g1_nodes, const double *g1_len, const double *a, const double *b,
+                           double *out, cudaStream_t s);
+void launch_field_norms(int nc, const double *geom, const int *cell_dofs, const double *w, double *out3,
+                        double *scratch, unsigned *counter, cudaStream_t s);
+void launch_spmv_residual(int n, const int *rowptr, const int *col, const double *vals, const double *x,
+                          const double *b, double *r, cudaStream_t s);                   // r = b - A x
+
+}  // namespace ocp

@@ -1,0 +1,150 @@
+"""Pins the CPU oracle to the reference's own FEniCS artefacts (KAT K1-K6 of SURVEY section 4)."""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle.buoy_oracle import BuoyOracle
+from oracle.fe_oracle import FEOracle
+
+
+@pytest.mark.parametrize("K", [2, 4, 6, 10, 100, 400])
+def test_K1_trajectories_match_fenics(K):
+    V = H.square32()
+    xr, ur = H.traj(K)
+    vel = V.velocity_nodal(H.field_for(K))
+    x, u, cell, mask, parked = BuoyOracle(V).forward(vel, xr[:, 0, :], H.NT, H.H, H.CENTER)
+    assert np.abs(x - xr).max() <= 4e-16 and np.abs(u - ur).max() <= 4e-16
+    assert mask.sum() == 0 and parked.sum() == 0 and (cell >= 0).all()
+    # the stored arrays satisfy the Euler recursion exactly, and so does the oracle
+    assert np.array_equal(x[:, 1:], x[:, :-1] + H.H * u[:, :-1])
+    assert np.array_equal(xr[:, 1:], xr[:, :-1] + H.H * ur[:, :-1])
+
+
+def test_K1_binned_search_equals_brute_force_definition():
+    V = H.square32()
+    xr, _ = H.traj(100)
+    vel = V.velocity_nodal(H.field_for(100))
+    a = BuoyOracle(V, brute=True).forward(vel, xr[:, 0, :], H.NT, H.H, H.CENTER)
+    b = BuoyOracle(V, brute=False).forward(vel, xr[:, 0, :], H.NT, H.H, H.CENTER)
+    for p, q in zip(a, b):
+        assert np.array_equal(p, q)
+
+
+def test_K2_twin_field_is_a_dirichlet_ns_solution():
+    """ud_construction_pipeline.py:95-106: nu=1, inflow (0.1,0) on x=0,2 (nodal P2), no-slip on y=0,2.
+    The stored 100/400/10000-buoy field is the second Newton iterate: its residual norm is 2.367e-9."""
+    V = H.square32()
+    O = FEOracle(V, 1.0)
+    w = H.field_for(100)
+    R = O.forward_residual(w, np.zeros((V.num_nodes, 2)))
+    xy = V.node_coords
+    bnd = (np.abs(xy[:, 0]) < 1e-12) | (np.abs(xy[:, 0] - 2) < 1e-12) | (np.abs(xy[:, 1]) < 1e-12) | (np.abs(xy[:, 1] - 2) < 1e-12)
+    free = np.ones(V.ndofs, bool)
+    free[V.dof_ux[bnd]] = False
+    free[V.dof_uy[bnd]] = False
+    # pressure pinned at x = 0 nodes
+    pin = np.abs(V.mesh.coords[:, 0]) < 1e-12
+    free[V.dof_p[pin]] = False
+    assert abs(np.linalg.norm(R[free]) - 2.367e-9) < 2e-11
+    inflow = (np.abs(xy[:, 0]) < 1e-12) | (np.abs(xy[:, 0] - 2) < 1e-12)
+    assert np.allclose(w[V.dof_ux[inflow]], 0.1, atol=1e-15) and np.allclose(w[V.dof_uy[inflow]], 0.0, atol=1e-15)
+
+
+def test_K3_newton_reproduces_u_bar():
+    V = H.square32()
+    O = FEOracle(V, 1.0)
+    ubar = H.fields()["u_bar"]
+    f, R = H.recover_control(V, O, ubar)
+    g1 = np.unique(V.g1_nodes)
+    other = np.ones(V.ndofs, bool)
+    other[V.dirichlet_dofs] = False
+    other[np.r_[V.dof_ux[g1], V.dof_uy[g1]]] = False
+    assert np.abs(R[other]).max() < 5e-14                      # stored state solves the discrete problem
+    w, its, hist = O.newton_solve(f, return_history=True)
+    assert its == 4
+    assert np.allclose(hist[:4], [1.8843123708, 0.13974755260, 1.0746543437e-3, 3.0903e-8], rtol=1e-4)
+    assert np.abs(w - ubar).max() < 1e-12
+
+
+def test_K4_cost_matches_J_array():
+    V = H.square32()
+    O = FEOracle(V, 1.0)
+    ubar = H.fields()["u_bar"]
+    xr, ud = H.traj(6)
+    x, u, *_ = BuoyOracle(V).forward(V.velocity_nodal(ubar), xr[:, 0, :], H.NT, H.H, H.CENTER)
+    J = O.cost(u, ud, H.q_nodal(V), H.H, 6e-6)
+    Jref = H.scalars()["u_bar_chapter_6.3.3"]["J_array"][0]
+    assert Jref == 0.0004978407145778218
+    assert abs(J - Jref) / Jref < 1e-13
+    assert abs(O.boundary_inner(H.q_nodal(V), H.q_nodal(V)) - 102.36563751185717) < 1e-10
+
+
+def test_K5_adjoint_chain_matches_stored_control_update():
+    V = H.square32()
+    O, B = FEOracle(V, 1.0), BuoyOracle(V)
+    ubar = H.fields()["u_bar"]
+    f, _ = H.recover_control(V, O, ubar)
+    xr, ud = H.traj(6)
+    P = H.OraclePipeline(V, 1.0, xr[:, 0, :].copy(), ud, 6e-6)
+    x, u, cell, mask, parked = P.primal(ubar)
+    mu = B.adjoint(O.project_gradient(ubar), x, u, ud, mask, H.H)
+    bn = B.point_sources(V.velocity_nodal(ubar), x, ud, mu, mask, H.H, H.CENTER)
+    z = V.velocity_nodal(O.adjoint_solve(ubar, O.rhs_from_nodal(bn)))
+    q, LR, alpha = H.q_nodal(V), 4.0, 6e-6
+    g1 = np.unique(V.g1_nodes)
+    z_implied = (q - (1 - LR * alpha) * f) / LR
+    assert abs(np.abs(z[g1]).max() - 1.7317e-3) < 1e-6
+    assert np.abs(z[g1] - z_implied[g1]).max() < 1e-12
+    gf = alpha * f - z
+    assert abs(np.sqrt(O.boundary_inner(gf, gf)) - 2.1821e-3) < 1e-6
+
+
+def test_diagnostics_match_reference_text_files():
+    V = H.square32()
+    O = FEOracle(V, 1.0)
+    sc = H.scalars()
+    div = float(sc["100_buoys"]["u_divergence.txt"].split("\n")[1].split()[0])
+    toks = sc["100_buoys"]["norms.txt"].split()
+    l2, h1 = float(toks[1]), float(toks[3])
+    w = H.field_for(100)
+    assert abs(O.divergence_norm(w) - div) < 1e-13
+    a, b = O.l2_h1_norms(w)
+    assert abs(a - l2) < 1e-13 and abs(b - h1) < 1e-13
+    divb = float(sc["u_bar_chapter_6.3.3"]["u_divergence.txt"].split("\n")[1].split()[0])
+    assert abs(O.divergence_norm(H.fields()["u_bar"]) - divb) < 1e-13
+
+
+def test_K6_gradient_check_values():
+    """PL defaults + 10_buoys (restatement-derived): J0, gradj and the centred FD plateau."""
+    V = H.square32()
+    xr, ud = H.traj(10)
+    from ocp_b200.pipeline import initial_control
+    f = initial_control(V, "PL")
+    P = H.OraclePipeline(V, 1.0, xr[:, 0, :].copy(), ud, 1e-5)
+    s = P.gradient_step(f)
+    assert s["its"] == 3
+    J0 = P.cost(s["u"], f)
+    df = np.full_like(f, 0.1)
+    gradj = P.O.boundary_inner(s["grad"], df)
+    assert abs(J0 - 0.025045819440590228) < 1e-12
+    assert abs(gradj - (-0.02603602981198921)) < 1e-11
+    hh = 1e-3
+    jr = P.cost(P.primal(P.O.newton_solve(f + hh * df))[1], f + hh * df)
+    jl = P.cost(P.primal(P.O.newton_solve(f - hh * df))[1], f - hh * df)
+    assert abs((jr - jl) / (2 * hh) - gradj) < 1e-7           # 2.1e-8 plateau
+
+
+def test_masked_and_parked_buoys_follow_the_reference_branches():
+    """OCP_dolfin.py:213-229: out-of-domain handling restated as data (mask, parked positions)."""
+    V = H.square32()
+    vel = np.zeros((V.num_nodes, 2))
+    vel[:, 0] = 1.0                                            # uniform flow to the right, leaves at x = 2
+    x0 = np.array([[1.9, 1.0], [2.5, 1.0], [0.5, 0.5], [2.0 - 198 * H.H - 1e-9, 0.7]])
+    x, u, cell, mask, parked = BuoyOracle(V, brute=True).forward(vel, x0, H.NT, H.H, H.CENTER)
+    assert mask.tolist() == [1.0, 1.0, 0.0, 0.0]
+    assert np.all(x[0] == H.CENTER) and np.all(x[1] == H.CENTER)
+    k = 21                                                     # 1.9 + 21*0.005 > 2: evaluation k = 21 fails
+    assert np.all(u[0, :k, 0] == 1.0) and u[0, k, 0] == 0.0 and u[0, k + 1, 0] == 1.0 and np.all(u[0, k + 2:] == 0)
+    assert np.all(u[1, 0] == 0) and np.all(u[1, 1] == [1.0, 0.0]) and np.all(u[1, 2:] == 0)   # started outside
+    assert parked.tolist() == [0, 0, 0, 1]
+    assert np.all(x[3, -1] == H.CENTER) and np.all(u[3, -1] == 0) and np.all(u[3, :-1, 0] == 1.0)
