@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Headline benchmark: full gradient-descent iterations of the 10 000-buoy square-mesh OCP (BASELINE.json cfg3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One *step* = one gradient-descent iteration of Pipeline_limits.py at its defaults (f = (0.1, 0), no line search):
+forward Navier-Stokes (Newton, 3 its), grad(u) projection, primal buoy ODE, backward sweep (adjoint ODE + point
+sources + misfit), [all-reduce], adjoint Navier-Stokes, gradient, control update, cost.  Every step restarts from
+q0 so that each step is exactly iteration 0 of the reference run (with LR = 5 the reference itself diverges
+after four iterations).  Each rank holds the reference's 100 x 100 buoy grid (weak scaling: K_global = 10 000 N,
+alpha = 1e-6 K_global, one NCCL all-reduce of [b | misfit | n_masked] per step).
+
+metric  = buoy-steps/s through full GD iterations = 3 sweeps x K_global x 200 samples per iteration / time
+          (the published 1500 s/iteration = 6.7e-4 it/s = 4.0e3 buoy-steps/s).
+value   = inputs resident in HBM; e2e = control / results cross the host boundary every step.
+roofline: the backward sweep (adjoint ODE + scatter + misfit), HBM-bound by design: 48 B per buoy-step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_PER_GPU = 10_000
+NT = 200
+PUBLISHED_BUOY_STEPS_PER_S = 4.0e3          # BASELINE.md section 1 (derived from 1500 s / iteration)
+METRIC = "gd_buoy_steps_per_sec"
+UNIT = "buoy-steps/s (3 sweeps x K x 200 per GD iteration)"
+
+
+def reference_grid():
+    """cfg3 start points: 100 x 100 grid on [0.1,0.4] x [0.25,1.75], x fastest."""
+    gx, gy = np.meshgrid(np.linspace(0.1, 0.4, 100), np.linspace(0.25, 1.75, 100))
+    return np.stack([gx.ravel(), gy.ravel()], 1)
+
+
+def golden_field():
+    f = np.load(os.path.join(ROOT, "tests", "golden", "fields.npz"))
+    return f["velocity_100"]                # identical to reference_runs/10000_buoys/paraview/velocity.h5
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def cpu_gd_iteration(P, f0, LR):
+    """One GD iteration with the oracle (CPU restatement of the reference's path)."""
+    s = P.gradient_step(f0)
+    f1 = f0 - LR * s["grad"]
+    return P.cost(s["u"], f1)
+
+
+def make_cpu_pipeline(K, threads):
+    import ocp_b200  # noqa: F401
+    from ocp_b200.fespace import TaylorHood
+    from ocp_b200.mesh import square_mesh
+    from ocp_b200.pipeline import initial_control
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    V = TaylorHood(square_mesh(32))
+    x0 = reference_grid()[:K]
+    from oracle.buoy_oracle import BuoyOracle
+    B = BuoyOracle(V)
+    B.set_threads(threads)
+    _, ud, *_ = B.forward(V.velocity_nodal(golden_field()), x0, NT, 0.005, [1.0, 1.0])
+    P = helpers.OraclePipeline(V, 1.0, x0, ud, 1e-6 * K)
+    P.B.set_threads(threads)
+    return P, initial_control(V, "PL")
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's CPU algorithm for the same step on the host cores.  FEniCS is not
+    installable here, so this is the oracle port: per-buoy loops in C over all host threads, FE assembly in NumPy,
+    SuperLU (SciPy) for the solves - the same workload (10 000 buoys, full GD iteration)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    P, f0 = make_cpu_pipeline(K_PER_GPU, threads)
+    for _ in range(min(args.warmup, 1)):
+        cpu_gd_iteration(P, f0, 5.0)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_gd_iteration(P, f0, 5.0)
+    dt = (time.perf_counter() - t0) / steps
+    val = 3 * K_PER_GPU * NT / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": val / PUBLISHED_BUOY_STEPS_PER_S, "dtype": "f64", "data": "synthetic",
+        "gd_iters_per_sec": 1.0 / dt,
+        "config": {"workload": "cfg3 square N=32 OCP, 10000 buoys, Pipeline_limits defaults, GD iteration 0",
+                   "K": K_PER_GPU, "nt": NT, "mesh": "square 32x32", "ndofs": 9539},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{steps} full GD iterations of the whole 10000-buoy workload (no sub-sampling); "
+                                   "buoy loops on all host threads, FE solves single-threaded SuperLU"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ocp_b200  # noqa: F401
+    from ocp_b200 import capi
+    from ocp_b200.fespace import TaylorHood
+    from ocp_b200.mesh import square_mesh
+    from ocp_b200.pipeline import OCP, Parameters, initial_control
+    from ocp_b200.sharding import init_from_env
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
+    group, rank, world, local = init_from_env("nccl")
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    V = TaylorHood(square_mesh(32))
+    P = Parameters()
+    x0 = reference_grid()
+    K = x0.shape[0]
+    f0 = initial_control(V, "PL")
+    LR = 5.0
+    # u_d regenerated from the stored 10000_buoys field with the primal kernel itself
+    ocp = OCP(V, P, x0, np.zeros((K, NT, 2)), device=dev, group=group)
+    d_field = torch.from_numpy(golden_field()).to(dev)
+    ocp._primal(d_field, ocp.d_x, ocp.d_u, ocp.d_mask)
+    ocp.d_ud.copy_(ocp.d_u)
+    ud_host = ocp._to_reference_layout(ocp.d_ud)
+    ctx = ocp.ctx
+    ctx.set_observations_host(x0, ud_host)
+    nn = V.num_nodes
+    d_f0 = torch.from_numpy(f0).to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, device=dev, dtype=torch.float64)     # > 126 MB L2
+
+    def barrier():
+        if group is not None:
+            dist.barrier(group=group)
+        torch.cuda.synchronize()
+
+    def step_resident():
+        flush.zero_()
+        ocp.d_f.copy_(d_f0)
+        ocp.gradient_step(ocp.d_f)
+        ocp.d_f.add_(ocp.d_grad, alpha=-LR)
+        return ocp._cost_from_acc(ocp.d_f)
+
+    h_f = torch.from_numpy(f0.copy()).pin_memory()
+    h_grad = torch.empty((nn, 2), dtype=torch.float64).pin_memory()
+    h_sc = torch.empty(4, dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        """Host control in, host gradient / cost / mask count out, through the public Python API."""
+        flush.zero_()
+        ocp.d_f.copy_(h_f, non_blocking=True)                     # H2D: control
+        ocp.gradient_step(ocp.d_f)
+        ocp.ctx.boundary_inner(ocp.d_f, ocp.d_f, ocp.d_sc)
+        h_grad.copy_(ocp.d_grad, non_blocking=True)               # D2H: gradient field
+        h_sc[:2].copy_(ocp.d_acc[2 * nn:], non_blocking=True)     # D2H: misfit, n_masked
+        h_sc[2:3].copy_(ocp.d_sc[:1], non_blocking=True)
+        torch.cuda.synchronize()
+        return float(h_sc[0] + 0.5 * ocp.alpha * h_sc[2])     # J(u, f) at the incoming control
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if group is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=group)
+        return float(ms.item()) / steps, out
+
+    warm = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.reset_solver_stats()
+    n_launch0 = capi.launch_count()
+    ms_step, J = timed(step_resident, args.steps, warm)
+    launches = (capi.launch_count() - n_launch0) / (args.steps + warm)
+    stats = ctx.solver_stats()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, J2 = timed(step_e2e, args.steps, 1)
+
+    # C-ABI host-buffer call (N=1 only: the C entry point has no collective inside)
+    ms_cabi = None
+    if world == 1:
+        out = (np.empty(V.ndofs), np.empty(V.ndofs), np.zeros(K), np.zeros(4))
+        ms_cabi, _ = timed(lambda: (flush.zero_(), ctx.gradient_host(f0, out))[1], args.steps, 1)
+
+    # ---- dominant hand-written kernel, timed live with CUDA events: the backward sweep
+    def back():
+        ocp.d_acc.zero_()
+        ctx.buoy_adjoint_scatter(ocp.d_vel, ocp.d_g, K, ocp.d_x, ocp.d_u, ocp.d_ud, ocp.d_mask, ocp.d_parked, None,
+                                 ocp.d_acc)
+
+    def kernel_ms(fn, reps=20):
+        fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / reps
+
+    ms_back = kernel_ms(back)
+    ms_fwd = kernel_ms(lambda: ocp._primal(ocp.d_w, ocp.d_x, ocp.d_u, ocp.d_mask))
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    bytes_back = 48.0 * K * NT
+    ach = bytes_back / (ms_back * 1e-3) / 1e9
+
+    # ---- the same kernels at sweep size (cfg5-like, 2^20 buoys on the same mesh) where they are bandwidth-relevant
+    sweep = None
+    if rank == 0 and not args.no_sweep:
+        Ks = 1 << 20
+        rng = np.random.default_rng(0)
+        xs = np.stack([rng.uniform(0.1, 1.9, Ks), rng.uniform(0.1, 1.9, Ks)], 1)
+        big = OCP(V, P, xs, np.zeros((Ks, NT, 2)), device=dev)
+        big.ctx.project_grad(ocp.d_w, big.d_g)
+        big._primal(ocp.d_w, big.d_x, big.d_u, big.d_mask)
+        big.d_ud.copy_(1.1 * big.d_u)
+
+        def bback():
+            big.d_acc.zero_()
+            big.ctx.buoy_adjoint_scatter(big.d_vel, big.d_g, Ks, big.d_x, big.d_u, big.d_ud, big.d_mask,
+                                         big.d_parked, None, big.d_acc)
+        mb = kernel_ms(bback, 5)
+        mf = kernel_ms(lambda: big._primal(ocp.d_w, big.d_x, big.d_u, big.d_mask), 5)
+        sweep = {"K": Ks, "backward_ms": mb, "forward_ms": mf,
+                 "backward_gbs": 48.0 * Ks * NT / (mb * 1e-3) / 1e9, "forward_gbs": 32.0 * Ks * NT / (mf * 1e-3) / 1e9,
+                 "backward_frac_of_peak": 48.0 * Ks * NT / (mb * 1e-3) / 1e9 / peak,
+                 "forward_frac_of_peak": 32.0 * Ks * NT / (mf * 1e-3) / 1e9 / peak,
+                 "buoy_steps_per_sec_fwd_plus_bwd": 2.0 * Ks * NT / ((mb + mf) * 1e-3)}
+        big.close()
+        del big
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only): the oracle on the full workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        Pc, f0c = make_cpu_pipeline(K_PER_GPU, threads)
+        cpu_gd_iteration(Pc, f0c, LR)
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            Jc = cpu_gd_iteration(Pc, f0c, LR)
+        dtc = (time.perf_counter() - t0) / reps
+        cpu = {"value": 3 * K_PER_GPU * NT / dtc, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{reps} full GD iterations of the whole 10000-buoy workload (no sub-sampling)",
+               "ms_per_step": dtc * 1e3, "J": Jc, "J_gpu": J, "J_rel_diff": abs(Jc - J) / abs(Jc)}
+
+    if rank == 0:
+        Kg = K * world
+        units = 3.0 * Kg * NT
+        val = units / (ms_step * 1e-3)
+        line = {
+            "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": val / PUBLISHED_BUOY_STEPS_PER_S, "dtype": "f64", "data": "synthetic",
+            "gd_iters_per_sec": 1e3 / ms_step,
+            "config": {"workload": "cfg3 square N=32 OCP, 10000 buoys per GPU, Pipeline_limits defaults, GD iteration 0",
+                       "K_per_gpu": K, "K_global": Kg, "nt": NT, "mesh": "square 32x32", "ndofs": V.ndofs,
+                       "nnz": int(V.csr_col.size), "newton_its": ocp.last_newton_its,
+                       "parallelism": f"buoys sharded x{world}, replicated FE solve, 1 all-reduce/step",
+                       "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
+            "e2e": {"value": units / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(h_f.numel() * 8), "d2h_bytes_per_step": int(h_grad.numel() * 8 + 24),
+                    "api": "OCP.gradient_step via pinned host control / gradient buffers",
+                    "cabi_host_call_ms": ms_cabi},
+            "gpu_launches": round(launches, 1),
+            "clocks": clocks,
+            "line_items_ms_per_step": {
+                "assembly": stats["assemble_ms"] / (args.steps + warm),
+                "sparse_lu_refactor": stats["factor_ms"] / (args.steps + warm),
+                "sparse_lu_solve": stats["solve_ms"] / (args.steps + warm),
+                "buoy_forward_kernel": ms_fwd, "buoy_backward_kernel": ms_back,
+                "n_factor_per_step": stats["n_factor"] / (args.steps + warm),
+                "n_solve_per_step": stats["n_solve"] / (args.steps + warm),
+                "one_time_symbolic_analysis_ms": stats["analyse_ms"]},
+            "roofline": {"bound": "hbm", "kernel": "buoy_adjoint_scatter_kernel", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_back,
+                         "note": "in-step launch at K=10000 is latency-bound (64 MB of trajectories); "
+                                 "see roofline_sweep for the same kernel at 2^20 buoys"},
+            "roofline_sweep": sweep,
+            "cpu_baseline": cpu,
+            "J_after_update": J, "J_at_q0_e2e": J2,
+        }
+        print(json.dumps(line), flush=True)
+    ocp.close()
+    if group is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 2^20-buoy kernel sweep")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args, int(os.environ.get("RANK", "0")))
+        return
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -164,11 +164,17 @@ int ocp_solve_primal_ode_host(ocp_ctx *ctx, const double *h_w, const double *h_x
 /* solve_adjoint_ode(wSol, grad_u, x, buoy_mask, u_values_array) -> mu (K,nt,2); h_g is (nv,4). */
 int ocp_solve_adjoint_ode_host(ocp_ctx *ctx, const double *h_g, const double *h_x, const double *h_u,
                                const double *h_ud, const double *h_mask, int K, double *h_mu);
-/* One full gradient evaluation for control h_f (nn,2) and K buoys (h_x0 (K,2), h_ud (K,nt,2)):
- * forward solve, projection, primal ODE, adjoint sweep, adjoint solve.  Outputs: h_w (ndofs), h_z (ndofs),
- * h_mask (K), h_scalars[0..3] = misfit, int_G1 |f|^2, n_masked, newton iterations. */
-int ocp_gradient_host(ocp_ctx *ctx, const double *h_f, const double *h_x0, const double *h_ud, int K,
-                      double *h_w, double *h_z, double *h_mask, double *h_scalars);
+/* The reference loads u_d / x_0 once into module globals (OCP_dolfin.py:176-183); this uploads them once:
+ * h_x0 (K,2), h_ud (K,nt,2) in the reference layout. */
+int ocp_set_observations_host(ocp_ctx *ctx, const double *h_x0, const double *h_ud, int K);
+/* One full gradient evaluation for control h_f (nn,2) on the resident observations: forward solve, projection,
+ * primal ODE, adjoint sweep, adjoint solve (the "outer" block OCP_dolfin.py:313-371).  Outputs: h_w (ndofs),
+ * h_z (ndofs), h_mask (K), h_scalars[0..3] = misfit, int_G1 |f|^2, n_masked, newton iterations. */
+int ocp_gradient_host(ocp_ctx *ctx, const double *h_f, double *h_w, double *h_z, double *h_mask,
+                      double *h_scalars);
+
+/* Number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+long long ocp_launch_count(void);
 
 /* ---- one-time host symbolic analysis (exported for CPU-side tests of the ordering / pivoting) --------------
  * LU of the CSR matrix with nested-dissection column order and threshold partial pivoting:

@@ -25,7 +25,8 @@ SYMBOLS = [
     "ocp_forward_solve", "ocp_assemble_forward", "ocp_assemble_adjoint", "ocp_project_grad",
     "ocp_velocity_nodal", "ocp_buoy_forward", "ocp_buoy_adjoint_scatter", "ocp_misfit",
     "ocp_adjoint_solve", "ocp_boundary_inner", "ocp_nodal_axpby", "ocp_field_norms", "ocp_traj_transpose",
-    "ocp_solve_primal_ode_host", "ocp_solve_adjoint_ode_host", "ocp_gradient_host",
+    "ocp_solve_primal_ode_host", "ocp_solve_adjoint_ode_host", "ocp_set_observations_host", "ocp_gradient_host",
+    "ocp_launch_count",
     "ocp_host_lu_probe", "ocp_selftest_cell_matrix", "ocp_selftest_facet_matrix",
 ]
 
@@ -70,6 +71,7 @@ def load_library() -> C.CDLL:
         lib.ocp_destroy.argtypes = [C.c_void_p]
         lib.ocp_destroy.restype = None
         lib.ocp_host_lu_probe.restype = C.c_int64
+        lib.ocp_launch_count.restype = C.c_longlong
         lib.ocp_set_viscosity.argtypes = [C.c_void_p, C.c_double]
         lib.ocp_set_viscosity.restype = None
         lib.ocp_get_solver_stats.restype = None
@@ -237,16 +239,25 @@ class Context:
                     "ocp_solve_adjoint_ode_host")
         return mu
 
-    def gradient_host(self, f, x0, ud):
-        K = x0.shape[0]
-        f, x0, ud = (np.ascontiguousarray(a, np.float64) for a in (f, x0, ud))
-        w = np.empty(self.ndofs)
-        z = np.empty(self.ndofs)
-        mask = np.zeros(K)
-        sc = np.zeros(4)
-        self._check(self.lib.ocp_gradient_host(self._h, _hp(f), _hp(x0), _hp(ud), K, _hp(w), _hp(z), _hp(mask),
-                                               _hp(sc)), "ocp_gradient_host")
+    def set_observations_host(self, x0: np.ndarray, ud: np.ndarray):
+        x0, ud = np.ascontiguousarray(x0, np.float64), np.ascontiguousarray(ud, np.float64)
+        self._obs_K = x0.shape[0]
+        self._check(self.lib.ocp_set_observations_host(self._h, _hp(x0), _hp(ud), self._obs_K),
+                    "ocp_set_observations_host")
+
+    def gradient_host(self, f, out=None):
+        """numpy control (nn,2) in -> w, z, mask (numpy) and scalars; `out` lets the caller reuse (pinned) buffers."""
+        f = np.ascontiguousarray(f, np.float64)
+        if out is None:
+            out = (np.empty(self.ndofs), np.empty(self.ndofs), np.zeros(self._obs_K), np.zeros(4))
+        w, z, mask, sc = out
+        self._check(self.lib.ocp_gradient_host(self._h, _hp(f), _hp(w), _hp(z), _hp(mask), _hp(sc)),
+                    "ocp_gradient_host")
         return w, z, mask, dict(misfit=sc[0], f_norm2=sc[1], n_masked=int(sc[2]), newton_its=int(sc[3]))
+
+
+def launch_count() -> int:
+    return int(load_library().ocp_launch_count())
 
 
 # -- element-level self-tests and host analysis (no GPU needed) ------------------------------------------------

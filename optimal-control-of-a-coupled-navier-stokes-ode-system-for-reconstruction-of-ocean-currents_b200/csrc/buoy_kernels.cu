@@ -315,6 +315,7 @@ int buoy_max_blocks(int K) { return (K + kBuoyThreads - 1) / kBuoyThreads; }
 void launch_buoy_forward(const DeviceTables &t, const double *vel, const double *x0, int K, int nt, double h,
                          double cx, double cy, double *x, double *u, int *cell, double *mask, uint8_t *parked,
                          cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (K <= 0) return;
     buoy_forward_kernel<<<buoy_max_blocks(K), kBuoyThreads, 0, s>>>(
         t, reinterpret_cast<const double2 *>(vel), reinterpret_cast<const double2 *>(x0), K, nt, h, cx, cy,
@@ -325,6 +326,7 @@ void launch_buoy_adjoint_scatter(const DeviceTables &t, const double *vel, const
                                  double cx, double cy, const double *x, const double *u, const double *ud,
                                  const double *mask, const uint8_t *parked, double *mu, double *acc,
                                  double *scratch, unsigned *counter, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (K <= 0) return;
     buoy_adjoint_scatter_kernel<<<buoy_max_blocks(K), kBuoyThreads, 0, s>>>(
         t, reinterpret_cast<const double2 *>(vel), reinterpret_cast<const double2 *>(g), K, nt, h, cx, cy,
@@ -334,6 +336,7 @@ void launch_buoy_adjoint_scatter(const DeviceTables &t, const double *vel, const
 
 void launch_misfit(int K, int nt, double h, const double *u, const double *ud, double *out, double *scratch,
                    unsigned *counter, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     const size_t n = (size_t)K * nt;
     if (n == 0) return;
     int blocks = (int)((n + 255) / 256);
@@ -343,6 +346,7 @@ void launch_misfit(int K, int nt, double h, const double *u, const double *ud, d
 }
 
 void launch_traj_transpose(const double *src, double *dst, int K, int nt, int to_time_major, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (K <= 0) return;
     const int rows = to_time_major ? K : nt, cols = to_time_major ? nt : K;
     dim3 grid((K + 31) / 32, (nt + 31) / 32), block(32, 8);

@@ -45,6 +45,9 @@ struct ocp_ctx {
     size_t stage_len[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint8_t *d_parked = nullptr;
     size_t parked_len = 0;
+    // resident observations (the reference's module globals u_d, xsarr, ysarr; OCP_dolfin.py:176-183)
+    double *d_obs_x0 = nullptr, *d_obs_ud = nullptr;
+    int obs_K = 0;
     SparseLU lu_fwd, lu_adj, lu_mass;
     bool mass_factored = false;
     int adj_refine = 1;
@@ -334,7 +337,7 @@ void ocp_destroy(ocp_ctx *c) {
                     c->d_dof_ux, c->d_dof_uy, c->d_dof_p, c->d_rowptr, c->d_col, c->d_dir, c->d_g1_nodes,
                     c->d_g1_dofs, c->d_g1_slots, c->d_bin_ptr, c->d_bin_cells, c->d_m_rowptr, c->d_m_col,
                     c->d_m_vals, c->d_vals, c->d_res, c->d_rhs, c->d_tmp, c->d_rhs4, c->d_scalar, c->d_scratch,
-                    c->d_counter, c->d_parked};
+                    c->d_counter, c->d_parked, c->d_obs_x0, c->d_obs_ud};
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < 8; ++i) cudaFree(c->d_stage[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -612,37 +615,58 @@ int ocp_solve_adjoint_ode_host(ocp_ctx *c, const double *h_g, const double *h_x,
     return OCP_OK;
 }
 
-int ocp_gradient_host(ocp_ctx *c, const double *h_f, const double *h_x0, const double *h_ud, int K, double *h_w,
-                      double *h_z, double *h_mask, double *h_scalars) {
-    if (!c || !h_f || !h_x0 || !h_ud || !h_w || !h_z || !h_mask || !h_scalars || K < 0) return OCP_ERR_INVALID;
+int ocp_set_observations_host(ocp_ctx *c, const double *h_x0, const double *h_ud, int K) {
+    if (!c || !h_x0 || !h_ud || K <= 0) return OCP_ERR_INVALID;
     cudaStream_t s = c->stream;
     const size_t tr = (size_t)K * c->nt * 2;
-    const size_t nacc = 2 * (size_t)c->nn + 2;
-    const int n = c->ndofs;
     int rc;
-    if ((rc = ensure_stage(c, 0, 2 * (size_t)n + 4 + 4 * (size_t)c->nv)) || (rc = ensure_stage(c, 1, nacc + 2 * (size_t)c->nn)) ||
-        (rc = ensure_stage(c, 2, tr)) || (rc = ensure_stage(c, 3, tr)) || (rc = ensure_stage(c, 4, tr)) ||
-        (rc = ensure_stage(c, 5, tr)) || (rc = ensure_stage(c, 6, 3 * (size_t)K + 4)) ||
+    if ((rc = ensure_stage(c, 5, tr))) return rc;
+    cudaFree(c->d_obs_x0);
+    cudaFree(c->d_obs_ud);
+    c->d_obs_x0 = c->d_obs_ud = nullptr;
+    c->obs_K = 0;
+    CUDA_OK(c, cudaMalloc((void **)&c->d_obs_x0, sizeof(double) * 2 * K));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_obs_ud, sizeof(double) * tr));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_obs_x0, h_x0, sizeof(double) * 2 * K, cudaMemcpyHostToDevice, s));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_stage[5], h_ud, sizeof(double) * tr, cudaMemcpyHostToDevice, s));
+    launch_traj_transpose(c->d_stage[5], c->d_obs_ud, K, c->nt, 1, s);
+    CUDA_OK(c, cudaStreamSynchronize(s));
+    CUDA_OK(c, cudaGetLastError());
+    c->obs_K = K;
+    return OCP_OK;
+}
+
+int ocp_gradient_host(ocp_ctx *c, const double *h_f, double *h_w, double *h_z, double *h_mask, double *h_scalars) {
+    if (!c || !h_f || !h_w || !h_z || !h_mask || !h_scalars) return OCP_ERR_INVALID;
+    if (c->obs_K <= 0) {
+        c->err = "ocp_gradient_host: call ocp_set_observations_host first";
+        return OCP_ERR_INVALID;
+    }
+    cudaStream_t s = c->stream;
+    const int K = c->obs_K, n = c->ndofs;
+    const size_t tr = (size_t)K * c->nt * 2;
+    const size_t nacc = 2 * (size_t)c->nn + 2;
+    const size_t npad = ((size_t)n + 1) & ~(size_t)1;   // keep 16-byte alignment of the packed sub-buffers
+    int rc;
+    if ((rc = ensure_stage(c, 0, 2 * npad + 4 * (size_t)c->nv)) || (rc = ensure_stage(c, 1, nacc + 2 * (size_t)c->nn)) ||
+        (rc = ensure_stage(c, 2, tr)) || (rc = ensure_stage(c, 3, tr)) || (rc = ensure_stage(c, 6, (size_t)K + 2)) ||
         (rc = ensure_stage(c, 7, 2 * (size_t)c->nn)) || (rc = ensure_parked(c, (size_t)K + 1)))
         return rc;
-    const size_t npad = ((size_t)n + 1) & ~(size_t)1, kpad = ((size_t)K + 1) & ~(size_t)1;   // keep 16-byte alignment
     double *d_w = c->d_stage[0], *d_z = d_w + npad, *d_g = d_z + npad;
     double *d_acc = c->d_stage[1], *d_f = d_acc + nacc;
-    double *d_x = c->d_stage[2], *d_u = c->d_stage[3], *d_ud = c->d_stage[4], *d_t = c->d_stage[5];
-    double *d_mask = c->d_stage[6], *d_x0 = d_mask + kpad;
-    double *d_vel = c->d_stage[7];
+    double *d_x = c->d_stage[2], *d_u = c->d_stage[3];
+    double *d_mask = c->d_stage[6], *d_vel = c->d_stage[7];
     CUDA_OK(c, cudaMemcpyAsync(d_f, h_f, sizeof(double) * 2 * c->nn, cudaMemcpyHostToDevice, s));
-    CUDA_OK(c, cudaMemcpyAsync(d_x0, h_x0, sizeof(double) * 2 * K, cudaMemcpyHostToDevice, s));
-    CUDA_OK(c, cudaMemcpyAsync(d_t, h_ud, sizeof(double) * tr, cudaMemcpyHostToDevice, s));
-    launch_traj_transpose(d_t, d_ud, K, c->nt, 1, s);
     CUDA_OK(c, cudaMemsetAsync(d_mask, 0, sizeof(double) * K, s));
     CUDA_OK(c, cudaMemsetAsync(d_acc, 0, sizeof(double) * nacc, s));
     int its = 0;
     if ((rc = ocp_forward_solve(c, d_f, d_w, 1, &its, nullptr))) return rc;
     if ((rc = ocp_project_grad(c, d_w, d_g))) return rc;
     launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, d_w, d_vel, s);
-    launch_buoy_forward(c->tab, d_vel, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, nullptr, d_mask, c->d_parked, s);
-    if ((rc = ocp_buoy_adjoint_scatter(c, d_vel, d_g, K, d_x, d_u, d_ud, d_mask, c->d_parked, nullptr, d_acc))) return rc;
+    launch_buoy_forward(c->tab, d_vel, c->d_obs_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, nullptr, d_mask,
+                        c->d_parked, s);
+    if ((rc = ocp_buoy_adjoint_scatter(c, d_vel, d_g, K, d_x, d_u, c->d_obs_ud, d_mask, c->d_parked, nullptr, d_acc)))
+        return rc;
     if ((rc = ocp_adjoint_solve(c, d_w, d_acc, d_z))) return rc;
     launch_boundary_inner(c->n_g1, c->d_g1_nodes, c->d_g1_len, d_f, d_f, c->d_scalar, s);
     CUDA_OK(c, cudaMemcpyAsync(h_w, d_w, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
@@ -658,6 +682,8 @@ int ocp_gradient_host(ocp_ctx *c, const double *h_f, const double *h_x0, const d
     CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
 }
+
+long long ocp_launch_count(void) { return ocp::g_launch_count.load(); }
 
 // ---- element-level self-tests: the same __host__ __device__ arithmetic the kernels run, evaluated on the
 // host for ONE element so that CPU-only unit tests can check it against the oracle.  Not a compute path.

@@ -6,6 +6,8 @@
 
 namespace ocp {
 
+std::atomic<long long> g_launch_count{0};
+
 namespace {
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -309,6 +311,7 @@ inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 void launch_assemble_cells(int nc, const double *geom, const int *cell_dofs, const int *slots, const double *w,
                            double nu, bool transpose, double *vals, double *res, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     const int blocks = cdiv((long long)nc * 16, 256);
     if (transpose)
         assemble_cells_kernel<true><<<blocks, 256, 0, s>>>(nc, geom, cell_dofs, slots, w, nu, vals, res);
@@ -320,6 +323,7 @@ void launch_assemble_facets(int n_g1, const int *g1_nodes, const int *g1_dofs, c
                             const double *g1_len, const double *g1_normal, const int *dof_ux, const int *dof_uy,
                             const double *w, const double *f, bool transpose, double *vals, double *res,
                             cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (n_g1 <= 0) return;
     const int blocks = cdiv((long long)n_g1 * 8, 128);
     if (transpose)
@@ -332,57 +336,68 @@ void launch_assemble_facets(int n_g1, const int *g1_nodes, const int *g1_dofs, c
 
 void launch_dirichlet(int n_dir, const int *dir, const int *rowptr, const int *col, double *vals, double *res,
                       const double *w, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (n_dir <= 0) return;
     dirichlet_kernel<<<cdiv((long long)n_dir * 32, 256), 256, 0, s>>>(n_dir, dir, rowptr, col, vals, res, w);
 }
 
 void launch_sumsq(int n, const double *v, double *out, double *scratch, unsigned *counter, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     int blocks = cdiv(n, 256);
     if (blocks > 296) blocks = 296;
     sumsq_kernel<<<blocks, 256, 0, s>>>(n, v, out, scratch, counter);
 }
 
 void launch_axpy(int n, double a, const double *x, double *y, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     axpy_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, a, x, y);
 }
 
 void launch_axpby(int n, double a, const double *x, double b, const double *y, double *out, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     axpby_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, a, x, b, y, out);
 }
 
 void launch_velocity_nodal(int nn, const int *dof_ux, const int *dof_uy, const double *w, double *vel,
                            cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     velocity_nodal_kernel<<<cdiv(nn, 256), 256, 0, s>>>(nn, dof_ux, dof_uy, w, reinterpret_cast<double2 *>(vel));
 }
 
 void launch_rhs_from_nodal(int nn, int nv, const int *dof_ux, const int *dof_uy, const int *dof_p,
                            const double *bnode, double *b, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     rhs_from_nodal_kernel<<<cdiv(nn, 256), 256, 0, s>>>(nn, nv, dof_ux, dof_uy, dof_p,
                                                         reinterpret_cast<const double2 *>(bnode), b);
 }
 
 void launch_gradproj_rhs(int nc, int nv, const double *geom, const int *cell_nodes, const int *cell_dofs,
                          const double *w, double *rhs4, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     gradproj_rhs_kernel<<<cdiv(nc, 128), 128, 0, s>>>(nc, nv, geom, cell_nodes, cell_dofs, w, rhs4);
 }
 
 void launch_transpose4(int nv, const double *src4, double *dst, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     transpose4_kernel<<<cdiv(nv, 256), 256, 0, s>>>(nv, src4, dst);
 }
 
 void launch_boundary_inner(int n_g1, const int *g1_nodes, const double *g1_len, const double *a, const double *b,
                            double *out, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     boundary_inner_kernel<<<1, 256, 0, s>>>(n_g1, g1_nodes, g1_len, reinterpret_cast<const double2 *>(a),
                                             reinterpret_cast<const double2 *>(b), out);
 }
 
 void launch_field_norms(int nc, const double *geom, const int *cell_dofs, const double *w, double *out3,
                         double *scratch, unsigned *counter, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     field_norms_kernel<<<cdiv(nc, 128), 128, 0, s>>>(nc, geom, cell_dofs, w, out3, scratch, counter);
 }
 
 void launch_spmv_residual(int n, const int *rowptr, const int *col, const double *vals, const double *x,
                           const double *b, double *r, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     spmv_residual_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(n, rowptr, col, vals, x, b, r);
 }
 

@@ -1,9 +1,14 @@
 // Kernel launchers of libocp_b200 (sm_100a).  All launches go to the stream passed in.
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <cstdint>
 
 namespace ocp {
+
+// process-wide count of kernels launched by this library (reported by bench.py as gpu_launches)
+extern std::atomic<long long> g_launch_count;
 
 struct DeviceTables {
     int nc, nn, nv;

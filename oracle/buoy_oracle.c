@@ -29,7 +29,24 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* The reference loops are serial (no MPI/threads anywhere in the pipelines).  For the timed CPU baseline the
+ * outer per-buoy loops may additionally be spread over host threads (buoys are independent); nthreads = 1
+ * keeps the reference's loop structure. */
+static int g_threads = 1;
+void oracle_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 
 #define LOCATE_TOL 1.0e-14
 #define LOCATE_MARGIN 1.0e-9
@@ -110,6 +127,7 @@ static int eval_velocity(const Tables *t, const double *vel, double x, double y,
  * parked: (K) uint8, 1 when only the last point left the domain (OCP_dolfin.py:226-229). */
 void oracle_buoy_forward(const Tables *t, const double *vel, int K, int nt, double h, const double *x0,
                          const double *center, double *x, double *u, int32_t *cell, double *mask, uint8_t *parked) {
+#pragma omp parallel for schedule(dynamic, 64) num_threads(g_threads)
     for (int b = 0; b < K; ++b) {
         double *xb = x + (size_t)b * nt * 2, *ub = u + (size_t)b * nt * 2;
         int32_t *cb = cell + (size_t)b * nt;
@@ -173,6 +191,7 @@ static int eval_grad(const Tables *t, const double *g, double x, double y, int h
 void oracle_buoy_adjoint(const Tables *t, const double *g, int K, int nt, double h, const double *x, const double *u,
                          const double *ud, const double *mask, double *mu) {
     memset(mu, 0, sizeof(double) * (size_t)K * nt * 2);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(g_threads)
     for (int b = 0; b < K; ++b) {
         if (mask[b] != 0.0) continue;
         const double *xb = x + (size_t)b * nt * 2, *ub = u + (size_t)b * nt * 2, *db = ud + (size_t)b * nt * 2;
@@ -192,10 +211,10 @@ void oracle_buoy_adjoint(const Tables *t, const double *g, int K, int nt, double
 }
 
 /* PointSource loop, OCP_dolfin.py:353-366: bnode (nn,2) += gamma_c * phi_i(point).  bnode is NOT cleared. */
-void oracle_point_sources(const Tables *t, const double *vel, int K, int nt, double h, const double *x,
-                          const double *ud, const double *mu, const double *mask, const double *center,
-                          double *bnode) {
-    for (int b = 0; b < K; ++b) {
+static void point_sources_range(const Tables *t, const double *vel, int b0, int b1, int nt, double h,
+                                const double *x, const double *ud, const double *mu, const double *mask,
+                                const double *center, double *bnode) {
+    for (int b = b0; b < b1; ++b) {
         if (mask[b] != 0.0) continue;
         int hint = -1;
         for (int k = 0; k < nt; ++k) {
@@ -221,6 +240,27 @@ void oracle_point_sources(const Tables *t, const double *vel, int K, int nt, dou
             }
         }
     }
+}
+
+void oracle_point_sources(const Tables *t, const double *vel, int K, int nt, double h, const double *x,
+                          const double *ud, const double *mu, const double *mask, const double *center,
+                          double *bnode) {
+    if (g_threads <= 1) {
+        point_sources_range(t, vel, 0, K, nt, h, x, ud, mu, mask, center, bnode);
+        return;
+    }
+    /* threaded baseline: private accumulators, summed in thread order */
+    const int nth = g_threads;
+    const size_t len = 2 * (size_t)t->nn;
+    double *priv = (double *)calloc(len * nth, sizeof(double));
+#pragma omp parallel for schedule(static) num_threads(nth)
+    for (int th = 0; th < nth; ++th) {
+        int b0 = (int)((long long)K * th / nth), b1 = (int)((long long)K * (th + 1) / nth);
+        point_sources_range(t, vel, b0, b1, nt, h, x, ud, mu, mask, center, priv + len * th);
+    }
+    for (int th = 0; th < nth; ++th)
+        for (size_t i = 0; i < len; ++i) bnode[i] += priv[len * th + i];
+    free(priv);
 }
 
 /* partA of J, OCP_dolfin.py:259 (all buoys, masked ones included) */

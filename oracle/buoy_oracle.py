@@ -58,6 +58,13 @@ class BuoyOracle:
             int(V.bin_dims[0]), int(V.bin_dims[1]), _p(k["bp"]), _p(k["bc"]), int(brute),
         )
 
+    def set_threads(self, n: int):
+        """1 = the reference's serial loop structure; >1 spreads the per-buoy loops over host threads."""
+        self.lib.oracle_set_threads(int(n))
+
+    def max_threads(self) -> int:
+        return int(self.lib.oracle_max_threads())
+
     def forward(self, vel, x0, nt, h, center, mask=None):
         """solve_primal_ode: returns x, u (K,nt,2), cell (K,nt), mask (K) f8, parked (K) u1."""
         vel = np.ascontiguousarray(vel, np.float64)

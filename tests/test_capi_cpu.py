@@ -1,0 +1,104 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol the header declares, refuses to run
+without a GPU (no CPU fallback), and its element arithmetic / host analysis agree with the oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import helpers as H
+from ocp_b200 import capi
+from ocp_b200.build import build
+from oracle.fe_oracle import FEOracle
+
+HEADER = os.path.join(H.ROOT, "include", "ocp_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build()
+    return capi.load_library()
+
+
+def _header_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ocp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = _header_symbols()
+    assert sorted(capi.SYMBOLS) == declared
+    out = subprocess.check_output(["nm", "-D", "--defined-only", capi.LIB_PATH], text=True)
+    exported = set(re.findall(r"\bT (ocp_[a-z0-9_]+)", out))
+    missing = [s for s in declared if s not in exported]
+    assert not missing, missing
+    for s in declared:
+        getattr(lib, s)
+
+
+def test_library_is_sm100a_cuda(lib):
+    out = subprocess.check_output(["cuobjdump", "-lelf", capi.LIB_PATH], text=True)
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.ocp_device_available() == -5
+    with pytest.raises(capi.OcpError):
+        capi.Context(H.square32(), 1.0, 0.005, 200, (1.0, 1.0))
+    from ocp_b200.pipeline import OCP, Parameters
+    with pytest.raises(capi.OcpError):
+        OCP(H.square32(), Parameters(), np.zeros((1, 2)), np.zeros((1, 200, 2)))
+
+
+def test_cell_element_arithmetic_matches_oracle(lib):
+    V = H.lshape()
+    nu = 0.37
+    O = FEOracle(V, nu)
+    w = np.random.default_rng(1).standard_normal(V.ndofs)
+    A, R = O.cell_jacobian(w), O.cell_residual(w)
+    for c in range(0, V.mesh.num_cells, 7):
+        Ac, Rc = capi.selftest_cell_matrix(V.cell_geom[c], w[V.cell_dofs[c]], nu)
+        assert H.rel(Ac, A[c]) < 1e-13 and H.rel(Rc, R[c]) < 1e-13      # two different exact quadrature rules
+
+
+def test_facet_element_arithmetic_matches_oracle(lib):
+    V = H.lshape()
+    O = FEOracle(V, 1.0)
+    rng = np.random.default_rng(2)
+    w, f = rng.standard_normal(V.ndofs), rng.standard_normal((V.num_nodes, 2))
+    rows, B = O.facet_jacobian(w)
+    _, Rv = O.facet_residual(w, f)
+    for k in range(V.g1_cell.size):
+        nodes = V.g1_nodes[k]
+        uv = np.r_[w[V.dof_ux[nodes]], w[V.dof_uy[nodes]]]
+        Af, Rf = capi.selftest_facet_matrix(V.g1_len[k], *V.g1_normal[k], uv, np.r_[f[nodes, 0], f[nodes, 1]])
+        gd = np.r_[V.dof_ux[nodes], V.dof_uy[nodes]]
+        idx = [int(np.nonzero(rows[k] == d)[0][0]) for d in gd]
+        assert H.rel(Af, B[k][np.ix_(idx, idx)]) < 1e-13 and H.rel(Rf, Rv[k][idx]) < 1e-13
+        off = np.ones(12, bool)
+        off[idx] = False
+        assert np.abs(B[k][off]).max() < 1e-14                     # only the facet's own nodes carry trace
+
+
+@pytest.mark.parametrize("which", ["square32", "lshape"])
+def test_host_lu_analysis_solves_the_newton_matrix(lib, which):
+    V = H.square32() if which == "square32" else H.lshape()
+    O = FEOracle(V, 1.0)
+    n = V.ndofs
+    w = 0.1 * np.random.default_rng(0).standard_normal(n)
+    vals = O.on_pattern(O.forward_jacobian(w))
+    A = sp.csr_matrix((vals, V.csr_col, V.csr_rowptr), shape=(n, n))
+    xy = np.zeros((n, 2))
+    xy[V.dof_ux], xy[V.dof_uy] = V.node_coords, V.node_coords
+    xy[V.dof_p] = V.node_coords[:V.mesh.num_vertices]
+    b = np.random.default_rng(1).standard_normal(n)
+    x, nnz_lu, p, q = capi.host_lu_probe(V.csr_rowptr, V.csr_col, vals, xy, b)
+    assert np.abs(A @ x - b).max() / np.abs(b).max() < 1e-10
+    assert sorted(p.tolist()) == list(range(n)) and sorted(q.tolist()) == list(range(n))
+    assert nnz_lu < 12 * vals.size                                  # nested dissection keeps the fill modest

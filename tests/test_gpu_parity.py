@@ -1,0 +1,319 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the committed FEniCS
+fixtures.  Bars (BASELINE.json north_star): cell indices and CSR pattern bit-exact, assembled matrices 1e-12 rel,
+trajectories 1e-10 (we get bit-exact), cost and gradient 1e-8 rel."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from ocp_b200 import capi
+from ocp_b200.pipeline import OCP, Knobs, Parameters, State, initial_control
+from oracle.buoy_oracle import BuoyOracle
+from oracle.fe_oracle import FEOracle
+
+pytestmark = pytest.mark.gpu
+MAT_TOL = 1e-12
+TRAJ_TOL = 1e-10
+COST_TOL = 1e-8
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+@pytest.fixture(scope="module")
+def sq():
+    V = H.square32()
+    xr, ud = H.traj(100)
+    ocp = OCP(V, Parameters(), xr[:, 0, :].copy(), ud, device=dev())
+    yield V, ocp
+    ocp.close()
+
+
+def test_extension_is_loaded_and_on_gpu():
+    lib = capi.load_library()
+    assert lib.ocp_device_available() == 0
+    with open("/proc/self/maps") as fh:
+        assert "libocp_b200.so" in fh.read()
+
+
+@pytest.mark.parametrize("K", [2, 4, 6, 10, 100, 400])
+def test_buoy_forward_bit_exact_vs_oracle_and_fenics(K):
+    V = H.square32()
+    xr, ur = H.traj(K)
+    w = H.field_for(K)
+    ocp = OCP(V, Parameters(), xr[:, 0, :].copy(), ur, device=dev())
+    cell = torch.empty((200, K), device=dev(), dtype=torch.int32)
+    ocp._primal(T(w), ocp.d_x, ocp.d_u, ocp.d_mask, d_cell=cell)
+    x, u = ocp._to_reference_layout(ocp.d_x), ocp._to_reference_layout(ocp.d_u)
+    xo, uo, co, mo, po = BuoyOracle(V, brute=True).forward(V.velocity_nodal(w), xr[:, 0, :], 200, H.H, H.CENTER)
+    assert np.array_equal(cell.cpu().numpy().T, co)              # point-location cell indices: bit-exact
+    assert np.array_equal(x, xo) and np.array_equal(u, uo)      # trajectories: bit-exact vs the oracle
+    assert np.abs(x - xr).max() < 4e-16 and np.abs(u - ur).max() < 4e-16   # and round-off level vs FEniCS
+    assert float(ocp.d_mask.sum()) == 0
+    # host-buffer entry point = the reference's solve_primal_ode(wSol, buoy_mask)
+    mask = np.zeros(K)
+    x2, u2 = ocp.ctx.solve_primal_ode_host(w, xr[:, 0, :], mask)
+    assert np.array_equal(x2, xo) and np.array_equal(u2, uo) and mask.sum() == 0
+    ocp.close()
+
+
+def test_buoy_forward_masks_and_parks_like_the_reference():
+    V = H.lshape()
+    P = Parameters()
+    O = FEOracle(V, 1.0)
+    f = initial_control(V, "PL")
+    w = O.newton_solve(f)
+    rng = np.random.default_rng(3)
+    K = 700
+    x0 = np.stack([rng.uniform(-0.05, 2.05, K), rng.uniform(-0.05, 2.05, K)], 1)
+    # two buoys that leave only with the last step, to hit the "parked" branch
+    ocp = OCP(V, P, x0, np.zeros((K, 200, 2)), device=dev())
+    mask = np.zeros(K)
+    x, u = ocp.solve_primal_ode(State(T(w)), mask)
+    xo, uo, co, mo, po = BuoyOracle(V, brute=True).forward(V.velocity_nodal(w), x0, 200, H.H, ocp.center_of_domain)
+    assert mo.sum() > 50                                         # many start outside the L
+    assert np.array_equal(mask, mo) and np.array_equal(x, xo) and np.array_equal(u, uo)
+    assert np.array_equal(ocp.d_parked.cpu().numpy(), po)
+    ocp.close()
+
+
+def test_parked_last_sample_branch():
+    V = H.square32()
+    vel = np.zeros((V.num_nodes, 2))
+    vel[:, 0] = 1.0
+    w = np.zeros(V.ndofs)
+    w[V.dof_ux] = 1.0
+    x0 = np.array([[1.9, 1.0], [2.5, 1.0], [0.5, 0.5], [2.0 - 198 * H.H - 1e-9, 0.7]])
+    ud = np.random.default_rng(0).standard_normal((4, 200, 2))
+    ocp = OCP(V, Parameters(), x0, ud, device=dev())
+    mask = np.zeros(4)
+    x, u = ocp.solve_primal_ode(State(T(w)), mask)
+    B = BuoyOracle(V, brute=True)
+    xo, uo, co, mo, po = B.forward(vel, x0, 200, H.H, H.CENTER)
+    assert np.array_equal(x, xo) and np.array_equal(u, uo) and mask.tolist() == [1, 1, 0, 0]
+    assert ocp.d_parked.cpu().numpy().tolist() == [0, 0, 0, 1]
+    # backward sweep with a parked buoy: the scatter re-evaluates u(centre)
+    g = np.random.default_rng(1).standard_normal((V.mesh.num_vertices, 4))
+    nn = V.num_nodes
+    acc = torch.zeros(2 * nn + 2, device=dev(), dtype=torch.float64)
+    mu = torch.empty_like(ocp.d_x)
+    ocp.ctx.buoy_adjoint_scatter(T(vel), T(g), 4, ocp.d_x, ocp.d_u, ocp.d_ud, ocp.d_mask, ocp.d_parked, mu, acc)
+    muo = B.adjoint(g, xo, uo, ud, mo, H.H)
+    bo = B.point_sources(vel, xo, ud, muo, mo, H.H, H.CENTER)
+    assert H.rel(ocp._to_reference_layout(mu), muo) < 1e-12
+    assert H.rel(acc[:2 * nn].cpu().numpy().reshape(-1, 2), bo) < 1e-12
+    assert abs(float(acc[2 * nn]) - B.misfit(uo, ud, H.H)) / B.misfit(uo, ud, H.H) < 1e-13
+    assert float(acc[2 * nn + 1]) == 2.0
+    ocp.close()
+
+
+def test_assembled_matrices_and_residual(sq):
+    V, ocp = sq
+    O = FEOracle(V, 1.0)
+    rng = np.random.default_rng(0)
+    w = 0.3 * rng.standard_normal(V.ndofs)
+    f = initial_control(V, "OCP")
+    vals = torch.zeros(V.csr_col.size, device=dev(), dtype=torch.float64)
+    res = torch.zeros(V.ndofs, device=dev(), dtype=torch.float64)
+    ocp.ctx.assemble_forward(T(w), T(f), vals, res, False)
+    assert H.rel(vals.cpu().numpy(), O.on_pattern(O.jacobian_unconstrained(w))) < MAT_TOL
+    assert H.rel(res.cpu().numpy(), O.forward_residual(w, f)) < MAT_TOL
+    ocp.ctx.assemble_forward(T(w), T(f), vals, res, True)
+    assert H.rel(vals.cpu().numpy(), O.on_pattern(O.forward_jacobian(w))) < MAT_TOL
+    r = O.forward_residual(w, f)
+    r[V.dirichlet_dofs] = w[V.dirichlet_dofs]
+    assert H.rel(res.cpu().numpy(), r) < MAT_TOL
+    ocp.ctx.assemble_adjoint(T(w), vals, True)
+    assert H.rel(vals.cpu().numpy(), O.on_pattern(O.adjoint_matrix(w))) < MAT_TOL
+
+
+def test_adjoint_matrix_ignores_viscosity():
+    """aAdj has no viscosity factor (OCP_dolfin.py:344): it is the transpose of the nu=1 Jacobian even when nu != 1."""
+    V = H.lshape()
+    P = Parameters(viscosity=0.01)
+    ocp = OCP(V, P, np.array([[1.5, 0.5]]), np.zeros((1, 200, 2)), device=dev())
+    O = FEOracle(V, 0.01)
+    w = 0.2 * np.random.default_rng(5).standard_normal(V.ndofs)
+    vals = torch.zeros(V.csr_col.size, device=dev(), dtype=torch.float64)
+    ocp.ctx.assemble_adjoint(T(w), vals, True)
+    assert H.rel(vals.cpu().numpy(), O.on_pattern(O.adjoint_matrix(w))) < MAT_TOL
+    ocp.ctx.assemble_forward(T(w), T(np.zeros((V.num_nodes, 2))), vals, None, True)
+    assert H.rel(vals.cpu().numpy(), O.on_pattern(O.forward_jacobian(w))) < MAT_TOL
+    ocp.close()
+
+
+def test_newton_matches_oracle_iterate_by_iterate(sq):
+    V, ocp = sq
+    O = FEOracle(V, 1.0)
+    for name in ("PL", "OCP"):
+        f = initial_control(V, name)
+        st = ocp.forward_solve(T(f))
+        wo, its, hist = O.newton_solve(f, return_history=True)
+        assert ocp.last_newton_its == its == 3
+        assert np.allclose(ocp.last_res_hist[:-1], hist[:-1], rtol=1e-6)
+        assert H.rel(st.vector(), wo) < 1e-11
+
+
+def test_newton_reproduces_fenics_u_bar(sq):
+    """KAT K3 on the GPU: Newton from zero with the recovered control gives the stored FEniCS state."""
+    V, ocp = sq
+    O = FEOracle(V, 1.0)
+    ubar = H.fields()["u_bar"]
+    f, _ = H.recover_control(V, O, ubar)
+    st = ocp.forward_solve(T(f))
+    assert ocp.last_newton_its == 4
+    assert np.abs(st.vector() - ubar).max() < 1e-11
+
+
+def test_projection_adjoint_chain_cost_against_fenics_artefacts():
+    """KAT K4 + K5 on the GPU."""
+    V = H.square32()
+    O, B = FEOracle(V, 1.0), BuoyOracle(V)
+    xr, ud = H.traj(6)
+    ocp = OCP(V, Parameters(), xr[:, 0, :].copy(), ud, device=dev())
+    ubar = H.fields()["u_bar"]
+    st = State(T(ubar))
+    g = ocp.project_grad(st)
+    assert H.rel(g.cpu().numpy(), O.project_gradient(ubar)) < 1e-12
+    mask = np.zeros(6)
+    x, u = ocp.solve_primal_ode(st, mask)
+    q = H.q_nodal(V)
+    Jref = H.scalars()["u_bar_chapter_6.3.3"]["J_array"][0]
+    assert abs(ocp.J(u, q) - Jref) / Jref < 1e-12                # K4: FEniCS' own J_array value
+    mu = ocp.solve_adjoint_ode(st, g, x, mask, u)
+    muo = B.adjoint(O.project_gradient(ubar), x, u, ud, mask, H.H)
+    assert H.rel(mu, muo) < 1e-12
+    z = ocp.adjoint_solve(st, x, u, mask, g)
+    f, _ = H.recover_control(V, O, ubar)
+    zn = V.velocity_nodal(z.vector())
+    g1 = np.unique(V.g1_nodes)
+    z_implied = (q - (1 - 4.0 * 6e-6) * f) / 4.0
+    assert np.abs(zn[g1] - z_implied[g1]).max() < 1e-11           # K5: implied by FEniCS' stored control update
+    gradj = ocp.gradient(f, z, np.full((V.num_nodes, 2), 0.1))
+    go = O.boundary_inner(6e-6 * f - zn, np.full((V.num_nodes, 2), 0.1))
+    assert abs(gradj - go) <= COST_TOL * abs(go)
+    d, l2, h1 = ocp.field_norms(st)
+    assert abs(d - O.divergence_norm(ubar)) < 1e-13
+    ocp.close()
+
+
+def test_gradient_host_entry_point_matches_oracle():
+    V = H.square32()
+    xr, ud = H.traj(10)
+    ocp = OCP(V, Parameters(), xr[:, 0, :].copy(), ud, device=dev())
+    f = initial_control(V, "PL")
+    ocp.ctx.set_observations_host(xr[:, 0, :], ud)
+    n0 = capi.launch_count()
+    w, z, mask, sc = ocp.ctx.gradient_host(f)
+    assert capi.launch_count() - n0 > 20
+    P = H.OraclePipeline(V, 1.0, xr[:, 0, :].copy(), ud, 1e-5)
+    s = P.gradient_step(f)
+    assert sc["newton_its"] == s["its"] and sc["n_masked"] == 0
+    assert H.rel(w, s["w"]) < 1e-11 and H.rel(z, s["z"]) < 1e-9
+    J = sc["misfit"] + 0.5 * 1e-5 * sc["f_norm2"]
+    assert abs(J - 0.025045819440590228) < COST_TOL * 0.025
+    ocp.close()
+
+
+def test_gd_loop_with_line_search_matches_oracle_pipeline():
+    """OCP_dolfin defaults on the 6-buoy case: cost history, Armijo trial counts and the control."""
+    V = H.square32()
+    xr, ud = H.traj(6)
+    ocp = OCP(V, Parameters(), xr[:, 0, :].copy(), ud, device=dev())
+    f0 = initial_control(V, "OCP")
+    r = ocp.run(f0, Knobs(num_steps=3, use_line_search=True))
+    ref = H.OraclePipeline(V, 1.0, xr[:, 0, :].copy(), ud, 6e-6).run(f0, 3, True)
+    assert r.inner_iterations == ref["inner"] == [1, 1, 1] and r.newton_its == [3, 3, 3]
+    assert np.allclose(r.J_array, ref["J_array"], rtol=COST_TOL, atol=0)
+    assert np.allclose(r.J_array, [0.54412, 0.43381, 0.36199], atol=2e-5)
+    g1 = np.unique(V.g1_nodes)
+    assert H.rel(r.f[g1], ref["f"][g1]) < 1e-8
+    ocp.close()
+
+
+def test_grad_check_reproduces_K6_table():
+    """Pipeline_limits defaults + 10_buoys + grad_check: J0, gradj and the FD error table."""
+    V = H.square32()
+    xr, ud = H.traj(10)
+    ocp = OCP(V, Parameters(), xr[:, 0, :].copy(), ud, device=dev())
+    r = ocp.run(initial_control(V, "PL"), Knobs(num_steps=2, use_line_search=False, grad_check=True, exit_rule="ten"))
+    t = r.grad_tables
+    assert abs(t["J0"] - 0.025045819440590228) < COST_TOL * 0.025
+    assert abs(t["gradj"] - (-0.02603602981198921)) < COST_TOL * 0.026
+    one = [row[2] for row in t["one_sided"]]
+    cen = [row[2] for row in t["centered"]]
+    assert np.allclose(one[:4], [1.19e-3, 1.19e-4, 1.19e-5, 1.17e-6], rtol=0.02)
+    assert 5e-6 < cen[0] < 6e-6 and all(1.5e-8 < c < 3e-8 for c in cen[2:7])    # intrinsic 2.1e-8 plateau
+    assert np.allclose(r.J_array, [0.02505, 0.04713], atol=1e-5)
+    ocp.close()
+
+
+def test_cfg1_masked_buoys_in_first_iteration():
+    """cfg1: OCP_dolfin q0 with the 10-buoy set masks 4 of 10 buoys in iteration 0."""
+    V = H.square32()
+    xr, ud = H.traj(10)
+    ocp = OCP(V, Parameters(), xr[:, 0, :].copy(), ud, device=dev())
+    f0 = initial_control(V, "OCP")
+    r = ocp.run(f0, Knobs(num_steps=1, use_line_search=True))
+    s = H.OraclePipeline(V, 1.0, xr[:, 0, :].copy(), ud, 1e-5).gradient_step(f0)
+    assert r.n_masked[0] == int(s["mask"].sum()) == 4
+    ocp.close()
+
+
+@pytest.mark.parametrize("K", [100_000, 1_000_003])
+def test_large_sweep_properties(K):
+    """Size-independent properties at sweep sizes the oracle cannot reach: exact Euler recursion, misfit
+    identities, partition of unity of the deposited sources, linearity of the scatter in gamma."""
+    V = H.square32()
+    rng = np.random.default_rng(0)
+    x0 = np.stack([rng.uniform(0.05, 1.95, K), rng.uniform(0.05, 1.95, K)], 1)
+    ocp = OCP(V, Parameters(), x0, np.zeros((K, 200, 2)), device=dev())
+    w = T(H.field_for(100))
+    ocp._primal(w, ocp.d_x, ocp.d_u, ocp.d_mask)
+    x, u = ocp.d_x, ocp.d_u
+    ok = ocp.d_mask == 0
+    assert int(ok.sum()) > 0.9 * K
+    # x_{k+1} == x_k + h u_k exactly (two roundings), for every buoy that stayed inside
+    inside = ok & (ocp.d_parked == 0)
+    assert bool((x[1:, inside] == x[:-1, inside] + H.H * u[:-1, inside]).all())
+    # parked buoys: only the last sample was moved to the centre (OCP_dolfin.py:226-229)
+    pk = ocp.d_parked != 0
+    if int(pk.sum()) > 0:
+        assert bool((x[1:-1, pk] == x[:-2, pk] + H.H * u[:-2, pk]).all())
+        assert bool((x[-1, pk] == torch.tensor(H.CENTER, device=x.device)).all()) and bool((u[-1, pk] == 0).all())
+    # a sample of buoys against the oracle, bit-exact
+    idx = rng.choice(K, 64, replace=False)
+    xo, uo, *_ = BuoyOracle(V).forward(V.velocity_nodal(H.field_for(100)), x0[idx], 200, H.H, H.CENTER)
+    assert np.array_equal(x[:, idx].cpu().numpy().transpose(1, 0, 2), xo)
+    assert np.array_equal(u[:, idx].cpu().numpy().transpose(1, 0, 2), uo)
+    nn = V.num_nodes
+    g = torch.zeros((V.mesh.num_vertices, 4), device=dev(), dtype=torch.float64)
+    # u_d = u  =>  misfit 0 and, with G = 0 (mu = 0), gamma = 0: nothing is deposited
+    ocp.d_ud.copy_(u)
+    acc = torch.zeros(2 * nn + 2, device=dev(), dtype=torch.float64)
+    ocp.ctx.buoy_adjoint_scatter(ocp.d_vel, g, K, x, u, ocp.d_ud, ocp.d_mask, ocp.d_parked, None, acc)
+    assert float(acc[2 * nn]) == 0.0 and float(acc[:2 * nn].abs().max()) == 0.0
+    assert float(acc[2 * nn + 1]) == float(ocp.d_mask.sum())
+    # u_d = u + c  =>  gamma = h c for every sample: sum of b = K_ok * nt * h * c (partition of unity), misfit closed form
+    cvec = torch.tensor([0.3, -0.7], device=dev(), dtype=torch.float64)
+    ocp.d_ud.copy_(u + cvec)
+    acc.zero_()
+    ocp.ctx.buoy_adjoint_scatter(ocp.d_vel, g, K, x, u, ocp.d_ud, ocp.d_mask, ocp.d_parked, None, acc)
+    nok = int(ok.sum())
+    parked = int(ocp.d_parked.sum())
+    b = acc[:2 * nn].view(-1, 2).sum(0).cpu().numpy()
+    expect = nok * 200 * H.H * np.array([0.3, -0.7])
+    if parked == 0:
+        assert np.allclose(b, expect, rtol=1e-10)
+    assert abs(float(acc[2 * nn]) - 0.5 * K * 200 * H.H * (0.09 + 0.49)) / (K * 0.58) < 1e-9
+    # linearity: doubling the offset doubles b
+    acc2 = torch.zeros_like(acc)
+    ocp.d_ud.copy_(u + 2 * cvec)
+    ocp.ctx.buoy_adjoint_scatter(ocp.d_vel, g, K, x, u, ocp.d_ud, ocp.d_mask, ocp.d_parked, None, acc2)
+    assert float((acc2[:2 * nn] - 2 * acc[:2 * nn]).abs().max()) <= 1e-9 * float(acc[:2 * nn].abs().max())
+    ocp.close()

@@ -144,7 +144,8 @@ def test_masked_and_parked_buoys_follow_the_reference_branches():
     assert mask.tolist() == [1.0, 1.0, 0.0, 0.0]
     assert np.all(x[0] == H.CENTER) and np.all(x[1] == H.CENTER)
     k = 21                                                     # 1.9 + 21*0.005 > 2: evaluation k = 21 fails
-    assert np.all(u[0, :k, 0] == 1.0) and u[0, k, 0] == 0.0 and u[0, k + 1, 0] == 1.0 and np.all(u[0, k + 2:] == 0)
-    assert np.all(u[1, 0] == 0) and np.all(u[1, 1] == [1.0, 0.0]) and np.all(u[1, 2:] == 0)   # started outside
+    one = lambda a: np.allclose(a, 1.0, atol=1e-14)            # partition of unity holds to round-off only
+    assert one(u[0, :k, 0]) and u[0, k, 0] == 0.0 and one(u[0, k + 1, 0]) and np.all(u[0, k + 2:] == 0)
+    assert np.all(u[1, 0] == 0) and one(u[1, 1, 0]) and u[1, 1, 1] == 0 and np.all(u[1, 2:] == 0)   # started outside
     assert parked.tolist() == [0, 0, 0, 1]
-    assert np.all(x[3, -1] == H.CENTER) and np.all(u[3, -1] == 0) and np.all(u[3, :-1, 0] == 1.0)
+    assert np.all(x[3, -1] == H.CENTER) and np.all(u[3, -1] == 0) and one(u[3, :-1, 0])
