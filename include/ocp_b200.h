@@ -182,6 +182,12 @@ long long ocp_launch_count(void);
 int64_t ocp_host_lu_probe(int32_t n, const int32_t *rowptr, const int32_t *col, const double *val,
                           const double *xy, double *rhs_inout, int32_t *p, int32_t *q);
 
+/* Same for the multifrontal solver: host symbolic analysis (nested-dissection tree, fronts, extend-add maps) and
+ * a host restatement of its numeric phase, to test the analysis without a GPU.  kind[i] = 1 for pressure dofs.
+ * stats8 = [#fronts, #levels, largest front, largest pivot block, flops, min |pivot|, workspace doubles, 0]. */
+int64_t ocp_host_mf_probe(int32_t n, const int32_t *rowptr, const int32_t *col, const double *val,
+                          const double *xy, const uint8_t *kind, double *rhs_inout, double *stats8);
+
 /* ---- element-level self-tests (host evaluation of the kernels' __host__ __device__ element arithmetic for one
  * element; used by CPU-only unit tests, never by a compute path).  coef15 = [u_x(6) u_y(6) p(3)];
  * uv6 = [u_x(va,vb,mid) u_y(va,vb,mid)], f6 likewise for the control. */

@@ -6,8 +6,10 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["capi.cu", "buoy_kernels.cu", "fe_kernels.cu", "sparse_solver.cu", "host_lu.cpp"]
-HEADERS = ["element_math.cuh", "kernels.cuh", "sparse_solver.cuh", "host_lu.hpp", "../../include/ocp_b200.h"]
+SOURCES = ["capi.cu", "buoy_kernels.cu", "fe_kernels.cu", "sparse_solver.cu", "multifrontal.cu", "host_lu.cpp",
+           "multifrontal.cpp"]
+HEADERS = ["element_math.cuh", "kernels.cuh", "sparse_solver.cuh", "host_lu.hpp", "multifrontal.hpp",
+           "multifrontal.cuh", "../../include/ocp_b200.h"]
 LIB = os.path.join(_HERE, "libocp_b200.so")
 
 

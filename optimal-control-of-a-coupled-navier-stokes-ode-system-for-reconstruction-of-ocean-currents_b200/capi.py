@@ -27,7 +27,7 @@ SYMBOLS = [
     "ocp_adjoint_solve", "ocp_boundary_inner", "ocp_nodal_axpby", "ocp_field_norms", "ocp_traj_transpose",
     "ocp_solve_primal_ode_host", "ocp_solve_adjoint_ode_host", "ocp_set_observations_host", "ocp_gradient_host",
     "ocp_launch_count",
-    "ocp_host_lu_probe", "ocp_selftest_cell_matrix", "ocp_selftest_facet_matrix",
+    "ocp_host_lu_probe", "ocp_host_mf_probe", "ocp_selftest_cell_matrix", "ocp_selftest_facet_matrix",
 ]
 
 
@@ -71,6 +71,7 @@ def load_library() -> C.CDLL:
         lib.ocp_destroy.argtypes = [C.c_void_p]
         lib.ocp_destroy.restype = None
         lib.ocp_host_lu_probe.restype = C.c_int64
+        lib.ocp_host_mf_probe.restype = C.c_int64
         lib.ocp_launch_count.restype = C.c_longlong
         lib.ocp_set_viscosity.argtypes = [C.c_void_p, C.c_double]
         lib.ocp_set_viscosity.restype = None
@@ -294,3 +295,19 @@ def host_lu_probe(rowptr, col, val, xy, rhs):
     if nz < 0:
         raise OcpError(f"host LU analysis failed ({ERRORS.get(nz, nz)})")
     return x, int(nz), p, q
+
+
+def host_mf_probe(rowptr, col, val, xy, kind, rhs):
+    """Multifrontal symbolic analysis + host restatement of its numeric phase: returns (x, stats dict)."""
+    lib = load_library()
+    n = rowptr.size - 1
+    rp, ci = np.ascontiguousarray(rowptr, np.int32), np.ascontiguousarray(col, np.int32)
+    v, c = np.ascontiguousarray(val, np.float64), np.ascontiguousarray(xy, np.float64)
+    kd = np.ascontiguousarray(kind, np.uint8)
+    x = np.array(rhs, dtype=np.float64, copy=True)
+    st = np.zeros(8)
+    rc = lib.ocp_host_mf_probe(n, _hp(rp), _hp(ci), _hp(v), _hp(c), _hp(kd), _hp(x), _hp(st))
+    if rc < 0:
+        raise OcpError(f"multifrontal host analysis failed ({ERRORS.get(rc, rc)})")
+    keys = ["fronts", "levels", "max_front", "max_pivot_block", "flops", "min_pivot", "workspace"]
+    return x, dict(zip(keys, st[:7]))

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,9 +15,44 @@
 #include "element_math.cuh"
 #include "host_lu.hpp"
 #include "kernels.cuh"
+#include "multifrontal.cuh"
 #include "sparse_solver.cuh"
 
 using namespace ocp;
+
+// Sparse direct solver behind one interface: the in-house multifrontal LU (default) or cusolverRf
+// (OCP_SOLVER=rf, or automatically when a front is too large for the multifrontal panel kernel).
+struct DirectSolver {
+    MultifrontalLU mf;
+    SparseLU rf;
+    bool use_mf = true, factored_once = false;
+    double analyse_ms = 0.0;
+    bool configure(int n, int nnz, const int *h_rowptr, const int *h_col, const int *d_rowptr, const int *d_col,
+                   const double *xy, const unsigned char *kind, std::string &err) {
+        const char *env = getenv("OCP_SOLVER");
+        use_mf = !(env && std::string(env) == "rf");
+        if (use_mf) {
+            std::string e2;
+            if (mf.configure(n, nnz, h_rowptr, h_col, xy, kind, e2)) {
+                analyse_ms = mf.analyse_ms;
+                return true;
+            }
+            use_mf = false;   // front too large for the panel kernel: fall back to the library refactorisation
+        }
+        rf.configure(n, nnz, h_rowptr, h_col, d_rowptr, d_col, xy, kind);
+        return true;
+    }
+    bool factor(const double *d_vals, cudaStream_t s, std::string &err) {
+        if (use_mf) return mf.factor(d_vals, s, err);
+        const bool first = !rf.analysed();
+        const bool ok = rf.factor(d_vals, s, err);
+        if (first) analyse_ms = rf.analyse_ms;
+        return ok;
+    }
+    bool solve(double *d_x, cudaStream_t s, std::string &err) {
+        return use_mf ? mf.solve(d_x, s, err) : rf.solve(d_x, s, err);
+    }
+};
 
 struct ocp_ctx {
     cudaStream_t stream = nullptr;
@@ -48,7 +84,7 @@ struct ocp_ctx {
     // resident observations (the reference's module globals u_d, xsarr, ysarr; OCP_dolfin.py:176-183)
     double *d_obs_x0 = nullptr, *d_obs_ud = nullptr;
     int obs_K = 0;
-    SparseLU lu_fwd, lu_adj, lu_mass;
+    DirectSolver lu_fwd, lu_adj, lu_mass;
     bool mass_factored = false;
     int adj_refine = 1;
     ocp_solver_stats stats{};
@@ -177,9 +213,8 @@ void ocp_get_solver_stats(const ocp_ctx *ctx, ocp_solver_stats *out) {
 
 void ocp_reset_solver_stats(ocp_ctx *ctx) {
     if (ctx) {
-        double keep = ctx->stats.analyse_ms;
         ctx->stats = ocp_solver_stats{};
-        ctx->stats.analyse_ms = keep;
+        ctx->stats.analyse_ms = ctx->lu_fwd.analyse_ms + ctx->lu_adj.analyse_ms + ctx->lu_mass.analyse_ms;
     }
 }
 
@@ -323,11 +358,13 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
         xy[2 * (size_t)d->dof_p[i] + 1] = d->node_coords[2 * (size_t)i + 1];
         kind[d->dof_p[i]] = 1;
     }
-    c->lu_fwd.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data());
-    c->lu_adj.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data());
     std::vector<unsigned char> kind0(nv, 0);
-    c->lu_mass.configure(nv, c->m_nnz, m_rowptr.data(), m_col.data(), c->d_m_rowptr, c->d_m_col, d->node_coords,
-                         kind0.data());
+    if (!c->lu_fwd.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data(), c->err) ||
+        !c->lu_adj.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data(), c->err) ||
+        !c->lu_mass.configure(nv, c->m_nnz, m_rowptr.data(), m_col.data(), c->d_m_rowptr, c->d_m_col, d->node_coords,
+                              kind0.data(), c->err))
+        return OCP_ERR_SOLVER;
+    c->stats.analyse_ms = c->lu_fwd.analyse_ms + c->lu_adj.analyse_ms + c->lu_mass.analyse_ms;
     return OCP_OK;
 }
 
@@ -400,9 +437,7 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
         }
         {
             PhaseTimer t(c, &c->stats.factor_ms);
-            bool first = !c->lu_fwd.analysed();
             if (!c->lu_fwd.factor(c->d_vals, s, c->err)) return OCP_ERR_SOLVER;
-            if (first) c->stats.analyse_ms += c->lu_fwd.analyse_ms;
             c->stats.n_factor++;
         }
         {
@@ -437,7 +472,6 @@ int ocp_project_grad(ocp_ctx *c, const double *d_w, double *d_g) {
     if (!c->mass_factored) {
         PhaseTimer t(c, &c->stats.factor_ms);
         if (!c->lu_mass.factor(c->d_m_vals, s, c->err)) return OCP_ERR_SOLVER;
-        c->stats.analyse_ms += c->lu_mass.analyse_ms;
         c->mass_factored = true;
     }
     {
@@ -497,9 +531,7 @@ int ocp_adjoint_solve(ocp_ctx *c, const double *d_w, const double *d_bnode, doub
     }
     {
         PhaseTimer t(c, &c->stats.factor_ms);
-        bool first = !c->lu_adj.analysed();
         if (!c->lu_adj.factor(c->d_vals, s, c->err)) return OCP_ERR_SOLVER;
-        if (first) c->stats.analyse_ms += c->lu_adj.analyse_ms;
         c->stats.n_factor++;
     }
     {
@@ -694,6 +726,21 @@ void ocp_selftest_cell_matrix(const double *geom6, const double *coef15, double 
 void ocp_selftest_facet_matrix(double len, double nx, double ny, const double *uv6, const double *f6, double *A36,
                                double *R6) {
     for (int r = 0; r < 6; ++r) facet_row(len, nx, ny, uv6, uv6 + 3, f6, f6 + 3, r, A36 + 6 * r, R6[r]);
+}
+
+int64_t ocp_host_mf_probe(int32_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *xy,
+                          const uint8_t *kind, double *rhs_inout, double *stats8) {
+    if (n <= 0 || !rowptr || !col || !val || !xy || !kind) return OCP_ERR_INVALID;
+    MFSymbolic S;
+    mf_analyse(n, rowptr, col, xy, kind, 48, S);
+    MFHostNumeric N;
+    if (!mf_factor_host(S, val, N)) return OCP_ERR_SOLVER;
+    if (rhs_inout) mf_solve_host(S, N, rhs_inout);
+    if (stats8) {
+        stats8[0] = S.nnodes; stats8[1] = S.nlevels; stats8[2] = S.max_front; stats8[3] = S.max_np;
+        stats8[4] = S.flops; stats8[5] = N.min_pivot; stats8[6] = (double)S.fsize; stats8[7] = 0.0;
+    }
+    return (int64_t)S.fsize;
 }
 
 int64_t ocp_host_lu_probe(int32_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *xy,

@@ -85,6 +85,46 @@ void mf_analyse(int n, const int *rowptr, const int *col, const double *xy, cons
     std::iota(all.begin(), all.end(), 0);
     b.rec(all);
     const int nn = (int)b.node_cols.size();
+    // ---- lift every pressure-like dof to the highest tree node among its structural neighbours, so that all
+    // velocities it couples to are eliminated before it and its pivot is a (non-zero) Schur complement even
+    // with pivoting restricted to the front's own rows.  The neighbours' nodes lie on one root path (they are
+    // all adjacent to the dof itself), so "highest" is well defined and the tree stays a valid elimination tree.
+    {
+        std::vector<int> par(nn, -1), depth(nn, 0), node_of(n, -1);
+        for (int s = 0; s < nn; ++s)
+            for (int c : {b.node_children[s].first, b.node_children[s].second})
+                if (c >= 0) par[c] = s;
+        for (int s = nn - 1; s >= 0; --s) depth[s] = par[s] < 0 ? 0 : depth[par[s]] + 1;   // parents have larger ids
+        for (int s = 0; s < nn; ++s)
+            for (int d : b.node_cols[s]) node_of[d] = s;
+        std::vector<int> target(n, -1);
+        bool any = false;
+        for (int d = 0; d < n; ++d) {
+            if (!kind[d]) continue;
+            int best = node_of[d];
+            for (int p = rowptr[d]; p < rowptr[d + 1]; ++p) {
+                const int t = node_of[col[p]];
+                if (depth[t] < depth[best]) best = t;
+            }
+            if (best != node_of[d]) {
+                target[d] = best;
+                any = true;
+            }
+        }
+        if (any) {
+            for (int s = 0; s < nn; ++s) {
+                std::vector<int> keep;
+                for (int d : b.node_cols[s])
+                    if (target[d] < 0) keep.push_back(d);
+                b.node_cols[s].swap(keep);
+            }
+            for (int d = 0; d < n; ++d)
+                if (target[d] >= 0) b.node_cols[target[d]].push_back(d);
+            for (int s = 0; s < nn; ++s)
+                std::stable_sort(b.node_cols[s].begin(), b.node_cols[s].end(),
+                                 [&](int a, int c) { return kind[a] < kind[c]; });
+        }
+    }
     S = MFSymbolic();
     S.n = n;
     S.nnodes = nn;

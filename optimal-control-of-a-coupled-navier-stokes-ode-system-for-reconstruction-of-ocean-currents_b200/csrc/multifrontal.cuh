@@ -1,0 +1,38 @@
+// Device-side multifrontal LU (numeric factorisation + triangular solves on the GPU); see multifrontal.hpp for the
+// host symbolic analysis it consumes.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "multifrontal.hpp"
+
+namespace ocp {
+
+class MultifrontalLU {
+  public:
+    MultifrontalLU();
+    ~MultifrontalLU();
+    MultifrontalLU(const MultifrontalLU &) = delete;
+    MultifrontalLU &operator=(const MultifrontalLU &) = delete;
+
+    // symbolic analysis (host, pattern + coordinates only) and upload of the schedule
+    bool configure(int n, int nnz, const int *h_rowptr, const int *h_col, const double *xy, const unsigned char *kind,
+                   std::string &err);
+    bool factor(const double *d_vals, cudaStream_t s, std::string &err);   // numeric factorisation on the GPU
+    bool solve(double *d_x, cudaStream_t s, std::string &err);             // in place
+    long long factor_nnz() const { return factor_nnz_; }
+    double flops() const { return flops_; }
+    int levels() const { return nlevels_; }
+    int max_front() const { return max_front_; }
+    double analyse_ms = 0.0;
+
+  private:
+    struct Impl;
+    Impl *impl_ = nullptr;
+    int n_ = 0, nnz_ = 0, nlevels_ = 0, max_front_ = 0;
+    long long factor_nnz_ = 0;
+    double flops_ = 0.0;
+};
+
+}  // namespace ocp

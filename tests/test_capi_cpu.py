@@ -102,3 +102,25 @@ def test_host_lu_analysis_solves_the_newton_matrix(lib, which):
     assert np.abs(A @ x - b).max() / np.abs(b).max() < 1e-10
     assert sorted(p.tolist()) == list(range(n)) and sorted(q.tolist()) == list(range(n))
     assert nnz_lu < 12 * vals.size                                  # nested dissection keeps the fill modest
+
+
+@pytest.mark.parametrize("which", ["square32", "lshape"])
+def test_multifrontal_analysis_solves_forward_and_adjoint_matrices(lib, which):
+    """Symbolic analysis (ND tree, pressure lifting, fronts, extend-add maps) + host restatement of the numeric
+    phase; the jittered L-shape needs the pressure lifting to keep every restricted pivot block non-singular."""
+    V = H.square32() if which == "square32" else H.lshape(20, 0.2)
+    O = FEOracle(V, 1.0)
+    n = V.ndofs
+    w = 0.1 * np.random.default_rng(0).standard_normal(n)
+    xy = np.zeros((n, 2))
+    xy[V.dof_ux], xy[V.dof_uy] = V.node_coords, V.node_coords
+    xy[V.dof_p] = V.node_coords[:V.mesh.num_vertices]
+    kind = np.zeros(n, np.uint8)
+    kind[V.dof_p] = 1
+    b = np.random.default_rng(1).standard_normal(n)
+    for M in (O.forward_jacobian(w), O.adjoint_matrix(w), O.forward_jacobian(0 * w)):
+        vals = O.on_pattern(M)
+        A = sp.csr_matrix((vals, V.csr_col, V.csr_rowptr), shape=(n, n))
+        x, st = capi.host_mf_probe(V.csr_rowptr, V.csr_col, vals, xy, kind, b)
+        assert np.abs(A @ x - b).max() / np.abs(b).max() < 1e-11
+        assert st["min_pivot"] > 1e-6 and st["levels"] <= 16
