@@ -3,14 +3,18 @@
 // the reference meshes); each CTA extend-adds its children's Schur complements, then runs a right-looking
 // blocked LU of the np fully-summed columns (panel of 16 columns in shared memory, 4x4 register tiles for the
 // trailing update) with partial pivoting restricted to the fully-summed rows.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.cuh"
 #include "multifrontal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ocp {
 
@@ -18,7 +22,7 @@ namespace {
 
 constexpr int NB = 16;     // panel width
 constexpr int CW = 128;    // trailing-update column chunk
-constexpr int TF = 256;    // threads per front CTA
+constexpr int TF = 512;    // threads per front CTA
 constexpr int SB = 32;     // triangular-solve block (one warp)
 
 struct MFDev {
@@ -34,138 +38,156 @@ __global__ void scatter_values_kernel(int nnz, const long long *__restrict__ des
     if (k < nnz) F[dest[k]] = vals[k];
 }
 
+// One CLUSTER of C CTAs per front (C = 1 for the many small fronts at the bottom of the tree, 8-16 for the few
+// large fronts near the root).  Per 16-column panel: CTA 0 factors the panel in its shared memory, the cluster
+// synchronises, then every CTA applies the row interchanges, solves U12 and updates the trailing matrix for the
+// column chunks it owns (chunk = absolute column index / cw, owner = chunk % C), and the cluster synchronises again.
+// All front accesses bypass L1 (ld.cg / st.cg): columns migrate between the panel owner (CTA 0) and chunk owners.
 __global__ void __launch_bounds__(TF)
-mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info) {
+mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int cw, int *info) {
     extern __shared__ double sm[];
     __shared__ int s_piv[NB];
+    cg::cluster_group cl = cg::this_cluster();
+    const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     double *P = sm;                              // panel, ld = mp
     double *Uc = sm + (size_t)max_m * NB;        // NB x CW, row-major
-    const int s = nodes[blockIdx.x];
+    const int s = nodes[blockIdx.x / C];
     const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
     double *F = d.F + d.front_ptr[s];
-    // ---- extend-add the children's update matrices
+    // ---- extend-add the children's update matrices (atomic: two children may hit the same entry)
     for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
         const int c = d.child[ci], mc = d.m[c], npc = d.np[c], nu = mc - npc;
         const double *Fc = d.F + d.front_ptr[c];
         const int *rel = d.rel + d.rel_ptr[c];
-        for (int e = tid; e < nu * nu; e += TF) {
-            const int i = e % nu, j = e / nu;
-            F[rel[i] + (size_t)rel[j] * m] += Fc[(npc + i) + (size_t)(npc + j) * mc];
+        for (int j = rank; j < nu; j += C) {
+            const double *src = Fc + npc + (size_t)(npc + j) * mc;
+            double *dst = F + (size_t)__ldg(rel + j) * m;
+            for (int i = tid; i < nu; i += TF) atomicAdd(dst + __ldg(rel + i), __ldcg(src + i));
         }
-        __syncthreads();
     }
+    cl.sync();
     if (np == 0) return;
     int *gpiv = d.piv + d.first[s];
     for (int k0 = 0; k0 < np; k0 += NB) {
         const int kb = min(NB, np - k0), mp = m - k0;
-        for (int e = tid; e < mp * kb; e += TF) {
-            const int i = e % mp, j = e / mp;
-            P[i + j * mp] = F[(k0 + i) + (size_t)(k0 + j) * m];
-        }
-        __syncthreads();
-        // ---- panel factorisation, pivot rows restricted to the fully-summed block
-        for (int j = 0; j < kb; ++j) {
-            if (tid < 32) {
-                double best = -1.0;
-                int r = j;
-                for (int i = j + tid; i < np - k0; i += 32) {
-                    const double a = fabs(P[i + j * mp]);
-                    if (a > best) {
-                        best = a;
-                        r = i;
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int orr = __shfl_xor_sync(0xffffffffu, r, o);
-                    if (ob > best || (ob == best && orr < r)) {
-                        best = ob;
-                        r = orr;
-                    }
-                }
-                if (tid == 0) {
-                    s_piv[j] = r;
-                    gpiv[k0 + j] = k0 + r;
-                    if (!(best > 0.0)) atomicExch(info, s + 1);
-                }
-            }
+        for (int j = 0; j < kb; ++j)
+            for (int i = tid; i < mp; i += TF) P[i + j * mp] = __ldcg(F + (k0 + i) + (size_t)(k0 + j) * m);
+        if (rank == 0) {
             __syncthreads();
-            const int r = s_piv[j];
-            if (r != j && tid < kb) {
-                const double t = P[j + tid * mp];
-                P[j + tid * mp] = P[r + tid * mp];
-                P[r + tid * mp] = t;
-            }
-            __syncthreads();
-            const double inv = 1.0 / P[j + j * mp];
-            for (int i = j + 1 + tid; i < mp; i += TF) {
-                const double l = P[i + j * mp] * inv;
-                P[i + j * mp] = l;
-                for (int jj = j + 1; jj < kb; ++jj) P[i + jj * mp] -= l * P[j + jj * mp];
-            }
-            __syncthreads();
-        }
-        for (int e = tid; e < mp * kb; e += TF) {
-            const int i = e % mp, j = e / mp;
-            F[(k0 + i) + (size_t)(k0 + j) * m] = P[i + j * mp];
-        }
-        // ---- the panel's row interchanges on all other columns of the front
-        for (int c = tid; c < m; c += TF) {
-            if (c >= k0 && c < k0 + kb) continue;
-            double *colp = F + (size_t)c * m + k0;
+            // ---- panel factorisation, pivot rows restricted to the fully-summed block
             for (int j = 0; j < kb; ++j) {
-                const int r = s_piv[j];
-                if (r != j) {
-                    const double t = colp[j];
-                    colp[j] = colp[r];
-                    colp[r] = t;
-                }
-            }
-        }
-        __syncthreads();
-        // ---- U12 = L11^{-1} F12 and trailing update, CW columns at a time
-        const int nrow = m - k0 - kb;
-        for (int c0 = k0 + kb; c0 < m; c0 += CW) {
-            const int cw = min(CW, m - c0);
-            if (tid < cw) {
-                double *colp = F + (size_t)(c0 + tid) * m + k0;
-                double u[NB];
+                if (tid < 32) {
+                    double best = -1.0;
+                    int r = j;
+                    for (int i = j + tid; i < np - k0; i += 32) {
+                        const double a = fabs(P[i + j * mp]);
+                        if (a > best) {
+                            best = a;
+                            r = i;
+                        }
+                    }
 #pragma unroll
-                for (int t = 0; t < NB; ++t) u[t] = t < kb ? colp[t] : 0.0;
-#pragma unroll
-                for (int t = 1; t < NB; ++t) {
-                    if (t < kb) {
-                        double a = u[t];
-#pragma unroll
-                        for (int tt = 0; tt < NB; ++tt)
-                            if (tt < t) a -= P[t + tt * mp] * u[tt];
-                        u[t] = a;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int orr = __shfl_xor_sync(0xffffffffu, r, o);
+                        if (ob > best || (ob == best && orr < r)) {
+                            best = ob;
+                            r = orr;
+                        }
+                    }
+                    if (tid == 0) {
+                        s_piv[j] = r;
+                        gpiv[k0 + j] = k0 + r;
+                        if (!(best > 0.0)) atomicExch(info, s + 1);
                     }
                 }
+                __syncthreads();
+                const int r = s_piv[j];
+                if (r != j && tid < kb) {
+                    const double t = P[j + tid * mp];
+                    P[j + tid * mp] = P[r + tid * mp];
+                    P[r + tid * mp] = t;
+                }
+                __syncthreads();
+                const double inv = 1.0 / P[j + j * mp];
+                for (int i = j + 1 + tid; i < mp; i += TF) {
+                    const double l = P[i + j * mp] * inv;
+                    P[i + j * mp] = l;
+                    for (int jj = j + 1; jj < kb; ++jj) P[i + jj * mp] -= l * P[j + jj * mp];
+                }
+                __syncthreads();
+            }
+            for (int j = 0; j < kb; ++j)
+                for (int i = tid; i < mp; i += TF) __stcg(F + (k0 + i) + (size_t)(k0 + j) * m, P[i + j * mp]);
+        }
+        cl.sync();
+        if (rank != 0) {
+            // the factored panel and its pivots, written by CTA 0
+            for (int j = 0; j < kb; ++j)
+                for (int i = tid; i < mp; i += TF) P[i + j * mp] = __ldcg(F + (k0 + i) + (size_t)(k0 + j) * m);
+            if (tid < kb) s_piv[tid] = __ldcg(gpiv + k0 + tid) - k0;
+        }
+        __syncthreads();
+        // ---- own column chunks: row interchanges, U12 = L11^{-1} F12, trailing update
+        const int nrow = m - k0 - kb;
+        for (int cbeg = rank * cw; cbeg < m; cbeg += C * cw) {
+            const int cend = min(m, cbeg + cw);
+            const int lo = max(cbeg, k0 + kb);        // first trailing column of this chunk
+            const int c = cbeg + tid;
+            if (c < cend && !(c >= k0 && c < k0 + kb)) {
+                double *colp = F + (size_t)c * m + k0;
+                for (int j = 0; j < kb; ++j) {
+                    const int r = s_piv[j];
+                    if (r != j) {
+                        const double t = __ldcg(colp + j);
+                        __stcg(colp + j, __ldcg(colp + r));
+                        __stcg(colp + r, t);
+                    }
+                }
+                if (c >= k0 + kb) {
+                    double u[NB];
 #pragma unroll
-                for (int t = 0; t < NB; ++t) {
-                    if (t < kb) colp[t] = u[t];
-                    Uc[t * CW + tid] = u[t];
+                    for (int t = 0; t < NB; ++t) u[t] = t < kb ? __ldcg(colp + t) : 0.0;
+#pragma unroll
+                    for (int t = 1; t < NB; ++t) {
+                        if (t < kb) {
+                            double a = u[t];
+#pragma unroll
+                            for (int tt = 0; tt < NB; ++tt)
+                                if (tt < t) a -= P[t + tt * mp] * u[tt];
+                            u[t] = a;
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) {
+                        if (t < kb) __stcg(colp + t, u[t]);
+                        Uc[t * CW + (c - lo)] = u[t];
+                    }
                 }
             }
             __syncthreads();
-            if (nrow > 0) {
-                const int tr = (nrow + 3) >> 2, tc = (cw + 3) >> 2;
+            const int ncol = cend - lo;
+            if (nrow > 0 && ncol > 0) {
+                const int tr = (nrow + 3) >> 2, tc = (ncol + 3) >> 2;
                 for (int tile = tid; tile < tr * tc; tile += TF) {
                     const int ti = tile % tr, tj = tile / tr;
                     const int i0 = kb + 4 * ti, cc0 = 4 * tj;
-                    double acc[4][4];
+                    double f[4][4], acc[4][4];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+                    for (int b = 0; b < 4; ++b) {
+                        const double *colp = F + (size_t)(lo + cc0 + b) * m + k0;
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+                        for (int a = 0; a < 4; ++a) {
+                            f[a][b] = (cc0 + b < ncol && i0 + a < mp) ? __ldcg(colp + i0 + a) : 0.0;
+                            acc[a][b] = 0.0;
+                        }
+                    }
                     for (int t = 0; t < kb; ++t) {
                         double l[4], uu[4];
 #pragma unroll
                         for (int a = 0; a < 4; ++a) l[a] = (i0 + a < mp) ? P[i0 + a + t * mp] : 0.0;
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) uu[b] = (cc0 + b < cw) ? Uc[t * CW + cc0 + b] : 0.0;
+                        for (int b = 0; b < 4; ++b) uu[b] = (cc0 + b < ncol) ? Uc[t * CW + cc0 + b] : 0.0;
 #pragma unroll
                         for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -173,17 +195,18 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info) {
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        if (cc0 + b < cw) {
-                            double *colp = F + (size_t)(c0 + cc0 + b) * m + k0;
+                        if (cc0 + b < ncol) {
+                            double *colp = F + (size_t)(lo + cc0 + b) * m + k0;
 #pragma unroll
                             for (int a = 0; a < 4; ++a)
-                                if (i0 + a < mp) colp[i0 + a] -= acc[a][b];
+                                if (i0 + a < mp) __stcg(colp + i0 + a, f[a][b] - acc[a][b]);
                         }
                     }
                 }
             }
             __syncthreads();
         }
+        cl.sync();
     }
 }
 
@@ -302,7 +325,7 @@ struct MultifrontalLU::Impl {
         *child = nullptr, *rel_ptr = nullptr, *rel = nullptr, *level_nodes = nullptr, *piv = nullptr, *info = nullptr;
     long long *front_ptr = nullptr, *a_dest = nullptr;
     double *F = nullptr;
-    std::vector<int> level_max_m;
+    std::vector<int> level_max_m, level_cluster, level_cw;
     MFDev dev{};
     ~Impl() {
         void *p[] = {m, np, first, idx_ptr, idx, child_ptr, child, rel_ptr, rel, level_nodes, piv, info, front_ptr,
@@ -349,7 +372,38 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     if (e == cudaSuccess) e = cudaMalloc((void **)&I.info, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(I.info, 0, sizeof(int));
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+        // the attribute is per kernel, not per solver instance: always allow the full opt-in budget
+        e = cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    // cluster size per level: as many CTAs per front as the chip has room for (powers of two, <= 16)
+    int max_cluster = 16;
+    if (const char *envc = getenv("OCP_MF_MAX_CLUSTER")) max_cluster = std::max(1, atoi(envc));
+    I.level_cluster.assign(S.nlevels, 1);
+    I.level_cw.assign(S.nlevels, 32);
+    for (int l = 0; l < S.nlevels && e == cudaSuccess; ++l) {
+        const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
+        int c = 1;
+        while (c * 2 <= max_cluster && nf * c * 2 <= 148 && c * 2 * 16 <= I.level_max_m[l]) c *= 2;
+        while (c > 1) {   // make sure the cluster shape is launchable with this kernel's resources
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(nf * c);
+            cfg.blockDim = dim3(TF);
+            cfg.dynamicSmemBytes = ((size_t)I.level_max_m[l] * NB + (size_t)NB * CW) * sizeof(double);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = c;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, mf_factor_kernel, &cfg) == cudaSuccess && ncl >= 1) break;
+            cudaGetLastError();
+            c /= 2;
+        }
+        I.level_cluster[l] = c;
+        I.level_cw[l] = (c >= 16) ? 16 : 32;
+    }
     if (e != cudaSuccess) {
         err = std::string("multifrontal setup: ") + cudaGetErrorString(e);
         return false;
@@ -377,8 +431,26 @@ bool MultifrontalLU::factor(const double *d_vals, cudaStream_t s, std::string &e
     scatter_values_kernel<<<(nnz_ + 255) / 256, 256, 0, s>>>(nnz_, I.a_dest, d_vals, I.F);
     for (int l = 0; l < S.nlevels; ++l) {
         const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
-        const size_t smem = ((size_t)I.level_max_m[l] * NB + (size_t)NB * CW) * sizeof(double);
-        mf_factor_kernel<<<nf, TF, smem, s>>>(I.dev, I.level_nodes + S.level_ptr[l], I.level_max_m[l], I.info);
+        const int c = I.level_cluster[l];
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(nf * c);
+        cfg.blockDim = dim3(TF);
+        cfg.dynamicSmemBytes = ((size_t)I.level_max_m[l] * NB + (size_t)NB * CW) * sizeof(double);
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = c;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, mf_factor_kernel, I.dev, (const int *)(I.level_nodes + S.level_ptr[l]),
+                                            I.level_max_m[l], I.level_cw[l], I.info);
+        if (le != cudaSuccess) {
+            err = std::string("multifrontal factor launch (level ") + std::to_string(l) + ", cluster " +
+                  std::to_string(c) + "): " + cudaGetErrorString(le);
+            return false;
+        }
     }
     int info = 0;
     cudaError_t e = cudaMemcpyAsync(&info, I.info, sizeof(int), cudaMemcpyDeviceToHost, s);
