@@ -94,6 +94,9 @@ const char *ocp_last_error(const ocp_ctx *ctx);
 void ocp_get_solver_stats(const ocp_ctx *ctx, ocp_solver_stats *out);
 void ocp_reset_solver_stats(ocp_ctx *ctx);
 void ocp_set_viscosity(ocp_ctx *ctx, double viscosity);
+/* Per-phase line-item timing (ocp_get_solver_stats) synchronises the stream after every phase; it is therefore off
+ * by default and switched on only for profiling runs (also: environment OCP_PROFILE=1). */
+void ocp_set_profiling(ocp_ctx *ctx, int on);
 
 /* ---- forward Navier-Stokes: `solve(F == 0, w, bcs)`, OCP_dolfin.py:315-325 (406, 274, 284, 289) ----------
  * d_f: control as P2 nodal field (nn,2) (only its Gamma_1 trace is used).  d_w: in = initial guess when
@@ -187,6 +190,9 @@ int64_t ocp_host_lu_probe(int32_t n, const int32_t *rowptr, const int32_t *col, 
  * stats8 = [#fronts, #levels, largest front, largest pivot block, flops, min |pivot|, workspace doubles, 0]. */
 int64_t ocp_host_mf_probe(int32_t n, const int32_t *rowptr, const int32_t *col, const double *val,
                           const double *xy, const uint8_t *kind, double *rhs_inout, double *stats8);
+/* Pivot-search window of that host restatement: 1 (default) = static pivoting exactly like the GPU kernels; a large
+ * value = partial pivoting restricted to the front's fully-summed rows (used by tests to validate static pivoting). */
+void ocp_host_mf_set_pivot_window(int rows);
 
 /* ---- element-level self-tests (host evaluation of the kernels' __host__ __device__ element arithmetic for one
  * element; used by CPU-only unit tests, never by a compute path).  coef15 = [u_x(6) u_y(6) p(3)];

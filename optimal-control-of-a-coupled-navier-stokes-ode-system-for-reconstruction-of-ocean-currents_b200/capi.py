@@ -21,13 +21,13 @@ ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "sparse solver error", -
 # every symbol include/ocp_b200.h declares (tests/test_capi_symbols.py checks the header against this list)
 SYMBOLS = [
     "ocp_version", "ocp_device_available", "ocp_create", "ocp_destroy", "ocp_last_error",
-    "ocp_get_solver_stats", "ocp_reset_solver_stats", "ocp_set_viscosity",
+    "ocp_get_solver_stats", "ocp_reset_solver_stats", "ocp_set_viscosity", "ocp_set_profiling",
     "ocp_forward_solve", "ocp_assemble_forward", "ocp_assemble_adjoint", "ocp_project_grad",
     "ocp_velocity_nodal", "ocp_buoy_forward", "ocp_buoy_adjoint_scatter", "ocp_misfit",
     "ocp_adjoint_solve", "ocp_boundary_inner", "ocp_nodal_axpby", "ocp_field_norms", "ocp_traj_transpose",
     "ocp_solve_primal_ode_host", "ocp_solve_adjoint_ode_host", "ocp_set_observations_host", "ocp_gradient_host",
     "ocp_launch_count",
-    "ocp_host_lu_probe", "ocp_host_mf_probe", "ocp_selftest_cell_matrix", "ocp_selftest_facet_matrix",
+    "ocp_host_lu_probe", "ocp_host_mf_probe", "ocp_host_mf_set_pivot_window", "ocp_selftest_cell_matrix", "ocp_selftest_facet_matrix",
 ]
 
 
@@ -72,11 +72,13 @@ def load_library() -> C.CDLL:
         lib.ocp_destroy.restype = None
         lib.ocp_host_lu_probe.restype = C.c_int64
         lib.ocp_host_mf_probe.restype = C.c_int64
+        lib.ocp_host_mf_set_pivot_window.restype = None
         lib.ocp_launch_count.restype = C.c_longlong
         lib.ocp_set_viscosity.argtypes = [C.c_void_p, C.c_double]
         lib.ocp_set_viscosity.restype = None
         lib.ocp_get_solver_stats.restype = None
         lib.ocp_reset_solver_stats.restype = None
+        lib.ocp_set_profiling.restype = None
         lib.ocp_selftest_cell_matrix.restype = None
         lib.ocp_selftest_facet_matrix.restype = None
         _lib = lib
@@ -166,6 +168,10 @@ class Context:
 
     def reset_solver_stats(self):
         self.lib.ocp_reset_solver_stats(self._h)
+
+    def set_profiling(self, on: bool):
+        """Line-item timing synchronises after every phase: keep it off outside profiling runs."""
+        self.lib.ocp_set_profiling(self._h, int(bool(on)))
 
     def set_viscosity(self, nu: float):
         self.lib.ocp_set_viscosity(self._h, float(nu))
@@ -297,9 +303,11 @@ def host_lu_probe(rowptr, col, val, xy, rhs):
     return x, int(nz), p, q
 
 
-def host_mf_probe(rowptr, col, val, xy, kind, rhs):
-    """Multifrontal symbolic analysis + host restatement of its numeric phase: returns (x, stats dict)."""
+def host_mf_probe(rowptr, col, val, xy, kind, rhs, pivot_window: int = 1):
+    """Multifrontal symbolic analysis + host restatement of its numeric phase: returns (x, stats dict).
+    pivot_window=1 is the GPU kernels' static pivoting; a large window = restricted partial pivoting."""
     lib = load_library()
+    lib.ocp_host_mf_set_pivot_window(int(pivot_window))
     n = rowptr.size - 1
     rp, ci = np.ascontiguousarray(rowptr, np.int32), np.ascontiguousarray(col, np.int32)
     v, c = np.ascontiguousarray(val, np.float64), np.ascontiguousarray(xy, np.float64)

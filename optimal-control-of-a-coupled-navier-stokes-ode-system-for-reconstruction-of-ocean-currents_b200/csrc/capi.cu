@@ -38,6 +38,7 @@ struct DirectSolver {
                 return true;
             }
             use_mf = false;   // front too large for the panel kernel: fall back to the library refactorisation
+            if (getenv("OCP_SOLVER_VERBOSE")) fprintf(stderr, "[ocp_b200] multifrontal unavailable (%s): using cusolverRf\n", e2.c_str());
         }
         rf.configure(n, nnz, h_rowptr, h_col, d_rowptr, d_col, xy, kind);
         return true;
@@ -52,6 +53,7 @@ struct DirectSolver {
     bool solve(double *d_x, cudaStream_t s, std::string &err) {
         return use_mf ? mf.solve(d_x, s, err) : rf.solve(d_x, s, err);
     }
+    bool check(std::string &err) { return use_mf ? mf.check(err) : true; }
 };
 
 struct ocp_ctx {
@@ -88,6 +90,7 @@ struct ocp_ctx {
     bool mass_factored = false;
     int adj_refine = 1;
     ocp_solver_stats stats{};
+    bool profile = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -145,11 +148,16 @@ int find_slot(const int *rowptr, const int *col, int r, int cidx) {
     return (p != e && *p == cidx) ? (int)(p - col) : -1;
 }
 
+// Per-phase CUDA-event timing (assembly / factor / solve line items).  Only active while profiling is switched on
+// (ocp_set_profiling): it synchronises after every phase, which the production path must not do.
 struct PhaseTimer {
     ocp_ctx *c;
     double *acc;
-    PhaseTimer(ocp_ctx *ctx, double *a) : c(ctx), acc(a) { cudaEventRecord(c->ev0, c->stream); }
+    PhaseTimer(ocp_ctx *ctx, double *a) : c(ctx), acc(a) {
+        if (c->profile) cudaEventRecord(c->ev0, c->stream);
+    }
     ~PhaseTimer() {
+        if (!c->profile) return;
         cudaEventRecord(c->ev1, c->stream);
         cudaEventSynchronize(c->ev1);
         float ms = 0.f;
@@ -218,6 +226,10 @@ void ocp_reset_solver_stats(ocp_ctx *ctx) {
     }
 }
 
+void ocp_set_profiling(ocp_ctx *ctx, int on) {
+    if (ctx) ctx->profile = on != 0;
+}
+
 void ocp_set_viscosity(ocp_ctx *ctx, double viscosity) {
     if (ctx) ctx->nu = viscosity;
 }
@@ -230,6 +242,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     ocp_ctx *c = new ocp_ctx();
     *out = c;   // returned even on failure so that the caller can read ocp_last_error, then destroy
     c->stream = (cudaStream_t)stream;
+    if (const char *ep = getenv("OCP_PROFILE")) c->profile = atoi(ep) != 0;
     c->nv = d->nv; c->nn = d->nn; c->nc = d->nc; c->ndofs = d->ndofs; c->nnz = d->nnz;
     c->n_dir = d->n_dirichlet; c->n_g1 = d->n_g1; c->nt = d->nt;
     c->nu = d->viscosity; c->dt = d->dt; c->cx = d->center_x; c->cy = d->center_y;
@@ -421,6 +434,7 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
         double ss;
         int rc = read_scalar(c, c->d_scalar, 1, &ss);
         if (rc != OCP_OK) return rc;
+        if (!c->lu_fwd.check(c->err)) return OCP_ERR_SOLVER;   // stream is idle here: pivot flag of the last factor
         r = std::sqrt(ss);
         if (it == 0) r0 = r;
         if (h_res_hist) h_res_hist[it] = r;
@@ -727,6 +741,8 @@ void ocp_selftest_facet_matrix(double len, double nx, double ny, const double *u
                                double *R6) {
     for (int r = 0; r < 6; ++r) facet_row(len, nx, ny, uv6, uv6 + 3, f6, f6 + 3, r, A36 + 6 * r, R6[r]);
 }
+
+void ocp_host_mf_set_pivot_window(int rows) { ocp::g_mf_host_window = rows < 1 ? 1 : rows; }
 
 int64_t ocp_host_mf_probe(int32_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *xy,
                           const uint8_t *kind, double *rhs_inout, double *stats8) {

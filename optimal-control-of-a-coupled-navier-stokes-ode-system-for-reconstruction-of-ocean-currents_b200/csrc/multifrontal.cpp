@@ -239,6 +239,8 @@ void mf_analyse(int n, const int *rowptr, const int *col, const double *xy, cons
     }
 }
 
+int g_mf_host_window = 1;   // pivot search window (rows): 1 = static pivoting like the device; larger = restricted partial pivoting
+
 bool mf_factor_host(const MFSymbolic &S, const double *vals, MFHostNumeric &N) {
     N.F.assign(S.fsize, 0.0);
     N.piv.assign(S.n, 0);
@@ -260,7 +262,8 @@ bool mf_factor_host(const MFSymbolic &S, const double *vals, MFHostNumeric &N) {
         for (int k = 0; k < np; ++k) {
             int p = k;
             double a = std::fabs(F[k + (size_t)k * m]);
-            for (int i = k + 1; i < np; ++i)
+            const int wend = (int)std::min<long long>(np, ((long long)(k / g_mf_host_window) + 1) * g_mf_host_window);
+            for (int i = k + 1; i < wend; ++i)
                 if (std::fabs(F[i + (size_t)k * m]) > a) {
                     a = std::fabs(F[i + (size_t)k * m]);
                     p = i;

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 
 #include "kernels.cuh"
 #include "multifrontal.cuh"
@@ -21,15 +22,15 @@ namespace ocp {
 namespace {
 
 constexpr int NB = 16;     // panel width
-constexpr int CW = 128;    // trailing-update column chunk
-constexpr int TF = 512;    // threads per front CTA
-constexpr int SB = 32;     // triangular-solve block (one warp)
+constexpr int CWO = 4;     // column-ownership granularity inside a cluster (= tile width)
 
 struct MFDev {
     const int *m, *np, *first, *idx_ptr, *idx, *child_ptr, *child, *rel_ptr, *rel;
     const long long *front_ptr;
     double *F;
     int *piv;
+    double *dinv;              // per 16-column panel: inverse of the unit-lower and of the upper diagonal block (2 x 256)
+    const int *dinv_ptr;       // per front: index of its first panel in dinv
 };
 
 __global__ void scatter_values_kernel(int nnz, const long long *__restrict__ dest, const double *__restrict__ vals,
@@ -38,19 +39,29 @@ __global__ void scatter_values_kernel(int nnz, const long long *__restrict__ des
     if (k < nnz) F[dest[k]] = vals[k];
 }
 
-// One CLUSTER of C CTAs per front (C = 1 for the many small fronts at the bottom of the tree, 8-16 for the few
-// large fronts near the root).  Per 16-column panel: CTA 0 factors the panel in its shared memory, the cluster
-// synchronises, then every CTA applies the row interchanges, solves U12 and updates the trailing matrix for the
-// column chunks it owns (chunk = absolute column index / cw, owner = chunk % C), and the cluster synchronises again.
-// All front accesses bypass L1 (ld.cg / st.cg): columns migrate between the panel owner (CTA 0) and chunk owners.
+// One CLUSTER of C CTAs per front (C = 1 for the many small fronts at the bottom of the tree, up to 16 for the few
+// large fronts near the root), one launch per tree level.
+//
+// Static pivoting: inside a front velocities precede pressures and every pressure dof sits above all velocities it
+// couples to (mf_analyse), so the velocity block is positive definite and each pressure pivot is a negative
+// definite Schur complement - LU in the given order is stable for the diffusion-dominated systems of this path
+// (validated against partial pivoting on the host, tests/test_capi_cpu.py) and nothing has to be searched or swapped.
+//
+// Per 16-column panel every CTA of the cluster redundantly (a) loads the panel, one row per thread, in registers,
+// (b) factors the 16x16 diagonal block inside warp 0 with shuffles, (c) turns its rows into L = A U11^{-1};
+// then it solves U12 and updates the trailing matrix only for the columns it owns (absolute column / 16 mod C).
+// One cluster barrier per panel publishes the updated columns.  Front accesses bypass L1 (ld.cg / st.cg).
+template <int TF, int RMAX>
 __global__ void __launch_bounds__(TF)
-mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int cw, int *info) {
+mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, long long *prof) {
     extern __shared__ double sm[];
-    __shared__ int s_piv[NB];
+    __shared__ double s_D[NB][NB + 1];            // factored diagonal block: L below, U on/above the diagonal
+    __shared__ double s_rd[NB];                   // reciprocals of its diagonal
     cg::cluster_group cl = cg::this_cluster();
     const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
-    double *P = sm;                              // panel, ld = mp
-    double *Uc = sm + (size_t)max_m * NB;        // NB x CW, row-major
+    const int ldu = max_m + CWO;                  // leading dimension of the U12 staging area
+    double *P = sm;                               // L panel, ld = mp
+    double *Uc = sm + (size_t)max_m * NB;         // NB x ldu, row-major, indexed by "own column" number
     const int s = nodes[blockIdx.x / C];
     const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
     double *F = d.F + d.front_ptr[s];
@@ -67,242 +78,388 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int cw, int 
     }
     cl.sync();
     if (np == 0) return;
-    int *gpiv = d.piv + d.first[s];
+    long long tp0 = 0, acc_panel = 0, acc_trail = 0, acc_sync = 0, acc_load = 0, acc_diag = 0, acc_trsm = 0;
+#define MF_TICK(accv) do { if (prof && tid == 0) { long long t_ = clock64(); accv += t_ - tp0; tp0 = t_; } } while (0)
+    if (prof && tid == 0) tp0 = clock64();
+    // own columns: chunk q covers absolute columns [(rank + q C) 16, +16); "own column number" = 16 q + (c % 16)
+    const int nown = (m > rank * CWO) ? (m - rank * CWO + C * CWO - 1) / (C * CWO) : 0;
     for (int k0 = 0; k0 < np; k0 += NB) {
-        const int kb = min(NB, np - k0), mp = m - k0;
-        for (int j = 0; j < kb; ++j)
-            for (int i = tid; i < mp; i += TF) P[i + j * mp] = __ldcg(F + (k0 + i) + (size_t)(k0 + j) * m);
-        if (rank == 0) {
-            __syncthreads();
-            // ---- panel factorisation, pivot rows restricted to the fully-summed block
-            for (int j = 0; j < kb; ++j) {
-                if (tid < 32) {
-                    double best = -1.0;
-                    int r = j;
-                    for (int i = j + tid; i < np - k0; i += 32) {
-                        const double a = fabs(P[i + j * mp]);
-                        if (a > best) {
-                            best = a;
-                            r = i;
-                        }
-                    }
+        const int kb = min(NB, np - k0), mp = m - k0, ctrail = k0 + kb;
+        // (a) panel rows into registers
+        double a[RMAX][NB];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                        const int orr = __shfl_xor_sync(0xffffffffu, r, o);
-                        if (ob > best || (ob == best && orr < r)) {
-                            best = ob;
-                            r = orr;
-                        }
-                    }
-                    if (tid == 0) {
-                        s_piv[j] = r;
-                        gpiv[k0 + j] = k0 + r;
-                        if (!(best > 0.0)) atomicExch(info, s + 1);
-                    }
-                }
-                __syncthreads();
-                const int r = s_piv[j];
-                if (r != j && tid < kb) {
-                    const double t = P[j + tid * mp];
-                    P[j + tid * mp] = P[r + tid * mp];
-                    P[r + tid * mp] = t;
-                }
-                __syncthreads();
-                const double inv = 1.0 / P[j + j * mp];
-                for (int i = j + 1 + tid; i < mp; i += TF) {
-                    const double l = P[i + j * mp] * inv;
-                    P[i + j * mp] = l;
-                    for (int jj = j + 1; jj < kb; ++jj) P[i + jj * mp] -= l * P[j + jj * mp];
-                }
-                __syncthreads();
-            }
-            for (int j = 0; j < kb; ++j)
-                for (int i = tid; i < mp; i += TF) __stcg(F + (k0 + i) + (size_t)(k0 + j) * m, P[i + j * mp]);
+        for (int q = 0; q < RMAX; ++q) {
+            const int i = tid + q * TF;
+#pragma unroll
+            for (int jj = 0; jj < NB; ++jj)
+                a[q][jj] = (i < mp && jj < kb) ? __ldcg(F + (k0 + i) + (size_t)(k0 + jj) * m) : 0.0;
         }
-        cl.sync();
-        if (rank != 0) {
-            // the factored panel and its pivots, written by CTA 0
-            for (int j = 0; j < kb; ++j)
-                for (int i = tid; i < mp; i += TF) P[i + j * mp] = __ldcg(F + (k0 + i) + (size_t)(k0 + j) * m);
-            if (tid < kb) s_piv[tid] = __ldcg(gpiv + k0 + tid) - k0;
+        if (prof) { __syncthreads(); MF_TICK(acc_load); }
+        // (b) diagonal block inside warp 0: lane i holds row i.  The dependent chain per step is
+        // pivot -> reciprocal -> multiplier -> update of the NEXT pivot, so the next pivot column is updated first
+        // and its reciprocal is started before the remaining columns of the step are touched.
+        if (tid < 32) {
+            double r[NB];
+#pragma unroll
+            for (int jj = 0; jj < NB; ++jj) r[jj] = (tid < kb) ? a[0][jj] : ((jj == tid) ? 1.0 : 0.0);   // pad with identity
+            double rinv = __drcp_rn(__shfl_sync(0xffffffffu, r[0], 0));
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                if (tid == j) {
+                    s_rd[j] = rinv;
+                    if (j < kb && !(fabs(rinv) < 1e280)) atomicExch(info, s + 1);
+                }
+                const bool below = tid > j;
+                const double l = r[j] * rinv;
+                if (below) r[j] = l;
+                double rnext = 0.0;
+                if (j + 1 < NB) {
+                    const double u1 = __shfl_sync(0xffffffffu, r[j + 1], j);
+                    if (below) r[j + 1] = fma(-l, u1, r[j + 1]);
+                    rnext = __drcp_rn(__shfl_sync(0xffffffffu, r[j + 1], j + 1));
+                }
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+                    if (jj > j + 1) {
+                        const double u = __shfl_sync(0xffffffffu, r[jj], j);
+                        if (below) r[jj] = fma(-l, u, r[jj]);
+                    }
+                }
+                rinv = rnext;
+            }
+            if (tid < NB) {
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) s_D[tid][jj] = r[jj];
+            }
+            if (tid < kb) {
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) a[0][jj] = r[jj];
+            }
         }
         __syncthreads();
-        // ---- own column chunks: row interchanges, U12 = L11^{-1} F12, trailing update
-        const int nrow = m - k0 - kb;
-        for (int cbeg = rank * cw; cbeg < m; cbeg += C * cw) {
-            const int cend = min(m, cbeg + cw);
-            const int lo = max(cbeg, k0 + kb);        // first trailing column of this chunk
-            const int c = cbeg + tid;
-            if (c < cend && !(c >= k0 && c < k0 + kb)) {
-                double *colp = F + (size_t)c * m + k0;
-                for (int j = 0; j < kb; ++j) {
-                    const int r = s_piv[j];
-                    if (r != j) {
-                        const double t = __ldcg(colp + j);
-                        __stcg(colp + j, __ldcg(colp + r));
-                        __stcg(colp + r, t);
-                    }
-                }
-                if (c >= k0 + kb) {
-                    double u[NB];
+        MF_TICK(acc_diag);
+        // (b') CTA 0: its two last warps invert the diagonal block (unit-lower and upper factor) for the triangular
+        // solves, which then need no sequential substitution inside a block
+        if (rank == 0 && tid >= TF - 64) {
+            const int lane = tid & 31, which = (tid >> 5) & 1;      // 1: L^{-1}, 0: U^{-1}
+            double X[NB];
 #pragma unroll
-                    for (int t = 0; t < NB; ++t) u[t] = t < kb ? __ldcg(colp + t) : 0.0;
+            for (int c = 0; c < NB; ++c) X[c] = (c == lane) ? 1.0 : 0.0;
+            if (which) {
 #pragma unroll
-                    for (int t = 1; t < NB; ++t) {
-                        if (t < kb) {
-                            double a = u[t];
+                for (int k = 0; k < NB; ++k) {
+                    const double lik = (lane > k && lane < kb && k < kb) ? s_D[lane < NB ? lane : 0][k] : 0.0;
 #pragma unroll
-                            for (int tt = 0; tt < NB; ++tt)
-                                if (tt < t) a -= P[t + tt * mp] * u[tt];
-                            u[t] = a;
+                    for (int c = 0; c < NB; ++c) {
+                        if (c <= k) {
+                            const double xkc = __shfl_sync(0xffffffffu, X[c], k);
+                            X[c] = fma(-lik, xkc, X[c]);
                         }
                     }
+                }
+            } else {
+#pragma unroll
+                for (int k = NB - 1; k >= 0; --k) {
+                    const bool live = k < kb;
+                    if (lane == k && live) {
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) X[c] *= s_rd[k];
+                    }
+                    const double uik = (lane < k && live) ? s_D[lane][k] : 0.0;
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) {
+                        if (c >= k) {
+                            const double ykc = __shfl_sync(0xffffffffu, X[c], k);
+                            X[c] = fma(-uik, ykc, X[c]);
+                        }
+                    }
+                }
+            }
+            if (lane < NB) {
+                double *dst = d.dinv + ((size_t)d.dinv_ptr[s] + k0 / NB) * (2 * NB * NB) + (which ? 0 : NB * NB) + lane * NB;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) dst[c] = X[c];
+            }
+        }
+        // (c) rows below the block: L = A U11^{-1}; every row goes to the shared panel, CTA 0 also writes the factor
+#pragma unroll
+        for (int q = 0; q < RMAX; ++q) {
+            const int i = tid + q * TF;
+            if (i < mp) {
+                if (i >= kb) {
 #pragma unroll
                     for (int t = 0; t < NB; ++t) {
-                        if (t < kb) __stcg(colp + t, u[t]);
-                        Uc[t * CW + (c - lo)] = u[t];
-                    }
-                }
-            }
-            __syncthreads();
-            const int ncol = cend - lo;
-            if (nrow > 0 && ncol > 0) {
-                const int tr = (nrow + 3) >> 2, tc = (ncol + 3) >> 2;
-                for (int tile = tid; tile < tr * tc; tile += TF) {
-                    const int ti = tile % tr, tj = tile / tr;
-                    const int i0 = kb + 4 * ti, cc0 = 4 * tj;
-                    double f[4][4], acc[4][4];
+                        if (t < kb) {
+                            const double l = a[q][t] * s_rd[t];
+                            a[q][t] = l;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const double *colp = F + (size_t)(lo + cc0 + b) * m + k0;
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            f[a][b] = (cc0 + b < ncol && i0 + a < mp) ? __ldcg(colp + i0 + a) : 0.0;
-                            acc[a][b] = 0.0;
-                        }
-                    }
-                    for (int t = 0; t < kb; ++t) {
-                        double l[4], uu[4];
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) l[a] = (i0 + a < mp) ? P[i0 + a + t * mp] : 0.0;
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) uu[b] = (cc0 + b < ncol) ? Uc[t * CW + cc0 + b] : 0.0;
-#pragma unroll
-                        for (int a = 0; a < 4; ++a)
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) acc[a][b] = fma(l[a], uu[b], acc[a][b]);
-                    }
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        if (cc0 + b < ncol) {
-                            double *colp = F + (size_t)(lo + cc0 + b) * m + k0;
-#pragma unroll
-                            for (int a = 0; a < 4; ++a)
-                                if (i0 + a < mp) __stcg(colp + i0 + a, f[a][b] - acc[a][b]);
+                            for (int jj = 0; jj < NB; ++jj)
+                                if (jj > t && jj < kb) a[q][jj] = fma(-l, s_D[t][jj], a[q][jj]);
                         }
                     }
                 }
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+                    if (jj < kb) {
+                        P[i + jj * mp] = a[q][jj];
+                        if (rank == 0) __stcg(F + (k0 + i) + (size_t)(k0 + jj) * m, a[q][jj]);
+                    }
+                }
             }
-            __syncthreads();
         }
+        if (prof) { __syncthreads(); MF_TICK(acc_trsm); }
+        // (d) U12 = L11^{-1} F12 for the own trailing columns
+        for (int idx = TF - 1 - tid; idx < nown * CWO; idx += TF) {
+            const int c = (rank + (idx / CWO) * C) * CWO + (idx % CWO);
+            if (c >= ctrail && c < m) {
+                double *colp = F + (size_t)c * m + k0;
+                double u[NB];
+#pragma unroll
+                for (int t = 0; t < NB; ++t) u[t] = t < kb ? __ldcg(colp + t) : 0.0;
+#pragma unroll
+                for (int t = 0; t < NB; ++t) {
+                    if (t < kb) {
+#pragma unroll
+                        for (int tt = 0; tt < NB; ++tt)
+                            if (tt > t && tt < kb) u[tt] = fma(-s_D[tt][t], u[t], u[tt]);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < NB; ++t) {
+                    if (t < kb) __stcg(colp + t, u[t]);
+                    Uc[t * ldu + idx] = u[t];
+                }
+            }
+        }
+        __syncthreads();
+        MF_TICK(acc_panel);
+        // (e) trailing update of the own columns, 4x4 register tiles
+        const int nrow = m - ctrail;
+        if (nrow > 0 && nown > 0) {
+            // first own chunk that still has trailing columns
+            int q0 = 0;
+            while (q0 < nown && (rank + q0 * C) * CWO + CWO <= ctrail) ++q0;
+            const int tr = (nrow + 3) >> 2, tc = (nown - q0) * (CWO / 4);
+            for (int tile = tid; tile < tr * tc; tile += TF) {
+                const int ti = tile % tr, tj = tile / tr;
+                const int i0 = kb + 4 * ti, idx0 = q0 * CWO + 4 * tj;
+                const int c0 = (rank + (idx0 / CWO) * C) * CWO + (idx0 % CWO);
+                double f[4][4], acc[4][4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const double *colp = F + (size_t)(c0 + b) * m + k0;
+                    const bool cv = c0 + b >= ctrail && c0 + b < m;
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) {
+                        f[aa][b] = (cv && i0 + aa < mp) ? __ldcg(colp + i0 + aa) : 0.0;
+                        acc[aa][b] = 0.0;
+                    }
+                }
+                for (int t = 0; t < kb; ++t) {
+                    double l[4], uu[4];
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) l[aa] = (i0 + aa < mp) ? P[i0 + aa + t * mp] : 0.0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) uu[b] = Uc[t * ldu + idx0 + b];
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[aa][b] = fma(l[aa], uu[b], acc[aa][b]);
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (c0 + b >= ctrail && c0 + b < m) {
+                        double *colp = F + (size_t)(c0 + b) * m + k0;
+#pragma unroll
+                        for (int aa = 0; aa < 4; ++aa)
+                            if (i0 + aa < mp) __stcg(colp + i0 + aa, f[aa][b] - acc[aa][b]);
+                    }
+                }
+            }
+        }
+        MF_TICK(acc_trail);
         cl.sync();
+        MF_TICK(acc_sync);
+    }
+    if (prof && tid == 0) {
+        if (rank == 0) {
+            long long v[6] = {acc_load, acc_diag, acc_trsm, acc_panel, acc_trail, acc_sync};
+            for (int k = 0; k < 6; ++k) atomicAdd((unsigned long long *)prof + k, (unsigned long long)v[k]);
+        }
     }
 }
 
-// forward substitution of one level: y_P = L11^{-1} Pi b_P,  b_U -= L21 y_P
-__global__ void __launch_bounds__(TF)
+// Triangular solves, one CTA per front and one launch per level.  Inside a front the pivot block is processed in
+// 16-row blocks: the block itself is a 16x16 mat-vec with the inverse stored by the factorisation (warp 0), the rows
+// outside the block are updated by all threads with the 16 block values; the matrix entries of the NEXT block are
+// loaded into registers while the current one is being applied.
+constexpr int TS = 512;    // threads per CTA in the solve kernels
+
+// forward: y_P = L11^{-1} b_P,  b_U -= L21 y_P      (RS = rows per thread: 1 for fronts <= 512, 2 up to 1024)
+template <int RS>
+__global__ void __launch_bounds__(TS)
 mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x) {
     extern __shared__ double y[];
+    __shared__ double yb[NB];
     const int s = nodes[blockIdx.x];
     const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
     if (np == 0) return;
     const double *F = d.F + d.front_ptr[s];
     const int *I = d.idx + d.idx_ptr[s];
-    const int *gpiv = d.piv + d.first[s];
-    for (int k = tid; k < m; k += TF) y[k] = k < np ? x[I[k]] : 0.0;
+    const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB);
+    for (int k = tid; k < m; k += TS) y[k] = k < np ? x[I[k]] : 0.0;
+    double lc[RS][NB], ln[RS][NB];
+#pragma unroll
+    for (int q = 0; q < RS; ++q) {
+        const int i = tid + q * TS;
+#pragma unroll
+        for (int t = 0; t < NB; ++t) lc[q][t] = (i < m && i >= min(NB, np) && t < np) ? __ldcg(F + i + (size_t)t * m) : 0.0;
+    }
+    double dl[NB];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) dl[t] = (tid < NB) ? __ldcg(Dinv + tid * NB + t) : 0.0;
     __syncthreads();
-    if (tid == 0) {
-        for (int k = 0; k < np; ++k) {
-            const int r = gpiv[k];
-            if (r != k) {
-                const double t = y[k];
-                y[k] = y[r];
-                y[r] = t;
+    const int nblk = (np + NB - 1) / NB;
+    for (int b = 0; b < nblk; ++b) {
+        const int k0 = b * NB, kb = min(NB, np - k0), k1 = k0 + NB;
+        // prefetch the next block's columns / inverse (rows below the next block; its last block may be partial)
+        if (b + 1 < nblk) {
+            const int rnext = k1 + min(NB, np - k1);
+#pragma unroll
+            for (int q = 0; q < RS; ++q) {
+                const int i = tid + q * TS;
+#pragma unroll
+                for (int t = 0; t < NB; ++t)
+                    ln[q][t] = (i < m && i >= rnext && k1 + t < np) ? __ldcg(F + i + (size_t)(k1 + t) * m) : 0.0;
             }
         }
-    }
-    __syncthreads();
-    for (int k0 = 0; k0 < np; k0 += SB) {
-        const int kb = min(SB, np - k0);
-        if (tid < 32) {
-            double Lr[SB];
+        if (tid < NB) {
+            double v = 0.0;
 #pragma unroll
-            for (int t = 0; t < SB; ++t) Lr[t] = (tid < kb && t < tid) ? F[(k0 + tid) + (size_t)(k0 + t) * m] : 0.0;
-            double v = tid < kb ? y[k0 + tid] : 0.0;
-#pragma unroll
-            for (int t = 0; t < SB; ++t) {
-                const double vt = __shfl_sync(0xffffffffu, v, t);
-                if (t < kb && tid > t) v -= Lr[t] * vt;
+            for (int t = 0; t < NB; ++t) v = fma(dl[t], (t < kb) ? y[k0 + t] : 0.0, v);
+            __syncwarp(0xffffu);
+            if (tid < kb) {
+                yb[tid] = v;
+                y[k0 + tid] = v;
             }
-            if (tid < kb) y[k0 + tid] = v;
+            if (b + 1 < nblk) {
+#pragma unroll
+                for (int t = 0; t < NB; ++t) dl[t] = __ldcg(Dinv + (size_t)(b + 1) * (2 * NB * NB) + tid * NB + t);
+            }
         }
         __syncthreads();
-        for (int i = k0 + kb + tid; i < m; i += TF) {
-            double acc = 0.0;
-            for (int t = 0; t < kb; ++t) acc = fma(F[i + (size_t)(k0 + t) * m], y[k0 + t], acc);
-            y[i] -= acc;
+#pragma unroll
+        for (int q = 0; q < RS; ++q) {
+            const int i = tid + q * TS;
+            if (i < m && i >= k0 + kb) {
+                double acc = 0.0;
+#pragma unroll
+                for (int t = 0; t < NB; ++t) acc = fma(lc[q][t], (t < kb) ? yb[t] : 0.0, acc);
+                y[i] -= acc;
+            }
         }
         __syncthreads();
+#pragma unroll
+        for (int q = 0; q < RS; ++q)
+#pragma unroll
+            for (int t = 0; t < NB; ++t) lc[q][t] = ln[q][t];
     }
-    for (int k = tid; k < np; k += TF) x[I[k]] = y[k];
-    for (int i = np + tid; i < m; i += TF) atomicAdd(x + I[i], y[i]);
+    for (int k = tid; k < np; k += TS) x[I[k]] = y[k];
+    for (int i = np + tid; i < m; i += TS) atomicAdd(x + I[i], y[i]);
 }
 
-// backward substitution of one level: x_P = U11^{-1} (y_P - U12 x_U)
-__global__ void __launch_bounds__(TF)
+// backward: x_P = U11^{-1} (y_P - U12 x_U)
+template <int RS>
+__global__ void __launch_bounds__(TS)
 mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x) {
     extern __shared__ double y[];
+    __shared__ double yb[NB];
     const int s = nodes[blockIdx.x];
     const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
     if (np == 0) return;
     const double *F = d.F + d.front_ptr[s];
     const int *I = d.idx + d.idx_ptr[s];
-    for (int k = tid; k < m; k += TF) y[k] = x[I[k]];
+    const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + NB * NB;
+    for (int k = tid; k < m; k += TS) y[k] = x[I[k]];
+    const int nblk = (np + NB - 1) / NB;
+    double uc[RS][NB], un[RS][NB];
+    {
+        const int k0 = (nblk - 1) * NB;
+#pragma unroll
+        for (int q = 0; q < RS; ++q) {
+            const int i = tid + q * TS;
+#pragma unroll
+            for (int t = 0; t < NB; ++t) uc[q][t] = (i < k0 && k0 + t < np) ? __ldcg(F + i + (size_t)(k0 + t) * m) : 0.0;
+        }
+    }
+    double du[NB];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) du[t] = (tid < NB) ? __ldcg(Dinv + (size_t)(nblk - 1) * (2 * NB * NB) + tid * NB + t) : 0.0;
     __syncthreads();
-    for (int k = tid; k < np; k += TF) {
-        double acc = 0.0;
-        for (int j = np; j < m; ++j) acc = fma(F[k + (size_t)j * m], y[j], acc);
-        y[k] -= acc;
+    // y_P -= U12 x_U: thread per pivot row, x_U in shared memory
+    for (int k = tid; k < np; k += TS) {
+        double a0 = 0.0, a1 = 0.0;
+        int j = np;
+        for (; j + 1 < m; j += 2) {
+            a0 = fma(__ldcg(F + k + (size_t)j * m), y[j], a0);
+            a1 = fma(__ldcg(F + k + (size_t)(j + 1) * m), y[j + 1], a1);
+        }
+        if (j < m) a0 = fma(__ldcg(F + k + (size_t)j * m), y[j], a0);
+        y[k] -= a0 + a1;
     }
     __syncthreads();
-    const int nblk = (np + SB - 1) / SB;
     for (int b = nblk - 1; b >= 0; --b) {
-        const int k0 = b * SB, kb = min(SB, np - k0);
-        if (tid < 32) {
-            double Ur[SB];
+        const int k0 = b * NB, kb = min(NB, np - k0);
+        if (b > 0) {
+            const int kp = k0 - NB;
 #pragma unroll
-            for (int t = 0; t < SB; ++t) Ur[t] = (tid < kb && t < kb && t >= tid) ? F[(k0 + tid) + (size_t)(k0 + t) * m] : 1.0;
-            double v = tid < kb ? y[k0 + tid] : 0.0;
+            for (int q = 0; q < RS; ++q) {
+                const int i = tid + q * TS;
 #pragma unroll
-            for (int t = SB - 1; t >= 0; --t) {
-                if (t < kb) {
-                    if (tid == t) v = v / Ur[t];
-                    const double vt = __shfl_sync(0xffffffffu, v, t);
-                    if (tid < t) v -= Ur[t] * vt;
-                }
+                for (int t = 0; t < NB; ++t) un[q][t] = (i < kp) ? __ldcg(F + i + (size_t)(kp + t) * m) : 0.0;
             }
-            if (tid < kb) y[k0 + tid] = v;
+        }
+        if (tid < NB) {
+            double v = 0.0;
+#pragma unroll
+            for (int t = 0; t < NB; ++t) v = fma(du[t], (t < kb) ? y[k0 + t] : 0.0, v);
+            __syncwarp(0xffffu);
+            if (tid < kb) {
+                yb[tid] = v;
+                y[k0 + tid] = v;
+            }
+            if (b > 0) {
+#pragma unroll
+                for (int t = 0; t < NB; ++t) du[t] = __ldcg(Dinv + (size_t)(b - 1) * (2 * NB * NB) + tid * NB + t);
+            }
         }
         __syncthreads();
-        for (int i = tid; i < k0; i += TF) {
-            double acc = 0.0;
-            for (int t = 0; t < kb; ++t) acc = fma(F[i + (size_t)(k0 + t) * m], y[k0 + t], acc);
-            y[i] -= acc;
+#pragma unroll
+        for (int q = 0; q < RS; ++q) {
+            const int i = tid + q * TS;
+            if (i < k0) {
+                double acc = 0.0;
+#pragma unroll
+                for (int t = 0; t < NB; ++t) acc = fma(uc[q][t], (t < kb) ? yb[t] : 0.0, acc);
+                y[i] -= acc;
+            }
         }
         __syncthreads();
+#pragma unroll
+        for (int q = 0; q < RS; ++q)
+#pragma unroll
+            for (int t = 0; t < NB; ++t) uc[q][t] = un[q][t];
     }
-    for (int k = tid; k < np; k += TF) x[I[k]] = y[k];
+    for (int k = tid; k < np; k += TS) x[I[k]] = y[k];
+}
+
+// kernel variants: <threads, panel rows per thread>
+enum { kVarSmall = 0, kVarMid = 1, kVarBig = 2 };
+inline int factor_variant(int max_m) { return max_m <= 256 ? kVarSmall : (max_m <= 512 ? kVarMid : kVarBig); }
+inline int variant_threads(int v) { return v == kVarSmall ? 256 : 512; }
+typedef void (*FactorKernel)(MFDev, const int *, int, int *, long long *);
+inline FactorKernel factor_kernel(int v) {
+    return v == kVarSmall ? mf_factor_kernel<256, 1> : (v == kVarMid ? mf_factor_kernel<512, 1> : mf_factor_kernel<512, 2>);
 }
 
 template <class T>
@@ -324,13 +481,56 @@ struct MultifrontalLU::Impl {
     int *m = nullptr, *np = nullptr, *first = nullptr, *idx_ptr = nullptr, *idx = nullptr, *child_ptr = nullptr,
         *child = nullptr, *rel_ptr = nullptr, *rel = nullptr, *level_nodes = nullptr, *piv = nullptr, *info = nullptr;
     long long *front_ptr = nullptr, *a_dest = nullptr;
-    double *F = nullptr;
+    double *F = nullptr, *dinv = nullptr;
+    int *dinv_ptr = nullptr;
+    long long *prof = nullptr;   // optional per-level phase cycle counters (OCP_MF_PROF=1)
     std::vector<int> level_max_m, level_cluster, level_cw;
+    // CUDA graphs of the factor / solve launch sequences, keyed by the (fixed) device pointer they operate on
+    std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs;
+    cudaStream_t cap_stream = nullptr;
+    bool use_graphs = true;
+    int *h_info = nullptr;       // pinned: zero-pivot flag of the most recent factorisations (checked lazily)
     MFDev dev{};
     ~Impl() {
         void *p[] = {m, np, first, idx_ptr, idx, child_ptr, child, rel_ptr, rel, level_nodes, piv, info, front_ptr,
-                     a_dest, F};
+                     a_dest, F, prof, dinv, dinv_ptr};
         for (void *q : p) cudaFree(q);
+        for (auto &kv : factor_graphs) cudaGraphExecDestroy(kv.second);
+        for (auto &kv : solve_graphs) cudaGraphExecDestroy(kv.second);
+        if (cap_stream) cudaStreamDestroy(cap_stream);
+        if (h_info) cudaFreeHost(h_info);
+    }
+    bool enqueue_factor(const double *d_vals, int nnz, cudaStream_t s, std::string &err);
+    bool enqueue_solve(double *d_x, cudaStream_t s, std::string &err);
+    template <class Fn>
+    bool run(std::map<const void *, cudaGraphExec_t> &cache, const void *key, cudaStream_t s, std::string &err, Fn enqueue) {
+        if (!use_graphs || prof) return enqueue(s);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            cudaGraph_t g = nullptr;
+            cudaGraphExec_t ge = nullptr;
+            if (cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                use_graphs = false;
+                return enqueue(s);
+            }
+            const bool ok = enqueue(cap_stream);
+            cudaError_t e = cudaStreamEndCapture(cap_stream, &g);
+            if (ok && e == cudaSuccess) e = cudaGraphInstantiate(&ge, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (!ok || e != cudaSuccess) {
+                cudaGetLastError();
+                use_graphs = false;      // capture not possible here: plain launches from now on
+                return enqueue(s);
+            }
+            it = cache.emplace(key, ge).first;
+        }
+        cudaError_t e = cudaGraphLaunch(it->second, s);
+        if (e != cudaSuccess) {
+            err = std::string("multifrontal graph launch: ") + cudaGetErrorString(e);
+            return false;
+        }
+        return true;
     }
 };
 
@@ -356,8 +556,8 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     for (int l = 0; l < S.nlevels; ++l)
         for (int k = S.level_ptr[l]; k < S.level_ptr[l + 1]; ++k)
             I.level_max_m[l] = std::max(I.level_max_m[l], S.m[S.level_nodes[k]]);
-    const size_t need = ((size_t)S.max_front * NB + (size_t)NB * CW) * sizeof(double);
-    if (need > 220 * 1024) {
+    const size_t need = ((size_t)S.max_front * NB + (size_t)NB * (S.max_front + CWO)) * sizeof(double);
+    if (need > 200 * 1024 || S.max_front > 1024) {
         err = "multifrontal: largest front (" + std::to_string(S.max_front) + ") exceeds the shared-memory panel";
         return false;
     }
@@ -371,10 +571,11 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     if (e == cudaSuccess) e = cudaMalloc((void **)&I.piv, sizeof(int) * std::max(n, 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&I.info, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(I.info, 0, sizeof(int));
-    if (e == cudaSuccess)
-        // the attribute is per kernel, not per solver instance: always allow the full opt-in budget
-        e = cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    // the attributes are per kernel, not per solver instance: always allow the full opt-in budget
+    for (int v = 0; v < 3 && e == cudaSuccess; ++v) {
+        e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    }
     // cluster size per level: as many CTAs per front as the chip has room for (powers of two, <= 16)
     int max_cluster = 16;
     if (const char *envc = getenv("OCP_MF_MAX_CLUSTER")) max_cluster = std::max(1, atoi(envc));
@@ -383,12 +584,12 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     for (int l = 0; l < S.nlevels && e == cudaSuccess; ++l) {
         const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
         int c = 1;
-        while (c * 2 <= max_cluster && nf * c * 2 <= 148 && c * 2 * 16 <= I.level_max_m[l]) c *= 2;
+        while (c * 2 <= max_cluster && nf * c * 2 <= 148 && c * 2 * 8 <= I.level_max_m[l]) c *= 2;
         while (c > 1) {   // make sure the cluster shape is launchable with this kernel's resources
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(nf * c);
-            cfg.blockDim = dim3(TF);
-            cfg.dynamicSmemBytes = ((size_t)I.level_max_m[l] * NB + (size_t)NB * CW) * sizeof(double);
+            cfg.blockDim = dim3(variant_threads(factor_variant(I.level_max_m[l])));
+            cfg.dynamicSmemBytes = ((size_t)I.level_max_m[l] * NB + (size_t)NB * (I.level_max_m[l] + CWO)) * sizeof(double);
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = c;
@@ -397,18 +598,40 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
             cfg.attrs = at;
             cfg.numAttrs = 1;
             int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, mf_factor_kernel, &cfg) == cudaSuccess && ncl >= 1) break;
+            cudaError_t oe = cudaOccupancyMaxActiveClusters(&ncl, factor_kernel(factor_variant(I.level_max_m[l])), &cfg);
+            if (oe == cudaSuccess && ncl >= 1) break;
             cudaGetLastError();
             c /= 2;
         }
         I.level_cluster[l] = c;
-        I.level_cw[l] = (c >= 16) ? 16 : 32;
     }
     if (e != cudaSuccess) {
         err = std::string("multifrontal setup: ") + cudaGetErrorString(e);
+        cudaGetLastError();
         return false;
     }
-    I.dev = MFDev{I.m, I.np, I.first, I.idx_ptr, I.idx, I.child_ptr, I.child, I.rel_ptr, I.rel, I.front_ptr, I.F, I.piv};
+    if (const char *eg = getenv("OCP_MF_GRAPHS")) I.use_graphs = atoi(eg) != 0;
+    if (cudaStreamCreateWithFlags(&I.cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void **)&I.h_info, sizeof(int)) != cudaSuccess) {
+        err = "multifrontal setup: stream / pinned allocation failed";
+        return false;
+    }
+    *I.h_info = 0;
+    if (getenv("OCP_MF_PROF")) {
+        cudaMalloc((void **)&I.prof, sizeof(long long) * 8 * S.nlevels);
+        cudaMemset(I.prof, 0, sizeof(long long) * 8 * S.nlevels);
+    }
+    {
+        std::vector<int> dp(S.nnodes + 1, 0);
+        for (int k = 0; k < S.nnodes; ++k) dp[k + 1] = dp[k] + (S.np[k] + NB - 1) / NB;
+        if (!up(&I.dinv_ptr, dp, err)) return false;
+        if (cudaMalloc((void **)&I.dinv, sizeof(double) * 2 * NB * NB * std::max(dp[S.nnodes], 1)) != cudaSuccess) {
+            err = "multifrontal setup: out of memory";
+            return false;
+        }
+    }
+    I.dev = MFDev{I.m, I.np, I.first, I.idx_ptr, I.idx, I.child_ptr, I.child, I.rel_ptr, I.rel, I.front_ptr, I.F, I.piv,
+                  I.dinv, I.dinv_ptr};
     factor_nnz_ = 0;
     for (int s = 0; s < S.nnodes; ++s)
         factor_nnz_ += (long long)S.m[s] * S.m[s] - (long long)(S.m[s] - S.np[s]) * (S.m[s] - S.np[s]);
@@ -419,23 +642,18 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     return true;
 }
 
-bool MultifrontalLU::factor(const double *d_vals, cudaStream_t s, std::string &err) {
-    if (!impl_) {
-        err = "MultifrontalLU::factor before configure";
-        return false;
-    }
-    Impl &I = *impl_;
-    const MFSymbolic &S = I.S;
-    cudaMemsetAsync(I.F, 0, sizeof(double) * S.fsize, s);
-    g_launch_count.fetch_add(1 + S.nlevels, std::memory_order_relaxed);
-    scatter_values_kernel<<<(nnz_ + 255) / 256, 256, 0, s>>>(nnz_, I.a_dest, d_vals, I.F);
+bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStream_t s, std::string &err) {
+    const MFSymbolic &S = this->S;
+    cudaMemsetAsync(F, 0, sizeof(double) * S.fsize, s);
+    scatter_values_kernel<<<(nnz + 255) / 256, 256, 0, s>>>(nnz, a_dest, d_vals, F);
     for (int l = 0; l < S.nlevels; ++l) {
         const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
-        const int c = I.level_cluster[l];
+        const int c = level_cluster[l];
         cudaLaunchConfig_t cfg = {};
+        const int var = factor_variant(level_max_m[l]);
         cfg.gridDim = dim3(nf * c);
-        cfg.blockDim = dim3(TF);
-        cfg.dynamicSmemBytes = ((size_t)I.level_max_m[l] * NB + (size_t)NB * CW) * sizeof(double);
+        cfg.blockDim = dim3(variant_threads(var));
+        cfg.dynamicSmemBytes = ((size_t)level_max_m[l] * NB + (size_t)NB * (level_max_m[l] + CWO)) * sizeof(double);
         cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
@@ -444,26 +662,78 @@ bool MultifrontalLU::factor(const double *d_vals, cudaStream_t s, std::string &e
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, mf_factor_kernel, I.dev, (const int *)(I.level_nodes + S.level_ptr[l]),
-                                            I.level_max_m[l], I.level_cw[l], I.info);
+        long long *lprof = this->prof ? this->prof + 8 * l : nullptr;
+        const int *lvl = level_nodes + S.level_ptr[l];
+        cudaError_t le = cudaLaunchKernelEx(&cfg, factor_kernel(var), dev, lvl, level_max_m[l], info, lprof);
         if (le != cudaSuccess) {
             err = std::string("multifrontal factor launch (level ") + std::to_string(l) + ", cluster " +
                   std::to_string(c) + "): " + cudaGetErrorString(le);
             return false;
         }
     }
-    int info = 0;
-    cudaError_t e = cudaMemcpyAsync(&info, I.info, sizeof(int), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, s);
+    return true;
+}
+
+bool MultifrontalLU::factor(const double *d_vals, cudaStream_t s, std::string &err) {
+    if (!impl_) {
+        err = "MultifrontalLU::factor before configure";
+        return false;
+    }
+    Impl &I = *impl_;
+    if (!check(err)) return false;
+    g_launch_count.fetch_add(1 + I.S.nlevels, std::memory_order_relaxed);
+    const int nnz = nnz_;
+    if (!I.run(I.factor_graphs, d_vals, s, err, [&](cudaStream_t q) { return I.enqueue_factor(d_vals, nnz, q, err); }))
+        return false;
+    if (I.prof) {
+        const MFSymbolic &S = I.S;
+        cudaStreamSynchronize(s);
+        std::vector<long long> h(8 * S.nlevels);
+        cudaMemcpy(h.data(), I.prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+        cudaMemset(I.prof, 0, sizeof(long long) * h.size());
+        for (int l = 0; l < S.nlevels; ++l)
+            fprintf(stderr, "[mf prof] level %d fronts %d cluster %d | CTA0 cycles: load %lld diag %lld trsm %lld u12 %lld trail %lld sync %lld\n",
+                    l, S.level_ptr[l + 1] - S.level_ptr[l], I.level_cluster[l], h[8 * l], h[8 * l + 1], h[8 * l + 2],
+                    h[8 * l + 3], h[8 * l + 4], h[8 * l + 5]);
+    }
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         err = std::string("multifrontal factor: ") + cudaGetErrorString(e);
         return false;
     }
-    if (info != 0) {
-        err = "multifrontal factor: zero pivot in front " + std::to_string(info - 1);
-        cudaMemsetAsync(I.info, 0, sizeof(int), s);
+    return true;
+}
+
+// Zero-pivot flag of factorisations that have already completed (never blocks: the flag is copied to pinned host
+// memory at the end of every factorisation and inspected by the next factor / solve call or by the caller after
+// it has synchronised the stream).
+bool MultifrontalLU::check(std::string &err) {
+    if (impl_ && impl_->h_info && *impl_->h_info != 0) {
+        err = "multifrontal factor: zero pivot in front " + std::to_string(*impl_->h_info - 1) +
+              " (static pivoting broke down; run with OCP_SOLVER=rf)";
+        *impl_->h_info = 0;
+        cudaMemsetAsync(impl_->info, 0, sizeof(int), nullptr);
         return false;
+    }
+    return true;
+}
+
+bool MultifrontalLU::Impl::enqueue_solve(double *d_x, cudaStream_t s, std::string &err) {
+    const MFSymbolic &S = this->S;
+    for (int l = 0; l < S.nlevels; ++l) {
+        const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
+        if (level_max_m[l] <= TS)
+            mf_forward_kernel<1><<<nf, TS, sizeof(double) * level_max_m[l], s>>>(dev, level_nodes + S.level_ptr[l], d_x);
+        else
+            mf_forward_kernel<2><<<nf, TS, sizeof(double) * level_max_m[l], s>>>(dev, level_nodes + S.level_ptr[l], d_x);
+    }
+    for (int l = S.nlevels - 1; l >= 0; --l) {
+        const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
+        if (level_max_m[l] <= TS)
+            mf_backward_kernel<1><<<nf, TS, sizeof(double) * level_max_m[l], s>>>(dev, level_nodes + S.level_ptr[l], d_x);
+        else
+            mf_backward_kernel<2><<<nf, TS, sizeof(double) * level_max_m[l], s>>>(dev, level_nodes + S.level_ptr[l], d_x);
     }
     return true;
 }
@@ -474,16 +744,9 @@ bool MultifrontalLU::solve(double *d_x, cudaStream_t s, std::string &err) {
         return false;
     }
     Impl &I = *impl_;
-    const MFSymbolic &S = I.S;
-    g_launch_count.fetch_add(2 * S.nlevels, std::memory_order_relaxed);
-    for (int l = 0; l < S.nlevels; ++l) {
-        const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
-        mf_forward_kernel<<<nf, TF, sizeof(double) * I.level_max_m[l], s>>>(I.dev, I.level_nodes + S.level_ptr[l], d_x);
-    }
-    for (int l = S.nlevels - 1; l >= 0; --l) {
-        const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
-        mf_backward_kernel<<<nf, TF, sizeof(double) * I.level_max_m[l], s>>>(I.dev, I.level_nodes + S.level_ptr[l], d_x);
-    }
+    if (!check(err)) return false;
+    g_launch_count.fetch_add(2 * I.S.nlevels, std::memory_order_relaxed);
+    if (!I.run(I.solve_graphs, d_x, s, err, [&](cudaStream_t q) { return I.enqueue_solve(d_x, q, err); })) return false;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         err = std::string("multifrontal solve: ") + cudaGetErrorString(e);

@@ -21,6 +21,7 @@ class MultifrontalLU {
                    std::string &err);
     bool factor(const double *d_vals, cudaStream_t s, std::string &err);   // numeric factorisation on the GPU
     bool solve(double *d_x, cudaStream_t s, std::string &err);             // in place
+    bool check(std::string &err);   // zero-pivot flag of completed factorisations (non-blocking)
     long long factor_nnz() const { return factor_nnz_; }
     double flops() const { return flops_; }
     int levels() const { return nlevels_; }

@@ -40,6 +40,7 @@ struct MFHostNumeric {
     std::vector<int> piv;                // per elimination position: local pivot row chosen inside its front
     double min_pivot = 0.0;
 };
+extern int g_mf_host_window;   // pivot-search window of mf_factor_host (1 = static pivoting like the device)
 bool mf_factor_host(const MFSymbolic &S, const double *vals, MFHostNumeric &N);
 void mf_solve_host(const MFSymbolic &S, const MFHostNumeric &N, double *x);
 

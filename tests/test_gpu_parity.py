@@ -319,9 +319,13 @@ def test_large_sweep_properties(K):
     if n_parked == 0:
         assert np.allclose(b, expect, rtol=1e-10)
     assert abs(float(acc[2 * nn]) - 0.5 * K * 200 * H.H * (0.09 + 0.49)) / (K * 0.58) < 1e-9
-    # linearity: doubling the offset doubles b
+    # linearity in the offset: b(2c) - b(0) = 2 (b(c) - b(0))   (b(0) is the parked-buoy term, zero without them)
+    acc0 = torch.zeros_like(acc)
+    ocp.d_ud.copy_(u)
+    ocp.ctx.buoy_adjoint_scatter(ocp.d_vel, g, K, x, u, ocp.d_ud, ocp.d_mask, ocp.d_parked, None, acc0)
     acc2 = torch.zeros_like(acc)
     ocp.d_ud.copy_(u + 2 * cvec)
     ocp.ctx.buoy_adjoint_scatter(ocp.d_vel, g, K, x, u, ocp.d_ud, ocp.d_mask, ocp.d_parked, None, acc2)
-    assert float((acc2[:2 * nn] - 2 * acc[:2 * nn]).abs().max()) <= 1e-9 * float(acc[:2 * nn].abs().max())
+    lhs, rhs = acc2[:2 * nn] - acc0[:2 * nn], 2 * (acc[:2 * nn] - acc0[:2 * nn])
+    assert float((lhs - rhs).abs().max()) <= 1e-9 * float(acc[:2 * nn].abs().max())
     ocp.close()

@@ -56,6 +56,7 @@ def main():
     x0, ud = tr["x_0_array"][:, 0, :].copy(), tr["u_d_array"]
     ocp = OCP(V, P, x0, ud, device=dev)
     ctx = ocp.ctx
+    ctx.set_profiling(True)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
     try:
@@ -183,6 +184,7 @@ def main():
                   f" masked {int(big.d_mask.sum())}")
             if K == 10_000:
                 big.ctx.reset_solver_stats()
+                big.ctx.set_profiling(os.environ.get('PROFILE_STEP', '0') == '1')
                 big.set_control(initial_control(V, "PL"))
                 ms_it = timed(lambda: big.gradient_step(big.d_f), 3)
                 print("full gradient step ms", ms_it, big.ctx.solver_stats())

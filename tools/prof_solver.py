@@ -16,6 +16,7 @@ from ocp_b200.pipeline import OCP, Parameters, initial_control  # noqa: E402
 V = TaylorHood(square_mesh(int(os.environ.get("MESH_N", "32"))))
 ocp = OCP(V, Parameters(), np.array([[0.5, 0.5]]), np.zeros((1, 200, 2)))
 f = torch.from_numpy(initial_control(V, "PL")).cuda()
+ocp.ctx.set_profiling(True)
 for _ in range(int(os.environ.get("REPS", "2"))):
     ocp.ctx.reset_solver_stats()
     ocp.forward_solve(f)
