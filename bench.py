@@ -163,7 +163,21 @@ def run_ours(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
-    group, rank, world, local = init_from_env("nccl")
+    # NCCL may print its version banner on stdout; the contract is ONE JSON line there, so route fd 1 to stderr
+    # while the communicator is created (first collective included)
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        group, rank, world, local = init_from_env("nccl")
+        if group is not None:
+            t_ = torch.zeros(1, device=torch.device("cuda", local))
+            dist.all_reduce(t_, group=group)
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     dev = torch.device("cuda", local)
