@@ -55,6 +55,7 @@ typedef struct {
     int32_t nt;          /* int(T/dt) samples per trajectory (200)           */
     const double *cell_geom;      /* (nc,6) x0 y0 a1 b1 a2 b2: lambda_1 = a1 (x-x0) + b1 (y-y0), lambda_2 likewise */
     const int32_t *cell_nodes;    /* (nc,6) v0 v1 v2 e0 e1 e2 (vertices sorted ascending, e_i opposite v_i)         */
+    const int32_t *cell_nbr;      /* (nc,3) cell across the edge opposite local vertex i, -1 on the boundary      */
     const double *node_coords;    /* (nn,2)                                   */
     const int32_t *dof_ux;        /* (nn) W dof of u_x at a node               */
     const int32_t *dof_uy;        /* (nn)                                      */

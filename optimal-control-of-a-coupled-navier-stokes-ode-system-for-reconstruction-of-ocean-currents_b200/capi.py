@@ -39,7 +39,7 @@ class ProblemDesc(C.Structure):
     _fields_ = [
         ("nv", C.c_int32), ("nn", C.c_int32), ("nc", C.c_int32), ("ndofs", C.c_int32), ("nnz", C.c_int32),
         ("n_dirichlet", C.c_int32), ("n_g1", C.c_int32), ("nt", C.c_int32),
-        ("cell_geom", C.c_void_p), ("cell_nodes", C.c_void_p), ("node_coords", C.c_void_p),
+        ("cell_geom", C.c_void_p), ("cell_nodes", C.c_void_p), ("cell_nbr", C.c_void_p), ("node_coords", C.c_void_p),
         ("dof_ux", C.c_void_p), ("dof_uy", C.c_void_p), ("dof_p", C.c_void_p),
         ("csr_rowptr", C.c_void_p), ("csr_col", C.c_void_p), ("dirichlet_dofs", C.c_void_p),
         ("g1_nodes", C.c_void_p), ("g1_len", C.c_void_p), ("g1_normal", C.c_void_p),
@@ -110,6 +110,7 @@ class Context:
         keep = dict(
             geom=np.ascontiguousarray(V.cell_geom, np.float64),
             cn=np.ascontiguousarray(V.cell_nodes, np.int32),
+            nbr=np.ascontiguousarray(V.cell_nbr, np.int32),
             xy=np.ascontiguousarray(V.node_coords, np.float64),
             ux=np.ascontiguousarray(V.dof_ux, np.int32), uy=np.ascontiguousarray(V.dof_uy, np.int32),
             pp=np.ascontiguousarray(V.dof_p, np.int32),
@@ -123,7 +124,7 @@ class Context:
         d = ProblemDesc(
             m.num_vertices, V.num_nodes, m.num_cells, V.ndofs, int(V.csr_col.size), int(V.dirichlet_dofs.size),
             int(V.g1_cell.size), int(nt),
-            _hp(keep["geom"]), _hp(keep["cn"]), _hp(keep["xy"]), _hp(keep["ux"]), _hp(keep["uy"]), _hp(keep["pp"]),
+            _hp(keep["geom"]), _hp(keep["cn"]), _hp(keep["nbr"]), _hp(keep["xy"]), _hp(keep["ux"]), _hp(keep["uy"]), _hp(keep["pp"]),
             _hp(keep["rp"]), _hp(keep["ci"]), _hp(keep["dd"]), _hp(keep["g1n"]), _hp(keep["g1l"]), _hp(keep["g1m"]),
             float(V.bin_origin[0]), float(V.bin_origin[1]), float(V.bin_inv_h[0]), float(V.bin_inv_h[1]),
             int(V.bin_dims[0]), int(V.bin_dims[1]), _hp(keep["bp"]), _hp(keep["bc"]),

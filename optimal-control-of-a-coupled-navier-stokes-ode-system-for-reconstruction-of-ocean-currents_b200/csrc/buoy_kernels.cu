@@ -6,6 +6,8 @@
 //   buoy_adjoint_scatter_kernel  solve_adjoint_ode           OCP_dolfin.py:234-252
 //                                + PointSource loop          OCP_dolfin.py:353-366
 //                                + partA of J                OCP_dolfin.py:259
+#include <algorithm>
+
 #include "element_math.cuh"
 #include "kernels.cuh"
 
@@ -27,16 +29,31 @@ __device__ __forceinline__ void load_nodes(const DeviceTables &t, int c, int n[6
     n[0] = a.x; n[1] = a.y; n[2] = b.x; n[3] = b.y; n[4] = d.x; n[5] = d.y;
 }
 
-// Lowest-index cell whose barycentrics are all >= -tol; `hint` short-cuts when the point is strictly
-// inside the previous cell (then no other cell can contain it).  -1 = dolfin's "point outside" error.
+// Lowest-index cell whose barycentrics are all >= -tol (the oracle's definition of dolfin's "first colliding cell").
+//   1. `hint` (previous cell): accepted when the point is strictly inside (margin 1e-9) - then no other cell can
+//      contain it, so the answer equals the definition.
+//   2. neighbour walk: leave through the edge with the most negative barycentric, at most 4 hops, again accepting
+//      only strictly-inside hits.  This is what a buoy crossing into the next cell costs (one or two hops).
+//   3. anything ambiguous (on an edge/vertex within the margin, outside the mesh, far jump): the definition itself,
+//      ascending scan of the bin's candidate list.
+// -1 = dolfin's "point outside" error.
 __device__ __forceinline__ int locate(const DeviceTables &t, double x, double y, int hint, double &l0, double &l1,
                                       double &l2) {
     if (!(x == x) || !(y == y)) return -1;
     double g[6];
     if (hint >= 0) {
-        load_geom(t, hint, g);
-        bary(g, x, y, l0, l1, l2);
-        if (l0 > kLocateMargin && l1 > kLocateMargin && l2 > kLocateMargin) return hint;
+        int c = hint;
+#pragma unroll 1
+        for (int hop = 0; hop < 5; ++hop) {
+            load_geom(t, c, g);
+            bary(g, x, y, l0, l1, l2);
+            if (l0 > kLocateMargin && l1 > kLocateMargin && l2 > kLocateMargin) return c;
+            const double lm = fmin(l0, fmin(l1, l2));
+            if (lm >= -kLocateTol) break;                       // within the tie zone of an edge: use the definition
+            const int e = (l0 == lm) ? 0 : ((l1 == lm) ? 1 : 2);
+            c = __ldg(t.cell_nbr + 3 * (size_t)c + e);
+            if (c < 0) break;
+        }
     }
     const double fx = floor(OCP_MUL(OCP_SUB(x, t.ox), t.ihx));
     const double fy = floor(OCP_MUL(OCP_SUB(y, t.oy), t.ihy));
@@ -71,8 +88,42 @@ __device__ __forceinline__ void eval_p2(const DeviceTables &t, const double2 *__
     uy = sy;
 }
 
+// P2 velocity from the per-cell coefficient record (12 doubles: (u_x, u_y) of the cell's six nodes, contiguous), same
+// operation order as eval_p2 - the record only replaces the node-index indirection by one contiguous 96-byte read.
+__device__ __forceinline__ void eval_p2_cell(const double2 *__restrict__ cellvel, int c, double l0, double l1,
+                                             double l2, double &ux, double &uy) {
+    double phi[6];
+    p2_basis(l0, l1, l2, phi);
+    const double2 *r = cellvel + 6 * (size_t)c;
+    double2 v = __ldg(r);
+    double sx = OCP_MUL(phi[0], v.x), sy = OCP_MUL(phi[0], v.y);
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        v = __ldg(r + i);
+        sx = OCP_FMA(phi[i], v.x, sx);
+        sy = OCP_FMA(phi[i], v.y, sy);
+    }
+    ux = sx;
+    uy = sy;
+}
+
+// cellvel[c][i] = vel[cell_nodes[c][i]], cellg[c][a] = g[cell_nodes[c][a]] (a < 3): rebuilt whenever the state changes
+__global__ void cell_records_kernel(int nc, const int *__restrict__ cell_nodes, const double2 *__restrict__ vel,
+                                    double2 *__restrict__ cellvel, const double2 *__restrict__ g,
+                                    double2 *__restrict__ cellg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc * 6) return;
+    const int c = i / 6, a = i % 6;
+    const int n = __ldg(cell_nodes + i);
+    if (cellvel) cellvel[i] = __ldg(vel + n);
+    if (cellg && a < 3) {
+        cellg[6 * (size_t)c + 2 * a] = __ldg(g + 2 * (size_t)n);
+        cellg[6 * (size_t)c + 2 * a + 1] = __ldg(g + 2 * (size_t)n + 1);
+    }
+}
+
 __global__ void __launch_bounds__(kBuoyThreads)
-buoy_forward_kernel(DeviceTables t, const double2 *__restrict__ vel, const double2 *__restrict__ x0, int K, int nt,
+buoy_forward_kernel(DeviceTables t, const double2 *__restrict__ vel /* per-cell records */, const double2 *__restrict__ x0, int K, int nt,
                     double h, double cx, double cy, double2 *__restrict__ x, double2 *__restrict__ u,
                     int *__restrict__ cell, double *__restrict__ mask, uint8_t *__restrict__ parked) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,7 +138,7 @@ buoy_forward_kernel(DeviceTables t, const double2 *__restrict__ vel, const doubl
             break;
         }
         double ux, uy;
-        eval_p2(t, vel, c, l0, l1, l2, ux, uy);
+        eval_p2_cell(vel, c, l0, l1, l2, ux, uy);
         const size_t o = (size_t)k * K + b;
         x[o] = p;
         u[o] = make_double2(ux, uy);
@@ -102,7 +153,7 @@ buoy_forward_kernel(DeviceTables t, const double2 *__restrict__ vel, const doubl
         const int c = locate(t, p.x, p.y, hint, l0, l1, l2);
         if (c >= 0) {
             double ux, uy;
-            eval_p2(t, vel, c, l0, l1, l2, ux, uy);
+            eval_p2_cell(vel, c, l0, l1, l2, ux, uy);
             x[o] = p;
             u[o] = make_double2(ux, uy);
             if (cell) cell[o] = c;
@@ -121,7 +172,7 @@ buoy_forward_kernel(DeviceTables t, const double2 *__restrict__ vel, const doubl
     parked[b] = 0;
     const int cc = locate(t, cx, cy, -1, l0, l1, l2);
     double ucx = 0.0, ucy = 0.0;
-    if (cc >= 0) eval_p2(t, vel, cc, l0, l1, l2, ucx, ucy);
+    if (cc >= 0) eval_p2_cell(vel, cc, l0, l1, l2, ucx, ucy);
     for (int k = 0; k < nt; ++k) {
         const size_t o = (size_t)k * K + b;
         x[o] = make_double2(cx, cy);
@@ -201,15 +252,24 @@ __device__ __forceinline__ void flush_sources(double *__restrict__ bnode, const 
 // gamma_c phi_i(x_k); deposits are accumulated in registers while the buoy stays in one cell and
 // flushed with 12 fp64 atomics when it changes cell (a buoy crosses a handful of cells per trajectory),
 // then mu_{k-1} = mu_k - h G(x_k)^T ((u_k - u_d,k) - mu_k).
-__global__ void __launch_bounds__(kBuoyThreads)
-buoy_adjoint_scatter_kernel(DeviceTables t, const double2 *__restrict__ vel, const double2 *__restrict__ g, int K,
+__global__ void __launch_bounds__(kBuoyThreads, 5)
+buoy_adjoint_scatter_kernel(DeviceTables t, const double2 *__restrict__ vel /* per-cell records */,
+                            const double2 *__restrict__ g /* per-cell vertex gradients */, int K,
                             int nt, double h, double cx, double cy, const double2 *__restrict__ x,
                             const double2 *__restrict__ u, const double2 *__restrict__ ud,
                             const double *__restrict__ mask, const uint8_t *__restrict__ parked,
                             double2 *__restrict__ mu, double *__restrict__ acc_out, double *scratch,
-                            unsigned *counter) {
+                            unsigned *counter, double *__restrict__ bpriv, int nrep) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double misfit = 0.0, nmasked = 0.0;
+    // point sources go to one of `nrep` private copies of b (selected by SM id) so that fp64 atomics of the
+    // thousands of buoys sharing a cell do not serialise on 12 addresses; the copies are summed afterwards
+    double *bdst = acc_out;
+    if (nrep > 1) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        bdst = bpriv + (size_t)(smid % (unsigned)nrep) * (2 * (size_t)t.nn);
+    }
     if (b < K) {
         const bool masked = mask[b] != 0.0;
         const bool park = parked[b] != 0;
@@ -219,10 +279,18 @@ buoy_adjoint_scatter_kernel(DeviceTables t, const double2 *__restrict__ vel, con
 #pragma unroll
         for (int i = 0; i < 12; ++i) acc[i] = 0.0;
         int acc_cell = -1, hint = -1;
+        // the three streams are read one sample ahead so that their HBM latency overlaps the arithmetic
+        double2 pn = __ldcs(x + (size_t)(nt - 1) * K + b), Un = __ldcs(u + (size_t)(nt - 1) * K + b),
+                Dn = __ldcs(ud + (size_t)(nt - 1) * K + b);
         for (int k = nt - 1; k >= 0; --k) {
             const size_t o = (size_t)k * K + b;
-            double2 p = __ldcs(x + o);
-            const double2 U = __ldcs(u + o), D = __ldcs(ud + o);
+            double2 p = pn;
+            const double2 U = Un, D = Dn;
+            if (k > 0) {
+                pn = __ldcs(x + o - K);
+                Un = __ldcs(u + o - K);
+                Dn = __ldcs(ud + o - K);
+            }
             const double ex = U.x - D.x, ey = U.y - D.y;
             misfit += ex * ex + ey * ey;
             if (masked) {
@@ -239,13 +307,13 @@ buoy_adjoint_scatter_kernel(DeviceTables t, const double2 *__restrict__ vel, con
                 c = locate(t, cx, cy, -1, l0, l1, l2);
             } else if (park && k == nt - 1) {
                 // the stored velocity of a parked last sample is 0, the scatter loop re-evaluates u(centre)
-                eval_p2(t, vel, c, l0, l1, l2, ukx, uky);
+                eval_p2_cell(vel, c, l0, l1, l2, ukx, uky);
             }
             if (mu) __stcs(mu + o, make_double2(mux, muy));
             if (c >= 0) {
                 hint = c;
                 if (c != acc_cell) {
-                    if (acc_cell >= 0) flush_sources(acc_out, t, acc_cell, acc);
+                    if (acc_cell >= 0) flush_sources(bdst, t, acc_cell, acc);
                     acc_cell = c;
                 }
                 const double gx = h * ((D.x - ukx) + mux), gy = h * ((D.y - uky) + muy);
@@ -257,12 +325,10 @@ buoy_adjoint_scatter_kernel(DeviceTables t, const double2 *__restrict__ vel, con
                     acc[6 + i] = fma(gy, phi[i], acc[6 + i]);
                 }
                 if (k > 0) {
-                    int n[6];
-                    load_nodes(t, c, n);
                     // continuous P1 tensor at the cell's three vertices, [g00 g01 | g10 g11] per vertex
-                    const double2 a0 = __ldg(g + 2 * (size_t)n[0]), a1 = __ldg(g + 2 * (size_t)n[0] + 1);
-                    const double2 b0 = __ldg(g + 2 * (size_t)n[1]), b1 = __ldg(g + 2 * (size_t)n[1] + 1);
-                    const double2 c0 = __ldg(g + 2 * (size_t)n[2]), c1 = __ldg(g + 2 * (size_t)n[2] + 1);
+                    const double2 *gr = g + 6 * (size_t)c;
+                    const double2 a0 = __ldg(gr), a1 = __ldg(gr + 1), b0 = __ldg(gr + 2), b1 = __ldg(gr + 3),
+                                  c0 = __ldg(gr + 4), c1 = __ldg(gr + 5);
                     const double G0 = l0 * a0.x + l1 * b0.x + l2 * c0.x;
                     const double G1 = l0 * a0.y + l1 * b0.y + l2 * c0.y;
                     const double G2 = l0 * a1.x + l1 * b1.x + l2 * c1.x;
@@ -273,10 +339,19 @@ buoy_adjoint_scatter_kernel(DeviceTables t, const double2 *__restrict__ vel, con
                 }
             }
         }
-        if (acc_cell >= 0) flush_sources(acc_out, t, acc_cell, acc);
+        if (acc_cell >= 0) flush_sources(bdst, t, acc_cell, acc);
     }
     block_finish2(misfit, nmasked, scratch, counter, acc_out + 2 * (size_t)t.nn, acc_out + 2 * (size_t)t.nn + 1,
                   0.5 * h);
+}
+
+// b += sum over the private copies, in copy order (deterministic given the copies)
+__global__ void reduce_private_kernel(int n, int nrep, const double *__restrict__ bpriv, double *__restrict__ b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int r = 0; r < nrep; ++r) s += bpriv[(size_t)r * n + i];
+    b[i] += s;
 }
 
 __global__ void __launch_bounds__(256)
@@ -312,26 +387,46 @@ __global__ void transpose_kernel(const double2 *__restrict__ src, double2 *__res
 
 int buoy_max_blocks(int K) { return (K + kBuoyThreads - 1) / kBuoyThreads; }
 
-void launch_buoy_forward(const DeviceTables &t, const double *vel, const double *x0, int K, int nt, double h,
+int buoy_private_copies(int K, int nc, int nn) {
+    if ((long long)K < 8LL * nc) return 1;                        // few buoys per cell: no contention to avoid
+    const long long cap = (256LL << 20) / (16LL * nn);            // at most 256 MiB of private copies
+    return (int)std::max(1LL, std::min(148LL, cap));
+}
+
+void launch_cell_records(const DeviceTables &t, const double *vel, double *cellvel, const double *g, double *cellg,
+                         cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    cell_records_kernel<<<(t.nc * 6 + 255) / 256, 256, 0, s>>>(
+        t.nc, t.cell_nodes, reinterpret_cast<const double2 *>(vel), reinterpret_cast<double2 *>(cellvel),
+        reinterpret_cast<const double2 *>(g), reinterpret_cast<double2 *>(cellg));
+}
+
+void launch_buoy_forward(const DeviceTables &t, const double *cellvel, const double *x0, int K, int nt, double h,
                          double cx, double cy, double *x, double *u, int *cell, double *mask, uint8_t *parked,
                          cudaStream_t s) {
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (K <= 0) return;
     buoy_forward_kernel<<<buoy_max_blocks(K), kBuoyThreads, 0, s>>>(
-        t, reinterpret_cast<const double2 *>(vel), reinterpret_cast<const double2 *>(x0), K, nt, h, cx, cy,
+        t, reinterpret_cast<const double2 *>(cellvel), reinterpret_cast<const double2 *>(x0), K, nt, h, cx, cy,
         reinterpret_cast<double2 *>(x), reinterpret_cast<double2 *>(u), cell, mask, parked);
 }
 
 void launch_buoy_adjoint_scatter(const DeviceTables &t, const double *vel, const double *g, int K, int nt, double h,
                                  double cx, double cy, const double *x, const double *u, const double *ud,
                                  const double *mask, const uint8_t *parked, double *mu, double *acc,
-                                 double *scratch, unsigned *counter, cudaStream_t s) {
+                                 double *scratch, unsigned *counter, double *bpriv, int nrep, cudaStream_t s) {
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (K <= 0) return;
+    if (nrep > 1) cudaMemsetAsync(bpriv, 0, sizeof(double) * 2 * (size_t)t.nn * nrep, s);
     buoy_adjoint_scatter_kernel<<<buoy_max_blocks(K), kBuoyThreads, 0, s>>>(
         t, reinterpret_cast<const double2 *>(vel), reinterpret_cast<const double2 *>(g), K, nt, h, cx, cy,
         reinterpret_cast<const double2 *>(x), reinterpret_cast<const double2 *>(u),
-        reinterpret_cast<const double2 *>(ud), mask, parked, reinterpret_cast<double2 *>(mu), acc, scratch, counter);
+        reinterpret_cast<const double2 *>(ud), mask, parked, reinterpret_cast<double2 *>(mu), acc, scratch, counter,
+        bpriv, nrep);
+    if (nrep > 1) {
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        reduce_private_kernel<<<(2 * t.nn + 255) / 256, 256, 0, s>>>(2 * t.nn, nrep, bpriv, acc);
+    }
 }
 
 void launch_misfit(int K, int nt, double h, const double *u, const double *ud, double *out, double *scratch,

@@ -64,7 +64,7 @@ struct ocp_ctx {
     DeviceTables tab{};
     // device tables
     double *d_geom = nullptr, *d_g1_len = nullptr, *d_g1_normal = nullptr;
-    int *d_cell_nodes = nullptr, *d_cell_dofs = nullptr, *d_cell_slots = nullptr;
+    int *d_cell_nodes = nullptr, *d_cell_dofs = nullptr, *d_cell_slots = nullptr, *d_cell_nbr = nullptr;
     int *d_dof_ux = nullptr, *d_dof_uy = nullptr, *d_dof_p = nullptr;
     int *d_rowptr = nullptr, *d_col = nullptr, *d_dir = nullptr;
     int *d_g1_nodes = nullptr, *d_g1_dofs = nullptr, *d_g1_slots = nullptr;
@@ -75,6 +75,9 @@ struct ocp_ctx {
     // work space
     double *d_vals = nullptr, *d_res = nullptr, *d_rhs = nullptr, *d_tmp = nullptr, *d_rhs4 = nullptr;
     double *d_scalar = nullptr, *d_scratch = nullptr;
+    double *d_cellvel = nullptr, *d_cellg = nullptr;   // per-cell coefficient records read by the buoy kernels
+    double *d_bpriv = nullptr;                         // private copies of the point-source vector (per SM id)
+    size_t bpriv_len = 0;
     size_t scratch_len = 0;
     unsigned *d_counter = nullptr;
     double *h_pinned = nullptr;    // 8 doubles
@@ -129,6 +132,16 @@ int ensure_stage(ocp_ctx *c, int i, size_t n) {
     c->stage_len[i] = 0;
     CUDA_OK(c, cudaMalloc((void **)&c->d_stage[i], sizeof(double) * n));
     c->stage_len[i] = n;
+    return OCP_OK;
+}
+
+int ensure_bpriv(ocp_ctx *c, size_t n) {
+    if (n <= c->bpriv_len) return OCP_OK;
+    cudaFree(c->d_bpriv);
+    c->d_bpriv = nullptr;
+    c->bpriv_len = 0;
+    CUDA_OK(c, cudaMalloc((void **)&c->d_bpriv, sizeof(double) * n));
+    c->bpriv_len = n;
     return OCP_OK;
 }
 
@@ -238,7 +251,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     if (!d || !out) return OCP_ERR_INVALID;
     *out = nullptr;
     if (ocp_device_available() != OCP_OK) return OCP_ERR_NO_DEVICE;
-    if (d->ndofs != 2 * d->nn + d->nv || d->nt < 2 || d->nc <= 0) return OCP_ERR_INVALID;
+    if (d->ndofs != 2 * d->nn + d->nv || d->nt < 2 || d->nc <= 0 || !d->cell_nbr) return OCP_ERR_INVALID;
     ocp_ctx *c = new ocp_ctx();
     *out = c;   // returned even on failure so that the caller can read ocp_last_error, then destroy
     c->stream = (cudaStream_t)stream;
@@ -318,6 +331,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     } while (0)
     UP(d_geom, d->cell_geom, (size_t)nc * 6);
     UP(d_cell_nodes, d->cell_nodes, (size_t)nc * 6);
+    UP(d_cell_nbr, d->cell_nbr, (size_t)nc * 3);
     UP(d_cell_dofs, cell_dofs.data(), cell_dofs.size());
     UP(d_cell_slots, slots.data(), slots.size());
     UP(d_dof_ux, d->dof_ux, nn);
@@ -343,6 +357,8 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     CUDA_OK(c, cudaMalloc((void **)&c->d_tmp, sizeof(double) * n));
     CUDA_OK(c, cudaMalloc((void **)&c->d_rhs4, sizeof(double) * 4 * nv));
     CUDA_OK(c, cudaMalloc((void **)&c->d_scalar, sizeof(double) * 8));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_cellvel, sizeof(double) * 12 * (size_t)nc));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_cellg, sizeof(double) * 12 * (size_t)nc));
     CUDA_OK(c, cudaMalloc((void **)&c->d_counter, sizeof(unsigned)));
     CUDA_OK(c, cudaMemset(c->d_counter, 0, sizeof(unsigned)));
     CUDA_OK(c, cudaMallocHost((void **)&c->h_pinned, sizeof(double) * 8));
@@ -352,7 +368,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     if (rc != OCP_OK) return rc;
 
     c->tab.nc = nc; c->tab.nn = nn; c->tab.nv = nv;
-    c->tab.geom = c->d_geom; c->tab.cell_nodes = c->d_cell_nodes;
+    c->tab.geom = c->d_geom; c->tab.cell_nodes = c->d_cell_nodes; c->tab.cell_nbr = c->d_cell_nbr;
     c->tab.ox = d->bin_ox; c->tab.oy = d->bin_oy; c->tab.ihx = d->bin_ihx; c->tab.ihy = d->bin_ihy;
     c->tab.nbx = d->nbx; c->tab.nby = d->nby;
     c->tab.bin_ptr = c->d_bin_ptr; c->tab.bin_cells = c->d_bin_cells;
@@ -387,7 +403,7 @@ void ocp_destroy(ocp_ctx *c) {
                     c->d_dof_ux, c->d_dof_uy, c->d_dof_p, c->d_rowptr, c->d_col, c->d_dir, c->d_g1_nodes,
                     c->d_g1_dofs, c->d_g1_slots, c->d_bin_ptr, c->d_bin_cells, c->d_m_rowptr, c->d_m_col,
                     c->d_m_vals, c->d_vals, c->d_res, c->d_rhs, c->d_tmp, c->d_rhs4, c->d_scalar, c->d_scratch,
-                    c->d_counter, c->d_parked, c->d_obs_x0, c->d_obs_ud};
+                    c->d_counter, c->d_parked, c->d_obs_x0, c->d_obs_ud, c->d_cell_nbr, c->d_cellvel, c->d_cellg, c->d_bpriv};
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < 8; ++i) cudaFree(c->d_stage[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -503,7 +519,8 @@ int ocp_project_grad(ocp_ctx *c, const double *d_w, double *d_g) {
 int ocp_buoy_forward(ocp_ctx *c, const double *d_vel, const double *d_x0, int K, double *d_x, double *d_u,
                      int32_t *d_cell, double *d_mask, uint8_t *d_parked) {
     if (!c || !d_vel || !d_x0 || !d_x || !d_u || !d_mask || !d_parked || K < 0) return OCP_ERR_INVALID;
-    launch_buoy_forward(c->tab, d_vel, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_cell, d_mask, d_parked,
+    launch_cell_records(c->tab, d_vel, c->d_cellvel, nullptr, nullptr, c->stream);
+    launch_buoy_forward(c->tab, c->d_cellvel, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_cell, d_mask, d_parked,
                         c->stream);
     CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
@@ -516,8 +533,11 @@ int ocp_buoy_adjoint_scatter(ocp_ctx *c, const double *d_vel, const double *d_g,
         return OCP_ERR_INVALID;
     int rc = ensure_scratch(c, 2 * (size_t)buoy_max_blocks(K) + 2);
     if (rc != OCP_OK) return rc;
-    launch_buoy_adjoint_scatter(c->tab, d_vel, d_g, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_ud, d_mask, d_parked,
-                                d_mu, d_acc, c->d_scratch, c->d_counter, c->stream);
+    const int nrep = buoy_private_copies(K, c->nc, c->nn);
+    if (nrep > 1 && (rc = ensure_bpriv(c, 2 * (size_t)c->nn * nrep)) != OCP_OK) return rc;
+    launch_cell_records(c->tab, d_vel, c->d_cellvel, d_g, c->d_cellg, c->stream);
+    launch_buoy_adjoint_scatter(c->tab, c->d_cellvel, c->d_cellg, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_ud, d_mask,
+                                d_parked, d_mu, d_acc, c->d_scratch, c->d_counter, c->d_bpriv, nrep, c->stream);
     CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
 }
@@ -613,7 +633,8 @@ int ocp_solve_primal_ode_host(ocp_ctx *c, const double *h_w, const double *h_x0,
     CUDA_OK(c, cudaMemcpyAsync(d_x0, h_x0, sizeof(double) * 2 * K, cudaMemcpyHostToDevice, s));
     CUDA_OK(c, cudaMemcpyAsync(d_mask, h_mask, sizeof(double) * K, cudaMemcpyHostToDevice, s));
     launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, d_w, d_vel, s);
-    launch_buoy_forward(c->tab, d_vel, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, nullptr, d_mask, c->d_parked, s);
+    launch_cell_records(c->tab, d_vel, c->d_cellvel, nullptr, nullptr, s);
+    launch_buoy_forward(c->tab, c->d_cellvel, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, nullptr, d_mask, c->d_parked, s);
     launch_traj_transpose(d_x, d_t, K, c->nt, 0, s);
     CUDA_OK(c, cudaMemcpyAsync(h_x, d_t, sizeof(double) * tr, cudaMemcpyDeviceToHost, s));
     CUDA_OK(c, cudaStreamSynchronize(s));   // d_t is reused for u
@@ -652,8 +673,9 @@ int ocp_solve_adjoint_ode_host(ocp_ctx *c, const double *h_g, const double *h_x,
     CUDA_OK(c, cudaMemsetAsync(d_vel, 0, sizeof(double) * 2 * c->nn, s));
     CUDA_OK(c, cudaMemsetAsync(c->d_parked, 0, (size_t)K + 1, s));
     CUDA_OK(c, cudaMemsetAsync(d_acc, 0, sizeof(double) * nacc, s));
-    launch_buoy_adjoint_scatter(c->tab, d_vel, d_g, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_ud, d_mask,
-                                c->d_parked, d_t, d_acc, c->d_scratch, c->d_counter, s);
+    launch_cell_records(c->tab, d_vel, c->d_cellvel, d_g, c->d_cellg, s);
+    launch_buoy_adjoint_scatter(c->tab, c->d_cellvel, c->d_cellg, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_ud, d_mask,
+                                c->d_parked, d_t, d_acc, c->d_scratch, c->d_counter, nullptr, 1, s);
     launch_traj_transpose(d_t, d_x, K, c->nt, 0, s);
     CUDA_OK(c, cudaMemcpyAsync(h_mu, d_x, sizeof(double) * tr, cudaMemcpyDeviceToHost, s));
     CUDA_OK(c, cudaStreamSynchronize(s));
@@ -709,7 +731,8 @@ int ocp_gradient_host(ocp_ctx *c, const double *h_f, double *h_w, double *h_z, d
     if ((rc = ocp_forward_solve(c, d_f, d_w, 1, &its, nullptr))) return rc;
     if ((rc = ocp_project_grad(c, d_w, d_g))) return rc;
     launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, d_w, d_vel, s);
-    launch_buoy_forward(c->tab, d_vel, c->d_obs_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, nullptr, d_mask,
+    launch_cell_records(c->tab, d_vel, c->d_cellvel, nullptr, nullptr, s);
+    launch_buoy_forward(c->tab, c->d_cellvel, c->d_obs_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, nullptr, d_mask,
                         c->d_parked, s);
     if ((rc = ocp_buoy_adjoint_scatter(c, d_vel, d_g, K, d_x, d_u, c->d_obs_ud, d_mask, c->d_parked, nullptr, d_acc)))
         return rc;

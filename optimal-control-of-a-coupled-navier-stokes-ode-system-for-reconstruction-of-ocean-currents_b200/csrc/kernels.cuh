@@ -14,20 +14,27 @@ struct DeviceTables {
     int nc, nn, nv;
     const double *geom;        // (nc,6)
     const int *cell_nodes;     // (nc,6)
+    const int *cell_nbr;       // (nc,3)
     double ox, oy, ihx, ihy;
     int nbx, nby;
     const int *bin_ptr, *bin_cells;
 };
 
 // ---- buoy sweeps (buoy_kernels.cu) ---------------------------------------------------------------------------
-void launch_buoy_forward(const DeviceTables &t, const double *vel, const double *x0, int K, int nt, double h,
+// per-cell coefficient records: cellvel (nc,6,2) from the nodal velocity, cellg (nc,3,4) from the vertex gradients
+// (either output may be null)
+void launch_cell_records(const DeviceTables &t, const double *vel, double *cellvel, const double *g, double *cellg,
+                         cudaStream_t s);
+// the buoy kernels read the per-cell records, not the nodal fields
+void launch_buoy_forward(const DeviceTables &t, const double *cellvel, const double *x0, int K, int nt, double h,
                          double cx, double cy, double *x, double *u, int *cell, double *mask, uint8_t *parked,
                          cudaStream_t s);
 // scratch: >= 2*max_blocks+2 doubles, counter: 1 unsigned (zero on entry, left zero)
-void launch_buoy_adjoint_scatter(const DeviceTables &t, const double *vel, const double *g, int K, int nt, double h,
+void launch_buoy_adjoint_scatter(const DeviceTables &t, const double *cellvel, const double *cellg, int K, int nt, double h,
                                  double cx, double cy, const double *x, const double *u, const double *ud,
                                  const double *mask, const uint8_t *parked, double *mu, double *acc,
-                                 double *scratch, unsigned *counter, cudaStream_t s);
+                                 double *scratch, unsigned *counter, double *bpriv, int nrep, cudaStream_t s);
+int buoy_private_copies(int K, int nc, int nn);   // number of private copies of b worth using (1 = none)
 void launch_misfit(int K, int nt, double h, const double *u, const double *ud, double *out, double *scratch,
                    unsigned *counter, cudaStream_t s);
 void launch_traj_transpose(const double *src, double *dst, int K, int nt, int to_time_major, cudaStream_t s);

@@ -54,6 +54,7 @@ class TaylorHood:
     g1_normal: np.ndarray = field(default=None, repr=False)     # (n1, 2) f8 outward unit normal
     # affine maps  lambda_1 = a1 (x-x0) + b1 (y-y0), lambda_2 = a2 (x-x0) + b2 (y-y0)
     cell_geom: np.ndarray = field(default=None, repr=False)     # (nc, 6) f8 [x0, y0, a1, b1, a2, b2]
+    cell_nbr: np.ndarray = field(default=None, repr=False)      # (nc, 3) i4 cell across the edge opposite local vertex i, -1 on the boundary
     # point-location bins
     bin_origin: np.ndarray = field(default=None, repr=False)    # (2,)
     bin_inv_h: np.ndarray = field(default=None, repr=False)     # (2,)
@@ -160,6 +161,10 @@ class TaylorHood:
         j21, j22 = p[:, 1, 1] - y0, p[:, 2, 1] - y0
         det = j11 * j22 - j12 * j21
         self.cell_geom = np.stack([x0, y0, j22 / det, -j12 / det, -j21 / det, j11 / det], axis=1)
+        m = self.mesh
+        ec = m.edge_cells[m.cell_edges]                               # (nc, 3, 2)
+        me = np.arange(m.num_cells, dtype=np.int32)[:, None]
+        self.cell_nbr = np.where(ec[:, :, 0] == me, ec[:, :, 1], ec[:, :, 0]).astype(np.int32)
 
     def _build_bins(self):
         m = self.mesh

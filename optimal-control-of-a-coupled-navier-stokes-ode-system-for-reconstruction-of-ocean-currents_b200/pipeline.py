@@ -94,9 +94,12 @@ class State:
 
 class OCP:
     def __init__(self, V: TaylorHood, params: Parameters, x0: np.ndarray, u_d: np.ndarray,
-                 device: Optional[torch.device] = None, group=None, alpha_scale_K: Optional[int] = None):
+                 device: Optional[torch.device] = None, group=None, alpha_scale_K: Optional[int] = None,
+                 sort_buoys: bool = True):
         """``x0`` (K,2) start points and ``u_d`` (K,nt,2) of THIS rank's buoys.  With a process group the
-        global buoy count is the sum over ranks; alpha is rescaled by the global K (OCP_dolfin.py:76)."""
+        global buoy count is the sum over ranks; alpha is rescaled by the global K (OCP_dolfin.py:76).
+        ``sort_buoys`` stores the buoys on the device in a spatially coherent order (sharding.spatial_order);
+        every host-facing array keeps the caller's order."""
         if not torch.cuda.is_available():
             raise capi.OcpError("OCP needs a CUDA device: the hot path has no CPU fallback")
         self.V, self.params = V, params
@@ -122,7 +125,18 @@ class OCP:
         K, nt, nn, nv, nd = self.K, self.nt, V.num_nodes, V.mesh.num_vertices, V.ndofs
         self.xsarr, self.ysarr = x0[:, 0].copy(), x0[:, 1].copy()
         self.u_d = u_d
+        # device order of the buoys: device index i holds the caller's buoy perm[i]
+        self.perm = None
+        if sort_buoys and K > 32:
+            from .sharding import spatial_order
+            perm = spatial_order(V, x0)
+            if not np.array_equal(perm, np.arange(K)):
+                self.perm = torch.from_numpy(perm).to(dev)
+                self.inv_perm = torch.empty_like(self.perm)
+                self.inv_perm[self.perm] = torch.arange(K, device=dev)
         self.d_x0 = torch.from_numpy(x0).to(dev)
+        if self.perm is not None:
+            self.d_x0 = self.d_x0[self.perm].contiguous()
         self.d_ud = self._to_time_major(u_d)
         self.d_x = torch.empty((nt, K, 2), device=dev, dtype=f64)
         self.d_u = torch.empty((nt, K, 2), device=dev, dtype=f64)
@@ -146,16 +160,41 @@ class OCP:
 
     # ------------------------------------------------------------------ helpers
     def _to_time_major(self, a: np.ndarray) -> torch.Tensor:
+        """host (K,nt,2) in the caller's buoy order -> device (nt,K,2) in device order"""
         src = torch.from_numpy(np.ascontiguousarray(a, np.float64)).to(self.device)
+        if self.perm is not None and a.shape[0] == self.K:
+            src = src[self.perm].contiguous()
         dst = torch.empty((self.nt, a.shape[0], 2), device=self.device, dtype=torch.float64)
         self.ctx.traj_transpose(src, dst, a.shape[0], True)
         return dst
 
     def _to_reference_layout(self, d: torch.Tensor) -> np.ndarray:
+        """device (nt,K,2) in device order -> host (K,nt,2) in the caller's buoy order"""
         K = d.shape[1]
         dst = torch.empty((K, self.nt, 2), device=self.device, dtype=torch.float64)
         self.ctx.traj_transpose(d, dst, K, False)
+        if self.perm is not None and K == self.K:
+            dst = dst[self.inv_perm]
         return dst.cpu().numpy()
+
+    def _buoy_vector_to_host(self, d: torch.Tensor) -> np.ndarray:
+        """per-buoy device vector (mask, parked) -> host array in the caller's order"""
+        if self.perm is not None and d.shape[0] == self.K:
+            d = d[self.inv_perm]
+        return d.cpu().numpy()
+
+    def _cells_to_host(self, d_cell: torch.Tensor) -> np.ndarray:
+        """device (nt,K) cell indices -> host (K,nt) in the caller's buoy order"""
+        c = d_cell.t()
+        if self.perm is not None and c.shape[0] == self.K:
+            c = c[self.inv_perm]
+        return c.contiguous().cpu().numpy()
+
+    def _buoy_vector_to_dev(self, a) -> torch.Tensor:
+        t = self._dev(np.asarray(a, np.float64))
+        if self.perm is not None and t.shape[0] == self.K:
+            t = t[self.perm].contiguous()
+        return t
 
     def _dev(self, a) -> torch.Tensor:
         if isinstance(a, torch.Tensor):
@@ -191,14 +230,14 @@ class OCP:
         """OCP_dolfin.py:201-230.  ``buoy_mask`` (K) float array is mutated in place; returns numpy
         ``x, u_values_array`` of shape (K,nt,2)."""
         self._primal(wSol.d_w, self.d_x, self.d_u, self.d_mask, init_mask=buoy_mask)
-        buoy_mask[:] = self.d_mask.cpu().numpy()
+        buoy_mask[:] = self._buoy_vector_to_host(self.d_mask)
         return self._to_reference_layout(self.d_x), self._to_reference_layout(self.d_u)
 
     def solve_adjoint_ode(self, wSol: State, grad_u: torch.Tensor, x, buoy_mask, u_values_array) -> np.ndarray:
         """OCP_dolfin.py:234-252 -> numpy mu (K,nt,2).  (The fused sweep also deposits point sources and the
         misfit into a scratch accumulator, which this reference-shaped call discards.)"""
         d_x, d_u = self._to_time_major(x), self._to_time_major(u_values_array)
-        d_mask = self._dev(np.asarray(buoy_mask, np.float64))
+        d_mask = self._buoy_vector_to_dev(buoy_mask)
         d_mu = torch.empty_like(d_x)
         acc = torch.zeros_like(self.d_acc)
         self.ctx.velocity_nodal(wSol.d_w, self.d_vel)
@@ -210,7 +249,7 @@ class OCP:
         """The adjoint PDE block OCP_dolfin.py:336-371 for host arrays x, u_values (K,nt,2): recomputes mu,
         deposits the point sources, all-reduces, assembles aAdj, applies the BC and solves."""
         d_x, d_u = self._to_time_major(x), self._to_time_major(u_values)
-        d_mask = self._dev(np.asarray(buoy_mask, np.float64))
+        d_mask = self._buoy_vector_to_dev(buoy_mask)
         g = grad_u if grad_u is not None else self.project_grad(w)
         self.ctx.velocity_nodal(w.d_w, self.d_vel)
         parked = ((d_x[-1, :, 0] == self.center_of_domain[0]) & (d_x[-1, :, 1] == self.center_of_domain[1])
@@ -240,7 +279,7 @@ class OCP:
         if init_mask is None:
             d_mask.zero_()
         else:
-            d_mask.copy_(self._dev(np.asarray(init_mask, np.float64)))
+            d_mask.copy_(self._buoy_vector_to_dev(init_mask))
         self.ctx.velocity_nodal(d_w, self.d_vel)
         self.ctx.buoy_forward(self.d_vel, self.d_x0, self.K, d_x, d_u, d_cell, d_mask, self.d_parked)
 
@@ -281,7 +320,7 @@ class OCP:
         d_f = self.d_f if f is None else self._dev(f)
         d_df = self._dev(df)
         fpert = torch.empty_like(d_f)
-        mask = self._dev(np.asarray(buoy_mask, np.float64)).clone()
+        mask = self._buoy_vector_to_dev(buoy_mask).clone()
         rows1, rows2 = [], []
 
         def Jat(hh):
@@ -301,7 +340,7 @@ class OCP:
             jl = Jat(-h_)
             ga = (jr - jl) / (2 * h_)
             rows2.append((gradj, ga, abs(gradj - ga), h_))
-        buoy_mask[:] = mask.cpu().numpy()
+        buoy_mask[:] = self._buoy_vector_to_host(mask)
         if out_dir is not None:
             os.makedirs(out_dir, exist_ok=True)
             hdr = "reduced Gradient j \t \t approximated gradient J \t Error \t \t \t h_i \n"
@@ -341,7 +380,7 @@ class OCP:
                 J0 = self._cost_from_acc(d_f)
                 u_keep, x_keep = self.d_u.clone(), self.d_x.clone()
                 wtmp = State(self.d_w.clone())
-                mask = self.d_mask.cpu().numpy()
+                mask = self._buoy_vector_to_host(self.d_mask)
                 res.grad_tables = self.grad_test(wtmp, J0, gradj, df, mask, f=d_f, out_dir=out_dir, iter=i)
                 res.grad_tables.update(J0=J0, gradj=gradj)
                 self.d_u.copy_(u_keep)

@@ -51,7 +51,7 @@ def test_buoy_forward_bit_exact_vs_oracle_and_fenics(K):
     ocp._primal(T(w), ocp.d_x, ocp.d_u, ocp.d_mask, d_cell=cell)
     x, u = ocp._to_reference_layout(ocp.d_x), ocp._to_reference_layout(ocp.d_u)
     xo, uo, co, mo, po = BuoyOracle(V, brute=True).forward(V.velocity_nodal(w), xr[:, 0, :], 200, H.H, H.CENTER)
-    assert np.array_equal(cell.cpu().numpy().T, co)              # point-location cell indices: bit-exact
+    assert np.array_equal(ocp._cells_to_host(cell), co)         # point-location cell indices: bit-exact
     assert np.array_equal(x, xo) and np.array_equal(u, uo)      # trajectories: bit-exact vs the oracle
     assert np.abs(x - xr).max() < 4e-16 and np.abs(u - ur).max() < 4e-16   # and round-off level vs FEniCS
     assert float(ocp.d_mask.sum()) == 0
@@ -78,7 +78,7 @@ def test_buoy_forward_masks_and_parks_like_the_reference():
     xo, uo, co, mo, po = BuoyOracle(V, brute=True).forward(V.velocity_nodal(w), x0, 200, H.H, ocp.center_of_domain)
     assert mo.sum() > 50                                         # many start outside the L
     assert np.array_equal(mask, mo) and np.array_equal(x, xo) and np.array_equal(u, uo)
-    assert np.array_equal(ocp.d_parked.cpu().numpy(), po)
+    assert np.array_equal(ocp._buoy_vector_to_host(ocp.d_parked), po)
     ocp.close()
 
 
@@ -289,8 +289,9 @@ def test_large_sweep_properties(K):
     # a sample of buoys against the oracle, bit-exact
     idx = rng.choice(K, 64, replace=False)
     xo, uo, *_ = BuoyOracle(V).forward(V.velocity_nodal(H.field_for(100)), x0[idx], 200, H.H, H.CENTER)
-    assert np.array_equal(x[:, idx].cpu().numpy().transpose(1, 0, 2), xo)
-    assert np.array_equal(u[:, idx].cpu().numpy().transpose(1, 0, 2), uo)
+    didx = ocp.inv_perm[torch.from_numpy(idx).to(x.device)] if ocp.perm is not None else idx     # device order
+    assert np.array_equal(x[:, didx].cpu().numpy().transpose(1, 0, 2), xo)
+    assert np.array_equal(u[:, didx].cpu().numpy().transpose(1, 0, 2), uo)
     nn = V.num_nodes
     g = torch.zeros((V.mesh.num_vertices, 4), device=dev(), dtype=torch.float64)
     # u_d = u  =>  misfit 0 and, with G = 0 (mu = 0), gamma = 0: nothing is deposited

@@ -69,3 +69,18 @@ def test_two_rank_allreduce_equals_single_rank():
         assert p.exitcode == 0
     assert np.array_equal(got[0], got[1])                       # identical on every rank after the all-reduce
     assert H.rel(got[0], ref) < 1e-12                           # summation order differs from the 1-rank sum
+
+
+def test_spatial_order_is_a_permutation_grouping_neighbours():
+    from ocp_b200.sharding import spatial_order
+    V = H.square32()
+    rng = np.random.default_rng(0)
+    x0 = np.stack([rng.uniform(-0.1, 2.1, 5000), rng.uniform(-0.1, 2.1, 5000)], 1)
+    x0[17] = np.nan
+    p = spatial_order(V, x0)
+    assert sorted(p.tolist()) == list(range(5000))
+    xs = x0[p]
+    ok = ~np.isnan(xs).any(axis=1)
+    d_sorted = np.linalg.norm(np.diff(xs[ok], axis=0), axis=1).mean()
+    d_orig = np.linalg.norm(np.diff(x0[~np.isnan(x0).any(axis=1)], axis=0), axis=1).mean()
+    assert d_sorted < 0.1 * d_orig                     # consecutive buoys are neighbours after sorting

@@ -69,7 +69,7 @@ def main():
         u = ocp._to_reference_layout(ocp.d_u)
         xo, uo, co, mo, po = B.forward(V.velocity_nodal(w), x0, ocp.nt, P.dt, ocp.center_of_domain)
         print("x bit-exact:", np.array_equal(x, xo), "u bit-exact:", np.array_equal(u, uo),
-              "cells equal:", np.array_equal(cell.cpu().numpy().T, co), "max|x-xref|", np.abs(x - tr["x_0_array"]).max())
+              "cells equal:", np.array_equal(ocp._cells_to_host(cell), co), "max|x-xref|", np.abs(x - tr["x_0_array"]).max())
         print("max |x-xo|", np.abs(x - xo).max(), "max|u-uo|", np.abs(u - uo).max())
     except Exception:
         traceback.print_exc()
