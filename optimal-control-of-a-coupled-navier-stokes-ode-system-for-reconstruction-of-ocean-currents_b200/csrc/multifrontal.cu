@@ -59,9 +59,9 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
     __shared__ double s_rd[NB];                   // reciprocals of its diagonal
     cg::cluster_group cl = cg::this_cluster();
     const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
-    const int ldu = max_m + CWO;                  // leading dimension of the U12 staging area
+    const int ldu = (max_m + CWO + 3) & ~3;       // leading dimension of the U12 staging area (multiple of 4)
     double *P = sm;                               // L panel, ld = mp
-    double *Uc = sm + (size_t)max_m * NB;         // NB x ldu, row-major, indexed by "own column" number
+    double *Uc = sm + (size_t)((max_m + 3) & ~3) * NB;   // NB x ldu, row-major, indexed by "own column" number
     const int s = nodes[blockIdx.x / C];
     const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
     double *F = d.F + d.front_ptr[s];
@@ -85,6 +85,7 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
     const int nown = (m > rank * CWO) ? (m - rank * CWO + C * CWO - 1) / (C * CWO) : 0;
     for (int k0 = 0; k0 < np; k0 += NB) {
         const int kb = min(NB, np - k0), mp = m - k0, ctrail = k0 + kb;
+        const int ldp = (mp + 3) & ~3;          // panel leading dimension, multiple of 4 so that tiles load as 2 x 16 B
         // (a) panel rows into registers
         double a[RMAX][NB];
 #pragma unroll
@@ -201,7 +202,7 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) {
                     if (jj < kb) {
-                        P[i + jj * mp] = a[q][jj];
+                        P[i + jj * ldp] = a[q][jj];
                         if (rank == 0) __stcg(F + (k0 + i) + (size_t)(k0 + jj) * m, a[q][jj]);
                     }
                 }
@@ -239,10 +240,11 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
             // first own chunk that still has trailing columns
             int q0 = 0;
             while (q0 < nown && (rank + q0 * C) * CWO + CWO <= ctrail) ++q0;
-            const int tr = (nrow + 3) >> 2, tc = (nown - q0) * (CWO / 4);
+            const int rbase = kb & ~3;                       // tile origin aligned to 4 rows (kb < 16 only in a front's last panel)
+            const int tr = (mp - rbase + 3) >> 2, tc = (nown - q0) * (CWO / 4);
             for (int tile = tid; tile < tr * tc; tile += TF) {
                 const int ti = tile % tr, tj = tile / tr;
-                const int i0 = kb + 4 * ti, idx0 = q0 * CWO + 4 * tj;
+                const int i0 = rbase + 4 * ti, idx0 = q0 * CWO + 4 * tj;
                 const int c0 = (rank + (idx0 / CWO) * C) * CWO + (idx0 % CWO);
                 double f[4][4], acc[4][4];
 #pragma unroll
@@ -251,16 +253,18 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
                     const bool cv = c0 + b >= ctrail && c0 + b < m;
 #pragma unroll
                     for (int aa = 0; aa < 4; ++aa) {
-                        f[aa][b] = (cv && i0 + aa < mp) ? __ldcg(colp + i0 + aa) : 0.0;
+                        f[aa][b] = (cv && i0 + aa >= kb && i0 + aa < mp) ? __ldcg(colp + i0 + aa) : 0.0;
                         acc[aa][b] = 0.0;
                     }
                 }
                 for (int t = 0; t < kb; ++t) {
-                    double l[4], uu[4];
-#pragma unroll
-                    for (int aa = 0; aa < 4; ++aa) l[aa] = (i0 + aa < mp) ? P[i0 + aa + t * mp] : 0.0;
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) uu[b] = Uc[t * ldu + idx0 + b];
+                    // i0 and ldp are multiples of 4: two conflict-free 16-byte shared loads per operand (rows beyond
+                    // mp hold stale data whose results are never stored)
+                    const double2 la = *reinterpret_cast<const double2 *>(P + i0 + t * ldp);
+                    const double2 lb = *reinterpret_cast<const double2 *>(P + i0 + t * ldp + 2);
+                    const double2 ua = *reinterpret_cast<const double2 *>(Uc + t * ldu + idx0);
+                    const double2 ub = *reinterpret_cast<const double2 *>(Uc + t * ldu + idx0 + 2);
+                    const double l[4] = {la.x, la.y, lb.x, lb.y}, uu[4] = {ua.x, ua.y, ub.x, ub.y};
 #pragma unroll
                     for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
@@ -272,7 +276,7 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
                         double *colp = F + (size_t)(c0 + b) * m + k0;
 #pragma unroll
                         for (int aa = 0; aa < 4; ++aa)
-                            if (i0 + aa < mp) __stcg(colp + i0 + aa, f[aa][b] - acc[aa][b]);
+                            if (i0 + aa >= kb && i0 + aa < mp) __stcg(colp + i0 + aa, f[aa][b] - acc[aa][b]);
                     }
                 }
             }
@@ -556,7 +560,7 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     for (int l = 0; l < S.nlevels; ++l)
         for (int k = S.level_ptr[l]; k < S.level_ptr[l + 1]; ++k)
             I.level_max_m[l] = std::max(I.level_max_m[l], S.m[S.level_nodes[k]]);
-    const size_t need = ((size_t)S.max_front * NB + (size_t)NB * (S.max_front + CWO)) * sizeof(double);
+    const size_t need = (size_t)NB * (2 * (size_t)((S.max_front + 3) & ~3) + CWO + 4) * sizeof(double);
     if (need > 200 * 1024 || S.max_front > 1024) {
         err = "multifrontal: largest front (" + std::to_string(S.max_front) + ") exceeds the shared-memory panel";
         return false;
@@ -589,7 +593,7 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(nf * c);
             cfg.blockDim = dim3(variant_threads(factor_variant(I.level_max_m[l])));
-            cfg.dynamicSmemBytes = ((size_t)I.level_max_m[l] * NB + (size_t)NB * (I.level_max_m[l] + CWO)) * sizeof(double);
+            cfg.dynamicSmemBytes = (size_t)NB * (2 * (size_t)((I.level_max_m[l] + 3) & ~3) + CWO + 4) * sizeof(double);
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = c;
@@ -653,7 +657,7 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
         const int var = factor_variant(level_max_m[l]);
         cfg.gridDim = dim3(nf * c);
         cfg.blockDim = dim3(variant_threads(var));
-        cfg.dynamicSmemBytes = ((size_t)level_max_m[l] * NB + (size_t)NB * (level_max_m[l] + CWO)) * sizeof(double);
+        cfg.dynamicSmemBytes = (size_t)NB * (2 * (size_t)((level_max_m[l] + 3) & ~3) + CWO + 4) * sizeof(double);
         cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
