@@ -95,6 +95,11 @@ const char *ocp_last_error(const ocp_ctx *ctx);
 void ocp_get_solver_stats(const ocp_ctx *ctx, ocp_solver_stats *out);
 void ocp_reset_solver_stats(ocp_ctx *ctx);
 void ocp_set_viscosity(ocp_ctx *ctx, double viscosity);
+/* Replace the Dirichlet set of the context: rows h_dofs (n) are constrained to h_vals (NULL = 0).  The OCP
+ * pipelines use the homogeneous velocity BC given to ocp_create (OCP_dolfin.py:136); the twin experiment that produced
+ * the reference's u_d data constrains the whole boundary and one pressure line with non-zero data
+ * (plotting/ud_construction_pipeline.py:95-106). */
+int ocp_set_dirichlet(ocp_ctx *ctx, const int32_t *h_dofs, const double *h_vals, int n);
 /* Per-phase line-item timing (ocp_get_solver_stats) synchronises the stream after every phase; it is therefore off
  * by default and switched on only for profiling runs (also: environment OCP_PROFILE=1). */
 void ocp_set_profiling(ocp_ctx *ctx, int on);

@@ -21,7 +21,7 @@ ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "sparse solver error", -
 # every symbol include/ocp_b200.h declares (tests/test_capi_symbols.py checks the header against this list)
 SYMBOLS = [
     "ocp_version", "ocp_device_available", "ocp_create", "ocp_destroy", "ocp_last_error",
-    "ocp_get_solver_stats", "ocp_reset_solver_stats", "ocp_set_viscosity", "ocp_set_profiling",
+    "ocp_get_solver_stats", "ocp_reset_solver_stats", "ocp_set_viscosity", "ocp_set_profiling", "ocp_set_dirichlet",
     "ocp_forward_solve", "ocp_assemble_forward", "ocp_assemble_adjoint", "ocp_project_grad",
     "ocp_velocity_nodal", "ocp_buoy_forward", "ocp_buoy_adjoint_scatter", "ocp_misfit",
     "ocp_adjoint_solve", "ocp_boundary_inner", "ocp_nodal_axpby", "ocp_field_norms", "ocp_traj_transpose",
@@ -173,6 +173,12 @@ class Context:
     def set_profiling(self, on: bool):
         """Line-item timing synchronises after every phase: keep it off outside profiling runs."""
         self.lib.ocp_set_profiling(self._h, int(bool(on)))
+
+    def set_dirichlet(self, dofs: np.ndarray, vals=None):
+        dofs = np.ascontiguousarray(dofs, np.int32)
+        v = None if vals is None else np.ascontiguousarray(vals, np.float64)
+        self._check(self.lib.ocp_set_dirichlet(self._h, _hp(dofs), _hp(v) if v is not None else C.c_void_p(0),
+                                               int(dofs.size)), "ocp_set_dirichlet")
 
     def set_viscosity(self, nu: float):
         self.lib.ocp_set_viscosity(self._h, float(nu))

@@ -67,6 +67,7 @@ struct ocp_ctx {
     int *d_cell_nodes = nullptr, *d_cell_dofs = nullptr, *d_cell_slots = nullptr, *d_cell_nbr = nullptr;
     int *d_dof_ux = nullptr, *d_dof_uy = nullptr, *d_dof_p = nullptr;
     int *d_rowptr = nullptr, *d_col = nullptr, *d_dir = nullptr;
+    double *d_dirval = nullptr;   // inhomogeneous Dirichlet data (null = homogeneous, the OCP pipelines)
     int *d_g1_nodes = nullptr, *d_g1_dofs = nullptr, *d_g1_slots = nullptr;
     int *d_bin_ptr = nullptr, *d_bin_cells = nullptr;
     int *d_m_rowptr = nullptr, *d_m_col = nullptr;   // P1 mass matrix
@@ -187,7 +188,7 @@ int assemble_forward(ocp_ctx *c, const double *d_w, const double *d_f, double *d
     launch_assemble_cells(c->nc, c->d_geom, c->d_cell_dofs, c->d_cell_slots, d_w, c->nu, false, d_vals, d_res, s);
     launch_assemble_facets(c->n_g1, c->d_g1_nodes, c->d_g1_dofs, c->d_g1_slots, c->d_g1_len, c->d_g1_normal,
                            c->d_dof_ux, c->d_dof_uy, d_w, d_f, false, d_vals, d_res, s);
-    if (bc) launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, d_vals, d_res, d_w, s);
+    if (bc) launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, d_vals, d_res, d_w, c->d_dirval, s);
     CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
 }
@@ -199,7 +200,7 @@ int assemble_adjoint(ocp_ctx *c, const double *d_w, double *d_vals, bool bc) {
     launch_assemble_cells(c->nc, c->d_geom, c->d_cell_dofs, c->d_cell_slots, d_w, 1.0, true, d_vals, nullptr, s);
     launch_assemble_facets(c->n_g1, c->d_g1_nodes, c->d_g1_dofs, c->d_g1_slots, c->d_g1_len, c->d_g1_normal,
                            c->d_dof_ux, c->d_dof_uy, d_w, nullptr, true, d_vals, nullptr, s);
-    if (bc) launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, d_vals, nullptr, nullptr, s);
+    if (bc) launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, d_vals, nullptr, nullptr, nullptr, s);
     CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
 }
@@ -237,6 +238,25 @@ void ocp_reset_solver_stats(ocp_ctx *ctx) {
         ctx->stats = ocp_solver_stats{};
         ctx->stats.analyse_ms = ctx->lu_fwd.analyse_ms + ctx->lu_adj.analyse_ms + ctx->lu_mass.analyse_ms;
     }
+}
+
+int ocp_set_dirichlet(ocp_ctx *c, const int32_t *h_dofs, const double *h_vals, int n) {
+    if (!c || n < 0 || (n > 0 && !h_dofs)) return OCP_ERR_INVALID;
+    for (int i = 0; i < n; ++i)
+        if (h_dofs[i] < 0 || h_dofs[i] >= c->ndofs) return OCP_ERR_INVALID;
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_dir);
+    cudaFree(c->d_dirval);
+    c->d_dir = nullptr;
+    c->d_dirval = nullptr;
+    c->n_dir = n;
+    int rc = upload(c, &c->d_dir, h_dofs, (size_t)n);
+    if (rc != OCP_OK) return rc;
+    if (h_vals) {
+        rc = upload(c, &c->d_dirval, h_vals, (size_t)n);
+        if (rc != OCP_OK) return rc;
+    }
+    return OCP_OK;
 }
 
 void ocp_set_profiling(ocp_ctx *ctx, int on) {
@@ -403,7 +423,7 @@ void ocp_destroy(ocp_ctx *c) {
                     c->d_dof_ux, c->d_dof_uy, c->d_dof_p, c->d_rowptr, c->d_col, c->d_dir, c->d_g1_nodes,
                     c->d_g1_dofs, c->d_g1_slots, c->d_bin_ptr, c->d_bin_cells, c->d_m_rowptr, c->d_m_col,
                     c->d_m_vals, c->d_vals, c->d_res, c->d_rhs, c->d_tmp, c->d_rhs4, c->d_scalar, c->d_scratch,
-                    c->d_counter, c->d_parked, c->d_obs_x0, c->d_obs_ud, c->d_cell_nbr, c->d_cellvel, c->d_cellg, c->d_bpriv};
+                    c->d_counter, c->d_parked, c->d_obs_x0, c->d_obs_ud, c->d_cell_nbr, c->d_cellvel, c->d_cellg, c->d_bpriv, c->d_dirval};
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < 8; ++i) cudaFree(c->d_stage[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -560,7 +580,7 @@ int ocp_adjoint_solve(ocp_ctx *c, const double *d_w, const double *d_bnode, doub
         int rc = assemble_adjoint(c, d_w, c->d_vals, true);
         if (rc != OCP_OK) return rc;
         launch_rhs_from_nodal(c->nn, c->nv, c->d_dof_ux, c->d_dof_uy, c->d_dof_p, d_bnode, c->d_rhs, s);
-        launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, nullptr, c->d_rhs, nullptr, s);   // b[d] = 0
+        launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, nullptr, c->d_rhs, nullptr, nullptr, s);   // b[d] = 0
         CUDA_OK(c, cudaGetLastError());
     }
     {

@@ -120,13 +120,13 @@ assemble_facets_kernel(int n_g1, const int *__restrict__ g1_nodes, const int *__
 
 __global__ void dirichlet_kernel(int n_dir, const int *__restrict__ dir, const int *__restrict__ rowptr,
                                  const int *__restrict__ col, double *__restrict__ vals, double *__restrict__ res,
-                                 const double *__restrict__ w) {
+                                 const double *__restrict__ w, const double *__restrict__ dirval) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_dir) return;
     const int d = dir[warp];
     if (vals)
         for (int p = rowptr[d] + lane; p < rowptr[d + 1]; p += 32) vals[p] = (col[p] == d) ? 1.0 : 0.0;
-    if (res && lane == 0) res[d] = w ? w[d] : 0.0;
+    if (res && lane == 0) res[d] = w ? (w[d] - (dirval ? dirval[warp] : 0.0)) : 0.0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -335,10 +335,10 @@ void launch_assemble_facets(int n_g1, const int *g1_nodes, const int *g1_dofs, c
 }
 
 void launch_dirichlet(int n_dir, const int *dir, const int *rowptr, const int *col, double *vals, double *res,
-                      const double *w, cudaStream_t s) {
+                      const double *w, const double *dirval, cudaStream_t s) {
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (n_dir <= 0) return;
-    dirichlet_kernel<<<cdiv((long long)n_dir * 32, 256), 256, 0, s>>>(n_dir, dir, rowptr, col, vals, res, w);
+    dirichlet_kernel<<<cdiv((long long)n_dir * 32, 256), 256, 0, s>>>(n_dir, dir, rowptr, col, vals, res, w, dirval);
 }
 
 void launch_sumsq(int n, const double *v, double *out, double *scratch, unsigned *counter, cudaStream_t s) {

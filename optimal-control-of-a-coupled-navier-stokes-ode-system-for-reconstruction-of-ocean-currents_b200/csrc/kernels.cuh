@@ -47,9 +47,9 @@ void launch_assemble_facets(int n_g1, const int *g1_nodes, const int *g1_dofs, c
                             const double *g1_len, const double *g1_normal, const int *dof_ux, const int *dof_uy,
                             const double *w, const double *f, bool transpose, double *vals, double *res,
                             cudaStream_t s);
-// rows -> identity on the CSR values; res[d] = w[d] (w may be null -> res[d] = 0)
+// rows -> identity on the CSR values; res[d] = w[d] - dirval[d] (w null -> res[d] = 0; dirval null -> 0)
 void launch_dirichlet(int n_dir, const int *dir, const int *rowptr, const int *col, double *vals, double *res,
-                      const double *w, cudaStream_t s);
+                      const double *w, const double *dirval, cudaStream_t s);
 void launch_sumsq(int n, const double *v, double *out, double *scratch, unsigned *counter, cudaStream_t s);
 void launch_axpy(int n, double a, const double *x, double *y, cudaStream_t s);           // y += a x
 void launch_axpby(int n, double a, const double *x, double b, const double *y, double *out, cudaStream_t s);

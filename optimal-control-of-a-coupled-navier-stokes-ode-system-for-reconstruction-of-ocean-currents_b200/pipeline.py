@@ -438,6 +438,14 @@ class OCP:
         d, l2, h1 = self.d_sc[:3].cpu().numpy()
         return float(np.sqrt(d)), float(np.sqrt(l2)), float(np.sqrt(l2 + h1))
 
+    def error_norms(self, w: State, w_ref) -> tuple:
+        """L2 and H1 norm of ``u - u_ref`` - the ``norm_table.txt`` of Pipeline_limits.py:433-443 (``w_ref`` is a W
+        vector, e.g. the stored u_bar of reference_runs/u_bar_chapter_6.3.3)."""
+        d = w.d_w - self._dev(w_ref)
+        self.ctx.field_norms(d, self.d_sc)
+        _, l2, h1 = self.d_sc[:3].cpu().numpy()
+        return float(np.sqrt(l2)), float(np.sqrt(l2 + h1))
+
     def close(self):
         self.ctx.close()
 

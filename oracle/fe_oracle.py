@@ -232,16 +232,19 @@ class FEOracle:
     def forward_jacobian(self, w):
         return self.apply_dirichlet_rows(self.jacobian_unconstrained(w), self.V.dirichlet_dofs)
 
-    def newton_solve(self, f_nodal, w0=None, atol=1e-10, rtol=1e-9, maxit=50, return_history=False):
-        """dolfin NewtonSolver defaults."""
+    def newton_solve(self, f_nodal, w0=None, atol=1e-10, rtol=1e-9, maxit=50, return_history=False,
+                     dir_dofs=None, dir_vals=None):
+        """dolfin NewtonSolver defaults.  ``dir_dofs/dir_vals`` replace the space's homogeneous
+        velocity BC by general Dirichlet data (the twin experiment of plotting/ud_construction_pipeline.py:95-106)."""
         V = self.V
         w = np.zeros(V.ndofs) if w0 is None else w0.copy()
-        d = V.dirichlet_dofs
+        d = V.dirichlet_dofs if dir_dofs is None else np.asarray(dir_dofs)
+        dv = np.zeros(d.size) if dir_vals is None else np.asarray(dir_vals, float)
         hist = []
 
         def resid(w):
             R = self.forward_residual(w, f_nodal)
-            R[d] = w[d]            # bc.apply(b, x): residual of a homogeneous Dirichlet row is w_d - 0
+            R[d] = w[d] - dv       # bc.apply(b, x): residual of a Dirichlet row is w_d - g_d
             return R
 
         R = resid(w)
@@ -251,7 +254,7 @@ class FEOracle:
         while not (hist[-1] < atol or (r0 > 0 and hist[-1] / r0 < rtol)):
             if it >= maxit:
                 raise RuntimeError("Newton solver did not converge")
-            Jm = self.forward_jacobian(w)
+            Jm = self.apply_dirichlet_rows(self.jacobian_unconstrained(w), d)
             dx = spla.splu(Jm.tocsc()).solve(R)
             w = w - dx
             it += 1

@@ -397,3 +397,32 @@ def test_device_buoy_order_does_not_change_results():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert H.rel(a[3], b[3]) < 1e-12                     # mu: per buoy, but grad(u) projection is atomically assembled per context
     assert H.rel(a[4], b[4]) < 1e-11 and abs(a[5] - b[5]) <= 1e-12 * abs(b[5])   # sums: order changes
+
+
+@pytest.mark.parametrize("K,nu", [(10, 0.01), (6, 1.0)])
+def test_twin_experiment_regenerates_reference_data(K, nu):
+    """the u_d generator on the GPU path reproduces the reference's stored field and its
+    x_0_array / u_d_array files."""
+    from ocp_b200.twin import TwinExperiment
+    V = H.square32()
+    xr, ur = H.traj(K)
+    if K == 6:
+        inflow = lambda x, y: (-np.cos(np.pi * x) * np.sin(np.pi * y), np.sin(np.pi * x) * np.cos(np.pi * y))
+    else:
+        inflow = lambda x, y: (0.1 + 0 * x, 0 * x)
+    tw = TwinExperiment(V, viscosity=nu, inflow=inflow, device=dev())
+    w, x, u = tw.solve(xr[:, 0, :])
+    assert tw.newton_its == 3
+    assert np.abs(w - H.field_for(K)).max() < 5e-12
+    assert np.abs(x - xr).max() < 1e-11 and np.abs(u - ur).max() < 1e-11
+
+
+def test_error_norm_table_matches_oracle(sq):
+    """Pipeline_limits.py:433-443: L2 / H1 norm of u - u_bar."""
+    V, ocp = sq
+    O = FEOracle(V, 1.0)
+    w = H.field_for(100)
+    ubar = H.fields()["u_bar"]
+    l2, h1 = ocp.error_norms(State(T(w)), ubar)
+    l2o, h1o = O.l2_h1_norms(w - ubar)
+    assert abs(l2 - l2o) < 1e-12 * l2o and abs(h1 - h1o) < 1e-12 * h1o

@@ -149,3 +149,23 @@ def test_masked_and_parked_buoys_follow_the_reference_branches():
     assert np.all(u[1, 0] == 0) and one(u[1, 1, 0]) and u[1, 1, 1] == 0 and np.all(u[1, 2:] == 0)   # started outside
     assert parked.tolist() == [0, 0, 0, 1]
     assert np.all(x[3, -1] == H.CENTER) and np.all(u[3, -1] == 0) and one(u[3, :-1, 0])
+
+
+@pytest.mark.parametrize("K,nu,its,tol", [(10, 0.01, 3, 1e-12), (2, 1.0, 3, 5e-12), (100, 1.0, 3, 5e-8)])
+def test_K2_twin_experiment_reproduces_stored_fields(K, nu, its, tol):
+    """plotting/ud_construction_pipeline.py:95-106 restated: Newton on the all-Dirichlet problem reproduces the
+    velocity.h5 fields that generated the reference's u_d data (the 100/400/10000-buoy field was stored one Newton
+    step early, residual 2.367e-9, hence the looser bound)."""
+    from ocp_b200.twin import twin_dirichlet
+    V = H.square32()
+    if K == 2:
+        inflow = lambda x, y: (-np.cos(np.pi * x) * np.sin(np.pi * y), np.sin(np.pi * x) * np.cos(np.pi * y))
+    else:
+        inflow = lambda x, y: (0.1 + 0 * x, 0 * x)
+    d, v = twin_dirichlet(V, inflow)
+    assert d.size == 545
+    w, n_it, hist = FEOracle(V, nu).newton_solve(np.zeros((V.num_nodes, 2)), dir_dofs=d, dir_vals=v, return_history=True)
+    assert n_it == its
+    assert np.abs(w - H.field_for(K)).max() < tol
+    if K == 100:
+        assert abs(hist[2] - 2.367e-9) < 2e-11
