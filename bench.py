@@ -386,6 +386,100 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_sweep(args):
+    """--workload sweep: the synthetic drifter sweep of BASELINE.json cfg5 - K_total = 1e7 buoys (uniform start
+    points, numpy default_rng(0)) advected through the cfg3 field and swept backwards, sharded over the ranks
+    (STRONG scaling), one all-reduce of [b | misfit | n_masked] per step.  One step = forward sweep + backward sweep
+    + all-reduce; value = 2 x K_total x 200 buoy-steps / time."""
+    import torch
+    import torch.distributed as dist
+    import ocp_b200  # noqa: F401
+    from ocp_b200.fespace import TaylorHood
+    from ocp_b200.mesh import square_mesh
+    from ocp_b200.pipeline import OCP, Parameters
+    from ocp_b200.sharding import init_from_env, shard_bounds
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        group, rank, world, local = init_from_env("nccl")
+        if group is not None:
+            dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local)), group=group)
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    Kt = args.sweep_buoys
+    lo, hi = shard_bounds(Kt, rank, world)
+    rng = np.random.default_rng(0)
+    x0 = np.stack([rng.uniform(0.1, 1.9, Kt), rng.uniform(0.1, 1.9, Kt)], 1)[lo:hi]
+    V = TaylorHood(square_mesh(args.sweep_mesh))
+    ocp = OCP(V, Parameters(), x0, None, device=dev, group=group, alpha_scale_K=Kt)
+    K = hi - lo
+    if args.sweep_mesh == 32:
+        d_w = torch.from_numpy(golden_field()).to(dev)
+    else:
+        from ocp_b200.pipeline import initial_control
+        d_w = ocp.forward_solve(torch.from_numpy(initial_control(V, "PL")).to(dev)).d_w
+    ocp.ctx.project_grad(d_w, ocp.d_g)
+    ocp._primal(d_w, ocp.d_x, ocp.d_u, ocp.d_mask)
+    torch.mul(ocp.d_u, 1.1, out=ocp.d_ud)                       # u_d = twin field scaled 1.1x (SURVEY 8(d) cfg5)
+
+    def step():
+        ocp._primal(d_w, ocp.d_x, ocp.d_u, ocp.d_mask)
+        ocp.d_acc.zero_()
+        ocp.ctx.buoy_adjoint_scatter(ocp.d_vel, ocp.d_g, K, ocp.d_x, ocp.d_u, ocp.d_ud, ocp.d_mask, ocp.d_parked,
+                                     None, ocp.d_acc)
+        ocp._allreduce(ocp.d_acc)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    if group is not None:
+        dist.barrier(group=group)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    if group is not None:
+        dist.barrier(group=group)
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if group is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=group)
+    ms_step = float(ms.item()) / args.steps
+    misfit = float(ocp.d_acc[2 * V.num_nodes].item())
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        gbs = 80.0 * K * NT / (ms_step * 1e-3) / 1e9            # per GPU: 32 B (fwd) + 48 B (bwd) per buoy-step
+        print(json.dumps({
+            "metric": "sweep_buoy_steps_per_sec", "value": 2.0 * Kt * NT / (ms_step * 1e-3),
+            "unit": "buoy-steps/s (forward + backward sweep)", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"cfg5 synthetic sweep, {Kt} buoys total on square {args.sweep_mesh}x{args.sweep_mesh}",
+                       "K_total": Kt, "K_per_gpu": K, "nt": NT,
+                       "l2": "trajectory arrays (3 x 32 B x K x 200) far exceed L2"},
+            "roofline": {"bound": "hbm", "kernel": "buoy_forward + buoy_adjoint_scatter", "achieved": gbs, "peak": peak,
+                         "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": 80.0 * K * NT},
+            "misfit": misfit}), flush=True)
+    ocp.close()
+    if group is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -394,7 +488,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 2^20-buoy kernel sweep")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "sweep"],
+                    help="cfg3 (default, the headline GD iteration) or the cfg5 synthetic drifter sweep")
+    ap.add_argument("--sweep-buoys", type=int, default=10_000_000)
+    ap.add_argument("--sweep-mesh", type=int, default=32)
     args = ap.parse_args()
+    if args.workload == "sweep" and args.impl == "ours":
+        run_sweep(args)
+        return
     if args.impl == "reference":
         run_reference_arm(args, int(os.environ.get("RANK", "0")))
         return

@@ -96,7 +96,7 @@ class OCP:
     def __init__(self, V: TaylorHood, params: Parameters, x0: np.ndarray, u_d: np.ndarray,
                  device: Optional[torch.device] = None, group=None, alpha_scale_K: Optional[int] = None,
                  sort_buoys: bool = True):
-        """``x0`` (K,2) start points and ``u_d`` (K,nt,2) of THIS rank's buoys.  With a process group the
+        """``x0`` (K,2) start points and ``u_d`` (K,nt,2) of THIS rank's buoys (``u_d=None``: zeros on the device).  With a process group the
         global buoy count is the sum over ranks; alpha is rescaled by the global K (OCP_dolfin.py:76).
         ``sort_buoys`` stores the buoys on the device in a spatially coherent order (sharding.spatial_order);
         every host-facing array keeps the caller's order."""
@@ -112,7 +112,7 @@ class OCP:
         self.ctx = capi.Context(V, params.viscosity, params.dt, self.nt, self.center_of_domain)
         x0 = np.ascontiguousarray(x0, np.float64).reshape(-1, 2)
         self.K = x0.shape[0]
-        if u_d.shape != (self.K, self.nt, 2):
+        if u_d is not None and u_d.shape != (self.K, self.nt, 2):
             raise ValueError(f"u_d must be ({self.K},{self.nt},2), got {u_d.shape}")
         Kg = self.K
         if group is not None:
@@ -137,7 +137,9 @@ class OCP:
         self.d_x0 = torch.from_numpy(x0).to(dev)
         if self.perm is not None:
             self.d_x0 = self.d_x0[self.perm].contiguous()
-        self.d_ud = self._to_time_major(u_d)
+        # u_d = None: synthetic sweeps fill the device array themselves (no 32 GB host array for 1e7 buoys)
+        self.d_ud = (self._to_time_major(u_d) if u_d is not None
+                     else torch.zeros((self.nt, self.K, 2), device=dev, dtype=torch.float64))
         self.d_x = torch.empty((nt, K, 2), device=dev, dtype=f64)
         self.d_u = torch.empty((nt, K, 2), device=dev, dtype=f64)
         self.d_x_ls = self.d_u_ls = None
