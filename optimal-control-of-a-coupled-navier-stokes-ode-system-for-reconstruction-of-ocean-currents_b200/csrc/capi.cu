@@ -92,7 +92,7 @@ struct ocp_ctx {
     int obs_K = 0;
     DirectSolver lu_fwd, lu_adj, lu_mass;
     bool mass_factored = false;
-    int adj_refine = 1;
+    int adj_refine = 0;   // iterative-refinement steps of the adjoint solve (OCP_ADJ_REFINE); 0 is already ~1e-11
     ocp_solver_stats stats{};
     bool profile = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -276,6 +276,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     *out = c;   // returned even on failure so that the caller can read ocp_last_error, then destroy
     c->stream = (cudaStream_t)stream;
     if (const char *ep = getenv("OCP_PROFILE")) c->profile = atoi(ep) != 0;
+    if (const char *er = getenv("OCP_ADJ_REFINE")) c->adj_refine = std::max(0, atoi(er));
     c->nv = d->nv; c->nn = d->nn; c->nc = d->nc; c->ndofs = d->ndofs; c->nnz = d->nnz;
     c->n_dir = d->n_dirichlet; c->n_g1 = d->n_g1; c->nt = d->nt;
     c->nu = d->viscosity; c->dt = d->dt; c->cx = d->center_x; c->cy = d->center_y;

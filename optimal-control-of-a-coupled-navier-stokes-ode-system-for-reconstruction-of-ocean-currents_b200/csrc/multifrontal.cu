@@ -488,7 +488,7 @@ struct MultifrontalLU::Impl {
     double *F = nullptr, *dinv = nullptr;
     int *dinv_ptr = nullptr;
     long long *prof = nullptr;   // optional per-level phase cycle counters (OCP_MF_PROF=1)
-    std::vector<int> level_max_m, level_cluster, level_cw;
+    std::vector<int> level_max_m, level_cluster;
     // CUDA graphs of the factor / solve launch sequences, keyed by the (fixed) device pointer they operate on
     std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs;
     cudaStream_t cap_stream = nullptr;
@@ -584,7 +584,6 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     int max_cluster = 16;
     if (const char *envc = getenv("OCP_MF_MAX_CLUSTER")) max_cluster = std::max(1, atoi(envc));
     I.level_cluster.assign(S.nlevels, 1);
-    I.level_cw.assign(S.nlevels, 32);
     for (int l = 0; l < S.nlevels && e == cudaSuccess; ++l) {
         const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
         int c = 1;

@@ -204,8 +204,8 @@ class OCP:
         return torch.from_numpy(np.ascontiguousarray(a, np.float64)).to(self.device)
 
     def _allreduce(self, t: torch.Tensor):
-        if self.group is not None and self.world > 1:
-            torch.distributed.all_reduce(t, group=self.group)
+        from .sharding import allreduce_accumulator
+        allreduce_accumulator(t, self.group)
 
     def set_control(self, f_nodal: np.ndarray):
         self.d_f.copy_(self._dev(f_nodal))
