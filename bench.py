@@ -32,6 +32,10 @@ sys.path.insert(0, ROOT)
 K_PER_GPU = 10_000
 NT = 200
 PUBLISHED_BUOY_STEPS_PER_S = 4.0e3          # BASELINE.md section 1 (derived from 1500 s / iteration)
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full captures (profiles/)
+NCU_TRAFFIC_INSTEP_BACKWARD = 96_212_736 + 3_859_456          # K = 10 000: algorithmic 96 000 000 B
+NCU_TRAFFIC_SWEEP_BACKWARD = 10_081_863_000 + 5_742_000       # K = 2^20:   algorithmic 10 066 329 600 B
+NCU_TRAFFIC_SWEEP_FORWARD = 19_127_000 + 6_656_207_000        # K = 2^20:   algorithmic  6 710 886 400 B
 METRIC = "gd_buoy_steps_per_sec"
 UNIT = "buoy-steps/s (3 sweeps x K x 200 per GD iteration)"
 
@@ -324,7 +328,9 @@ def run_ours(args):
                  "backward_gbs": 48.0 * Ks * NT / (mb * 1e-3) / 1e9, "forward_gbs": 32.0 * Ks * NT / (mf * 1e-3) / 1e9,
                  "backward_frac_of_peak": 48.0 * Ks * NT / (mb * 1e-3) / 1e9 / peak,
                  "forward_frac_of_peak": 32.0 * Ks * NT / (mf * 1e-3) / 1e9 / peak,
-                 "buoy_steps_per_sec_fwd_plus_bwd": 2.0 * Ks * NT / ((mb + mf) * 1e-3)}
+                 "buoy_steps_per_sec_fwd_plus_bwd": 2.0 * Ks * NT / ((mb + mf) * 1e-3),
+                 "backward_traffic": NCU_TRAFFIC_SWEEP_BACKWARD, "forward_traffic": NCU_TRAFFIC_SWEEP_FORWARD,
+                 "traffic_source": "profiles/prof_buoy_final.raw.txt"}
         big.close()
         del big
 
@@ -372,11 +378,15 @@ def run_ours(args):
                 "n_solve_per_step": stats["n_solve"] / nprof,
                 "one_time_symbolic_analysis_ms": stats["analyse_ms"]},
             "roofline": {"bound": "hbm", "kernel": "buoy_adjoint_scatter_kernel", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_INSTEP_BACKWARD,
+                         "traffic_source": "profiles/prof_instep_backward.raw.txt (ncu --set full, dram read+write)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_back,
                          "note": "in-step launch at K=10000 is latency-bound (64 MB of trajectories); "
                                  "see roofline_sweep for the same kernel at 2^20 buoys"},
             "roofline_sweep": sweep,
+            "dominant_by_time": "mf_factor_kernel (multifrontal LU, ~64% of the step; latency / fp64-pipe bound, no "
+                                "bandwidth roofline - see profiles/launches_r1_final_summary.txt)",
             "cpu_baseline": cpu,
             "J_after_update": J, "J_at_q0_e2e": J2,
         }
