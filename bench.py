@@ -214,7 +214,7 @@ def run_ours(args):
         flush.zero_()
         ocp.d_f.copy_(d_f0)
         ocp.gradient_step(ocp.d_f)
-        ocp.d_f.add_(ocp.d_grad, alpha=-LR)
+        ocp.ctx.nodal_axpby(1.0, ocp.d_f, -LR, ocp.d_grad, ocp.d_f)       # f <- f - LR (alpha f - z), OCP_dolfin.py:426
         return ocp._cost_from_acc(ocp.d_f)
 
     h_f = torch.from_numpy(f0.copy()).pin_memory()

@@ -326,7 +326,7 @@ class OCP:
         rows1, rows2 = [], []
 
         def Jat(hh):
-            torch.add(d_f, d_df, alpha=hh, out=fpert)
+            self.ctx.nodal_axpby(1.0, d_f, hh, d_df, fpert)
             self.forward_solve(fpert, w0=w)
             self.ctx.velocity_nodal(w.d_w, self.d_vel)
             self.ctx.buoy_forward(self.d_vel, self.d_x0, self.K, self.d_x, self.d_u, None, mask, self.d_parked)
@@ -399,7 +399,7 @@ class OCP:
                     self.d_x_ls, self.d_u_ls = torch.empty_like(self.d_x), torch.empty_like(self.d_u)
                 while True:
                     inner += 1
-                    torch.add(d_f, self.d_grad, alpha=-LR, out=self.d_f_ls)          # f + LR*df
+                    self.ctx.nodal_axpby(1.0, d_f, -LR, self.d_grad, self.d_f_ls)    # f + LR*df, df = -(alpha f - z)
                     self.ctx.forward_solve(self.d_f_ls, self.d_w_ls, True)
                     self._primal(self.d_w_ls, self.d_x_ls, self.d_u_ls, self.d_mask_ls)
                     J_new = self._cost(self.d_u_ls, self.d_f_ls)
@@ -414,7 +414,7 @@ class OCP:
             res.inner_time.append(time.time() - t1)
             res.inner_iterations.append(inner)
             # control update f <- f - LR (alpha f - z), OCP_dolfin.py:426
-            d_f.add_(self.d_grad, alpha=-LR)
+            self.ctx.nodal_axpby(1.0, d_f, -LR, self.d_grad, d_f)
             # J_array uses the OLD velocities with the NEW control (OCP_dolfin.py:426-429)
             res.J_array.append(self._cost_from_acc(d_f))
             self.ctx.field_norms(self.d_w, self.d_sc)
