@@ -1,6 +1,8 @@
 """Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the committed FEniCS
 fixtures.  Bars (BASELINE.json north_star): cell indices and CSR pattern bit-exact, assembled matrices 1e-12 rel,
 trajectories 1e-10 (we get bit-exact), cost and gradient 1e-8 rel."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -426,3 +428,57 @@ def test_error_norm_table_matches_oracle(sq):
     l2, h1 = ocp.error_norms(State(T(w)), ubar)
     l2o, h1o = O.l2_h1_norms(w - ubar)
     assert abs(l2 - l2o) < 1e-12 * l2o and abs(h1 - h1o) < 1e-12 * h1o
+
+
+def _sharded_worker(rank, world, port, q):
+    import os
+    import sys
+    sys.path.insert(0, H.ROOT)
+    sys.path.insert(0, os.path.join(H.ROOT, "tests"))
+    import torch.distributed as dist
+    from ocp_b200.sharding import shard_buoys
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # gloo: both ranks share the one test GPU
+    try:
+        V = H.square32()
+        xr, ud = H.traj(100)
+        x0, ud_loc = shard_buoys(xr[:, 0, :].copy(), ud, rank, world)
+        ocp = OCP(V, Parameters(), x0, ud_loc, device=torch.device("cuda:0"), group=dist.group.WORLD)
+        assert ocp.K_global == 100 and abs(ocp.alpha - 1e-4) < 1e-18
+        r = ocp.run(initial_control(V, "PL"), Knobs(num_steps=2, use_line_search=True))
+        q.put((rank, r.J_array, r.inner_iterations, r.f, float(ocp.d_acc[2 * V.num_nodes])))
+        ocp.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_buoys_sharded_over_two_ranks_match_single_rank():
+    """buoys partitioned over ranks, one all-reduce of [b | misfit | n_masked] per gradient evaluation
+    (plus the misfit scalar in the line search); every rank ends with the single-rank cost history and control."""
+    import torch.multiprocessing as mp
+    V = H.square32()
+    xr, ud = H.traj(100)
+    ocp = OCP(V, Parameters(), xr[:, 0, :].copy(), ud, device=dev())
+    ref = ocp.run(initial_control(V, "PL"), Knobs(num_steps=2, use_line_search=True))
+    ocp.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        rank, J, inner, f, misfit = q.get(timeout=600)
+        got[rank] = (J, inner, f, misfit)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    g1 = np.unique(V.g1_nodes)
+    for rank in (0, 1):
+        J, inner, f, misfit = got[rank]
+        assert inner == ref.inner_iterations
+        assert np.allclose(J, ref.J_array, rtol=1e-11, atol=0)
+        assert H.rel(f[g1], ref.f[g1]) < 1e-9
+    assert got[0][3] == got[1][3]                                # the all-reduced accumulator is identical on both ranks
