@@ -19,6 +19,7 @@ Layout written by dolfin for a function called ``name``::
 """
 from __future__ import annotations
 
+import os
 import struct
 from typing import Dict
 
@@ -185,3 +186,173 @@ def read_checkpoint(path: str, name: str | None = None) -> Dict[str, np.ndarray]
     out["cell_dofs"] = out["cell_dofs"].reshape(-1).astype(np.int64)
     out["topology"] = out["topology"].astype(np.int64)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Writer: the same file structure dolfin's ``XDMFFile.write_checkpoint`` produces through libhdf5 (superblock v0,
+# v1 object headers, symbol-table groups with a v1 B-tree + local heap, contiguous datasets carrying the dataspace
+# / datatype / fill-value / layout / mtime messages and dolfin's ``partition`` attribute) - OCP_dolfin.py:440-441,
+# 485-486, 578-588.  h5py / libhdf5 are not available here, so the writer is validated by reading its files back
+# with ``H5File`` and by comparing its object-header message set with the reference's own checkpoints
+# (tests/test_checkpoint_io.py).
+# ---------------------------------------------------------------------------------------------------------------
+_LEAF_K, _INTERNAL_K = 4, 16
+
+
+def _pad8(b: bytes) -> bytes:
+    return b + b"\0" * (-len(b) % 8)
+
+
+def _dtype_message(dt: np.dtype) -> bytes:
+    dt = np.dtype(dt)
+    if dt.kind in "iu":
+        bits0 = 0x08 if dt.kind == "i" else 0x00
+        return struct.pack("<BBBBIHH", 0x10, bits0, 0, 0, dt.itemsize, 0, 8 * dt.itemsize) + b"\0" * 4
+    if dt == np.float64:
+        return bytes.fromhex("11203f000800000000004000340b0034ff03000000000000")
+    raise H5FormatError(f"cannot write dtype {dt}")
+
+
+def _message(mtype: int, data: bytes) -> bytes:
+    data = _pad8(data)
+    return struct.pack("<HHB3x", mtype, len(data), 0) + data
+
+
+def _object_header(messages) -> bytes:
+    body = b"".join(messages)
+    return struct.pack("<BBHII4x", 1, 0, len(messages), 1, len(body)) + body
+
+
+class _Writer:
+    def __init__(self):
+        self.buf = bytearray(96)          # superblock placeholder
+
+    def alloc(self, data: bytes) -> int:
+        self.buf += b"\0" * (-len(self.buf) % 8)
+        addr = len(self.buf)
+        self.buf += data
+        return addr
+
+    def dataset(self, arr: np.ndarray, mtime: int) -> int:
+        arr = np.ascontiguousarray(arr)
+        if arr.ndim == 1:
+            arr = arr.reshape(-1, 1)
+        raw = arr.astype(arr.dtype.newbyteorder("<"), copy=False).tobytes()
+        data_addr = self.alloc(raw)
+        rank = arr.ndim
+        dims = struct.pack("<%dQ" % rank, *arr.shape)
+        dspace = struct.pack("<BBB5x", 1, rank, 1) + dims + dims            # max dims = dims
+        attr_dt = _dtype_message(np.dtype("<u8"))[:12]
+        attr = (struct.pack("<BBHHH", 1, 0, 10, 12, 24) + _pad8(b"partition\0") + _pad8(attr_dt)
+                + struct.pack("<BBB5xQQ", 1, 1, 1, 1, 1) + struct.pack("<Q", 0))
+        msgs = [
+            _message(0x01, dspace),
+            _message(0x03, _dtype_message(arr.dtype)),
+            _message(0x05, bytes.fromhex("0202020100000000")),
+            _message(0x08, struct.pack("<BBQQ", 3, 1, data_addr, len(raw))),
+            _message(0x12, struct.pack("<B3xI", 1, mtime)),
+            _message(0x0C, attr),
+        ]
+        return self.alloc(_object_header(msgs))
+
+    def group(self, children: dict) -> tuple:
+        """children: name -> (object header address, (btree, heap) for groups or None). Returns (hdr, btree, heap)."""
+        names = sorted(children)
+        if len(names) > 2 * _LEAF_K:
+            raise H5FormatError("more than 8 links per group are not needed for checkpoints")
+        heap_data = bytearray(8)                       # offset 0: the empty name
+        offs = {}
+        for n in names:
+            offs[n] = len(heap_data)
+            heap_data += _pad8(n.encode() + b"\0")
+        if len(heap_data) < 88:                        # libhdf5's default data segment, rest is one free block
+            free_off = len(heap_data)
+            free = bytearray(88 - free_off)
+            struct.pack_into("<QQ", free, 0, 1, len(free))
+            heap_data += free
+        else:
+            free_off = 1                               # H5HL_FREE_NULL
+        data_addr = self.alloc(bytes(heap_data))
+        heap = self.alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), free_off, data_addr))
+        snod = bytearray(8 + 2 * _LEAF_K * 40)
+        snod[:4] = b"SNOD"
+        struct.pack_into("<BBH", snod, 4, 1, 0, len(names))
+        for k, n in enumerate(names):
+            hdr, sub = children[n]
+            if sub is None:
+                struct.pack_into("<QQII16x", snod, 8 + 40 * k, offs[n], hdr, 0, 0)
+            else:
+                struct.pack_into("<QQIIQQ", snod, 8 + 40 * k, offs[n], hdr, 1, 0, sub[0], sub[1])
+        snod_addr = self.alloc(bytes(snod))
+        tree = bytearray(24 + (2 * _INTERNAL_K + 1) * 8 + 2 * _INTERNAL_K * 8)
+        tree[:4] = b"TREE"
+        struct.pack_into("<BBHQQ", tree, 4, 0, 0, 1, _UNDEF, _UNDEF)
+        struct.pack_into("<QQQ", tree, 24, 0, snod_addr, offs[names[-1]] if names else 0)
+        btree = self.alloc(bytes(tree))
+        hdr = self.alloc(_object_header([_message(0x11, struct.pack("<QQ", btree, heap))]))
+        return hdr, btree, heap
+
+    def finish(self, root) -> bytes:
+        hdr, btree, heap = root
+        self.buf += b"\0" * (-len(self.buf) % 8)
+        sb = _SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, _LEAF_K, _INTERNAL_K, 0)
+        sb += struct.pack("<QQQQ", 0, _UNDEF, len(self.buf), _UNDEF)
+        sb += struct.pack("<QQIIQQ", 0, hdr, 1, 0, btree, heap)
+        assert len(sb) == 96
+        self.buf[:96] = sb
+        return bytes(self.buf)
+
+
+def write_checkpoint(path_h5: str, name: str, topology, geometry, cell_dofs, vector, dofs_per_cell: int,
+                     mtime: int = 0, element_degree: int = 2, value_rank: int = 1) -> str:
+    """Write ``<name>/<name>_0/{mesh/{topology,geometry},cell_dofs,x_cell_dofs,cells,vector}`` like dolfin's
+    ``write_checkpoint(fn, name, 0)`` and the companion ``.xdmf``; returns the xdmf path."""
+    topology = np.asarray(topology, np.int32)
+    geometry = np.asarray(geometry, np.float64)
+    cell_dofs = np.asarray(cell_dofs, np.int32).reshape(-1)
+    vector = np.asarray(vector, np.float64).reshape(-1)
+    nc = topology.shape[0]
+    w = _Writer()
+    ds = lambda a: (w.dataset(a, mtime), None)
+    mesh = w.group({"topology": ds(topology), "geometry": ds(geometry)})
+    inner = w.group({
+        "mesh": (mesh[0], mesh[1:]),
+        "cell_dofs": ds(cell_dofs),
+        "x_cell_dofs": ds(np.arange(nc + 1, dtype=np.uint64) * np.uint64(dofs_per_cell)),
+        "cells": ds(np.arange(nc, dtype=np.uint64)),
+        "vector": ds(vector),
+    })
+    outer = w.group({f"{name}_0": (inner[0], inner[1:])})
+    root = w.group({name: (outer[0], outer[1:])})
+    with open(path_h5, "wb") as fh:
+        fh.write(w.finish(root))
+    base = os.path.basename(path_h5)
+    grp = f"{base}:{name}/{name}_0"
+    atype = "Vector" if value_rank == 1 else "Scalar"
+    xdmf = f"""<?xml version="1.0"?>
+<Xdmf Version="3.0">
+  <Domain>
+    <Grid GridType="Collection" CollectionType="Temporal" Name="{name}">
+      <Grid Name="{name}_0" GridType="Uniform">
+        <Topology NumberOfElements="{nc}" TopologyType="Triangle" NodesPerElement="3">
+          <DataItem Dimensions="{nc} 3" NumberType="UInt" Format="HDF">{grp}/mesh/topology</DataItem>
+        </Topology>
+        <Geometry GeometryType="XY">
+          <DataItem Dimensions="{geometry.shape[0]} 2" Format="HDF">{grp}/mesh/geometry</DataItem>
+        </Geometry>
+        <Time Value="0.000000000000000e+00" />
+        <Attribute ItemType="FiniteElementFunction" ElementFamily="CG" ElementDegree="{element_degree}" ElementCell="triangle" Name="{name}" Center="Other" AttributeType="{atype}">
+          <DataItem Dimensions="{cell_dofs.size} 1" NumberType="UInt" Format="HDF">{grp}/cell_dofs</DataItem>
+          <DataItem Dimensions="{vector.size} 1" NumberType="Float" Format="HDF">{grp}/vector</DataItem>
+          <DataItem Dimensions="{nc + 1} 1" NumberType="UInt" Format="HDF">{grp}/x_cell_dofs</DataItem>
+          <DataItem Dimensions="{nc} 1" NumberType="UInt" Format="HDF">{grp}/cells</DataItem>
+        </Attribute>
+      </Grid>
+    </Grid>
+  </Domain>
+</Xdmf>
+"""
+    path_x = os.path.splitext(path_h5)[0] + ".xdmf"
+    with open(path_x, "w") as fh:
+        fh.write(xdmf)
+    return path_x

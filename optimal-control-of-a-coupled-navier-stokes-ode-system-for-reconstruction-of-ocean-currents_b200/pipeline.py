@@ -419,6 +419,11 @@ class OCP:
             res.J_array.append(self._cost_from_acc(d_f))
             self.ctx.field_norms(self.d_w, self.d_sc)
             res.divs_u.append(float(np.sqrt(self.d_sc[0].item())))
+            if out_dir is not None:
+                # control checkpoint of this iteration (OCP_dolfin.py:440-441); resume with checkpoint.read_control
+                from . import checkpoint
+                os.makedirs(os.path.join(out_dir, "checkpoints"), exist_ok=True)
+                checkpoint.write_control(os.path.join(out_dir, "checkpoints", "q.h5"), self.V, d_f.cpu().numpy())
             if callback is not None:
                 callback(i, self, res)
             if res.exit_reason == "line_search_stalled":
@@ -432,7 +437,44 @@ class OCP:
                 break
         res.LR = LR
         res.f = d_f.cpu().numpy()
+        if out_dir is not None:
+            self.save_run(res, out_dir, kn)
         return res
+
+    def save_run(self, res: RunResult, out_dir: str, kn: Knobs):
+        """The files the reference writes at the end of a run, same names and text formats: ``timings.txt``
+        (OCP_dolfin.py:476-482), ``q_backup/q.xdmf`` (485-486), ``u_divergence.txt`` (489-492), ``variables.txt``
+        (495-507), ``J_array.npy`` (510-511), ``paraview/checkpoint/{u,p}.xdmf`` (578-588).  Plots are out of scope."""
+        from . import checkpoint
+        os.makedirs(os.path.join(out_dir, "q_backup"), exist_ok=True)
+        with open(os.path.join(out_dir, "timings.txt"), "w") as fh:
+            for k, it in enumerate(res.inner_iterations):
+                fh.write(f"Iteration {k}:\n")
+                fh.write(f"  outer loop time: {res.outer_time[k]:.6f} seconds\n")
+                fh.write(f"  inner loop time: {res.inner_time[k]:.6f} seconds\n")
+                fh.write(f"  inner loop iterations: {it}\n")
+                fh.write("-" * 40 + "\n")
+        checkpoint.write_control(os.path.join(out_dir, "q_backup", "q.h5"), self.V, res.f)
+        with open(os.path.join(out_dir, "u_divergence.txt"), "w") as fh:
+            for i, dv in enumerate(res.divs_u):
+                fh.write("div(u) \t \t \t i  \n")
+                fh.write(f" {dv} \t {i} \n")
+        nx = int(round(np.sqrt(self.V.mesh.num_cells / 2))) if not self.V.mesh.l_shape else self.V.mesh.num_cells
+        with open(os.path.join(out_dir, "variables.txt"), "w") as fh:
+            fh.write("mesh resolution: %s \n" % nx)
+            fh.write("ud type: %s \n" % ("L-shape" if self.V.mesh.l_shape else "custom_ud"))
+            fh.write("t0: %s \n" % self.params.t0)
+            fh.write("T: %s \n" % self.params.T)
+            fh.write("dt: %s \n" % self.params.dt)
+            fh.write("viscosity: %s \n" % self.params.viscosity)
+            fh.write("buoy count: %s \n" % self.K_global)
+            fh.write("LR: %s \n" % res.LR)
+            fh.write("LR_MAX: %s \n" % kn.LR_MAX)
+            fh.write("LR_MIN: %s \n" % kn.LR_MIN)
+            fh.write("conv. crit.: %s \n" % kn.conv_crit)
+            fh.write("gradient descent steps: %s \n" % kn.num_steps)
+        np.save(os.path.join(out_dir, "J_array.npy"), np.array(res.J_array))
+        checkpoint.write_state(os.path.join(out_dir, "paraview", "checkpoint"), self.V, self.d_w.cpu().numpy())
 
     def field_norms(self, w: State):
         """(||div u||, ||u||_L2, ||u||_H1) - OCP_dolfin.py:430, Pipeline_limits.py:433-443."""

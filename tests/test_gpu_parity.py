@@ -482,3 +482,29 @@ def test_buoys_sharded_over_two_ranks_match_single_rank():
         assert np.allclose(J, ref.J_array, rtol=1e-11, atol=0)
         assert H.rel(f[g1], ref.f[g1]) < 1e-9
     assert got[0][3] == got[1][3]                                # the all-reduced accumulator is identical on both ranks
+
+
+def test_run_writes_the_reference_output_files_and_resumes(tmp_path):
+    """Output files of a run (names / formats of OCP_dolfin.py:476-511, 578-588) and resume from the control
+    checkpoint (OCP_dolfin.py:151-160)."""
+    from ocp_b200 import checkpoint
+    V = H.square32()
+    xr, ud = H.traj(6)
+    ocp = OCP(V, Parameters(), xr[:, 0, :].copy(), ud, device=dev())
+    out = str(tmp_path / "run")
+    f0 = initial_control(V, "OCP")
+    r3 = ocp.run(f0, Knobs(num_steps=3, use_line_search=True))
+    r2 = ocp.run(f0, Knobs(num_steps=2, use_line_search=True), out_dir=out)
+    for name in ("timings.txt", "u_divergence.txt", "variables.txt", "J_array.npy", "q_backup/q.xdmf", "q_backup/q.h5",
+                 "checkpoints/q.h5", "paraview/checkpoint/u.h5", "paraview/checkpoint/p.xdmf"):
+        assert os.path.exists(os.path.join(out, name)), name
+    assert np.allclose(np.load(os.path.join(out, "J_array.npy")), r2.J_array)
+    assert "buoy count: 6" in open(os.path.join(out, "variables.txt")).read()
+    # resume: third iteration from the checkpointed control equals the uninterrupted run
+    q = checkpoint.read_control(os.path.join(out, "checkpoints", "q.h5"), V)
+    assert np.array_equal(q, r2.f)
+    r1 = ocp.run(q, Knobs(num_steps=1, use_line_search=True), LR=r2.LR)
+    assert abs(r1.J_array[0] - r3.J_array[2]) <= 1e-10 * abs(r3.J_array[2])
+    w = checkpoint.read_state(os.path.join(out, "paraview/checkpoint/u.h5"), V, "u")
+    assert w.shape == (V.ndofs,)
+    ocp.close()
