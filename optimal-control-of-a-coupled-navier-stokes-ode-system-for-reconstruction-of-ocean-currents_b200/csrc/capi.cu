@@ -90,7 +90,8 @@ struct ocp_ctx {
     // resident observations (the reference's module globals u_d, xsarr, ysarr; OCP_dolfin.py:176-183)
     double *d_obs_x0 = nullptr, *d_obs_ud = nullptr;
     int obs_K = 0;
-    DirectSolver lu_fwd, lu_adj, lu_mass;
+    DirectSolver lu_fwd, lu_adj, lu_mass, lu_stokes;
+    bool stokes_valid = false;   // lu_stokes holds the factors of dF/dw at w = 0 (the Stokes operator + BC rows)
     bool mass_factored = false;
     int adj_refine = 0;   // iterative-refinement steps of the adjoint solve (OCP_ADJ_REFINE); 0 is already ~1e-11
     ocp_solver_stats stats{};
@@ -236,7 +237,7 @@ void ocp_get_solver_stats(const ocp_ctx *ctx, ocp_solver_stats *out) {
 void ocp_reset_solver_stats(ocp_ctx *ctx) {
     if (ctx) {
         ctx->stats = ocp_solver_stats{};
-        ctx->stats.analyse_ms = ctx->lu_fwd.analyse_ms + ctx->lu_adj.analyse_ms + ctx->lu_mass.analyse_ms;
+        ctx->stats.analyse_ms = ctx->lu_fwd.analyse_ms + ctx->lu_adj.analyse_ms + ctx->lu_mass.analyse_ms + ctx->lu_stokes.analyse_ms;
     }
 }
 
@@ -250,6 +251,7 @@ int ocp_set_dirichlet(ocp_ctx *c, const int32_t *h_dofs, const double *h_vals, i
     c->d_dir = nullptr;
     c->d_dirval = nullptr;
     c->n_dir = n;
+    c->stokes_valid = false;
     int rc = upload(c, &c->d_dir, h_dofs, (size_t)n);
     if (rc != OCP_OK) return rc;
     if (h_vals) {
@@ -264,7 +266,10 @@ void ocp_set_profiling(ocp_ctx *ctx, int on) {
 }
 
 void ocp_set_viscosity(ocp_ctx *ctx, double viscosity) {
-    if (ctx) ctx->nu = viscosity;
+    if (ctx) {
+        ctx->nu = viscosity;
+        ctx->stokes_valid = false;
+    }
 }
 
 int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
@@ -411,10 +416,11 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     std::vector<unsigned char> kind0(nv, 0);
     if (!c->lu_fwd.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data(), c->err) ||
         !c->lu_adj.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data(), c->err) ||
+        !c->lu_stokes.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data(), c->err) ||
         !c->lu_mass.configure(nv, c->m_nnz, m_rowptr.data(), m_col.data(), c->d_m_rowptr, c->d_m_col, d->node_coords,
                               kind0.data(), c->err))
         return OCP_ERR_SOLVER;
-    c->stats.analyse_ms = c->lu_fwd.analyse_ms + c->lu_adj.analyse_ms + c->lu_mass.analyse_ms;
+    c->stats.analyse_ms = c->lu_fwd.analyse_ms + c->lu_adj.analyse_ms + c->lu_mass.analyse_ms + c->lu_stokes.analyse_ms;
     return OCP_OK;
 }
 
@@ -461,17 +467,22 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
     double r0 = 0.0, r = 0.0;
     int it = 0;
     for (;;) {
+        // The Newton matrix at the zero initial guess is the Stokes operator (convection and the Gamma_1 term vanish
+        // at u = 0): it does not depend on the control, so its factors are computed once per context and reused by the
+        // first Newton step of every forward solve that starts from zero (OCP_dolfin.py:315, 395: `w = Function(W)`).
+        const bool stokes_step = zero_init && it == 0;
         {
             PhaseTimer t(c, &c->stats.assemble_ms);
             // residual and Newton matrix at the current iterate in one pass over the cells
-            int rc = assemble_forward(c, d_w, d_f, c->d_vals, c->d_res, true);
+            double *vals = (stokes_step && c->stokes_valid) ? nullptr : c->d_vals;
+            int rc = assemble_forward(c, d_w, d_f, vals, c->d_res, true);
             if (rc != OCP_OK) return rc;
             launch_sumsq(n, c->d_res, c->d_scalar, c->d_scratch, c->d_counter, s);
         }
         double ss;
         int rc = read_scalar(c, c->d_scalar, 1, &ss);
         if (rc != OCP_OK) return rc;
-        if (!c->lu_fwd.check(c->err)) return OCP_ERR_SOLVER;   // stream is idle here: pivot flag of the last factor
+        if (!c->lu_fwd.check(c->err) || !c->lu_stokes.check(c->err)) return OCP_ERR_SOLVER;   // stream is idle: pivot flags
         r = std::sqrt(ss);
         if (it == 0) r0 = r;
         if (h_res_hist) h_res_hist[it] = r;
@@ -486,14 +497,16 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
             if (newton_its) *newton_its = it;
             return OCP_ERR_NOT_CONVERGED;
         }
-        {
+        DirectSolver &lu = stokes_step ? c->lu_stokes : c->lu_fwd;
+        if (!(stokes_step && c->stokes_valid)) {
             PhaseTimer t(c, &c->stats.factor_ms);
-            if (!c->lu_fwd.factor(c->d_vals, s, c->err)) return OCP_ERR_SOLVER;
+            if (!lu.factor(c->d_vals, s, c->err)) return OCP_ERR_SOLVER;
             c->stats.n_factor++;
+            if (stokes_step) c->stokes_valid = true;
         }
         {
             PhaseTimer t(c, &c->stats.solve_ms);
-            if (!c->lu_fwd.solve(c->d_res, s, c->err)) return OCP_ERR_SOLVER;   // d_res <- dx
+            if (!lu.solve(c->d_res, s, c->err)) return OCP_ERR_SOLVER;   // d_res <- dx
             launch_axpy(n, -1.0, c->d_res, d_w, s);
             c->stats.n_solve++;
         }
