@@ -53,6 +53,13 @@ struct DirectSolver {
     bool solve(double *d_x, cudaStream_t s, std::string &err) {
         return use_mf ? mf.solve(d_x, s, err) : rf.solve(d_x, s, err);
     }
+    bool solve_transposed(double *d_x, cudaStream_t s, std::string &err) {
+        if (!use_mf) {
+            err = "transposed solve needs the multifrontal solver";
+            return false;
+        }
+        return mf.solve(d_x, s, err, true);
+    }
     bool check(std::string &err) { return use_mf ? mf.check(err) : true; }
 };
 
@@ -92,6 +99,9 @@ struct ocp_ctx {
     int obs_K = 0;
     DirectSolver lu_fwd, lu_adj, lu_mass, lu_stokes;
     bool stokes_valid = false;   // lu_stokes holds the factors of dF/dw at w = 0 (the Stokes operator + BC rows)
+    DirectSolver *last_newton_lu = nullptr;   // factors used by the last Newton step of the last forward solve
+    bool adj_reuse = true;                    // adjoint solve through the transposed Newton factors (nu == 1 only)
+    int n_adj_reused = 0, n_adj_fallback = 0;
     bool mass_factored = false;
     int adj_refine = 0;   // iterative-refinement steps of the adjoint solve (OCP_ADJ_REFINE); 0 is already ~1e-11
     ocp_solver_stats stats{};
@@ -282,6 +292,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     c->stream = (cudaStream_t)stream;
     if (const char *ep = getenv("OCP_PROFILE")) c->profile = atoi(ep) != 0;
     if (const char *er = getenv("OCP_ADJ_REFINE")) c->adj_refine = std::max(0, atoi(er));
+    if (const char *er = getenv("OCP_ADJ_REUSE")) c->adj_reuse = atoi(er) != 0;
     c->nv = d->nv; c->nn = d->nn; c->nc = d->nc; c->ndofs = d->ndofs; c->nnz = d->nnz;
     c->n_dir = d->n_dirichlet; c->n_g1 = d->n_g1; c->nt = d->nt;
     c->nu = d->viscosity; c->dt = d->dt; c->cx = d->center_x; c->cy = d->center_y;
@@ -507,6 +518,7 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
         {
             PhaseTimer t(c, &c->stats.solve_ms);
             if (!lu.solve(c->d_res, s, c->err)) return OCP_ERR_SOLVER;   // d_res <- dx
+            c->last_newton_lu = &lu;
             launch_axpy(n, -1.0, c->d_res, d_w, s);
             c->stats.n_solve++;
         }
@@ -596,6 +608,35 @@ int ocp_adjoint_solve(ocp_ctx *c, const double *d_w, const double *d_bnode, doub
         launch_rhs_from_nodal(c->nn, c->nv, c->d_dof_ux, c->d_dof_uy, c->d_dof_p, d_bnode, c->d_rhs, s);
         launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, nullptr, c->d_rhs, nullptr, nullptr, s);   // b[d] = 0
         CUDA_OK(c, cudaGetLastError());
+    }
+    // ---- fast path.  With viscosity 1 the adjoint matrix is the transpose of the Newton matrix at the converged state
+    //  with the BC rows reset, and the last Newton step of the forward solve factored that matrix one
+    // iterate earlier (|w_n - w_{n-1}| ~ 1e-9).  So solve with the TRANSPOSED Newton factors and one refinement step
+    // against the exactly assembled adjoint matrix - no factorisation.  The final residual is checked; if it is not at
+    // round-off (w does not belong to these factors, nu != 1, ...) the regular path below runs instead.
+    if (c->adj_reuse && c->nu == 1.0 && c->last_newton_lu && c->last_newton_lu->use_mf) {
+        PhaseTimer t(c, &c->stats.solve_ms);
+        DirectSolver &lu = *c->last_newton_lu;
+        CUDA_OK(c, cudaMemcpyAsync(d_z, c->d_rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        if (!lu.solve_transposed(d_z, s, c->err)) return OCP_ERR_SOLVER;
+        launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, nullptr, d_z, nullptr, nullptr, s);      // z_D = 0
+        launch_spmv_residual(n, c->d_rowptr, c->d_col, c->d_vals, d_z, c->d_rhs, c->d_tmp, s);
+        if (!lu.solve_transposed(c->d_tmp, s, c->err)) return OCP_ERR_SOLVER;
+        launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, nullptr, c->d_tmp, nullptr, nullptr, s);
+        launch_axpy(n, 1.0, c->d_tmp, d_z, s);
+        c->stats.n_solve += 2;
+        launch_spmv_residual(n, c->d_rowptr, c->d_col, c->d_vals, d_z, c->d_rhs, c->d_tmp, s);
+        launch_sumsq(n, c->d_tmp, c->d_scalar, c->d_scratch, c->d_counter, s);
+        launch_sumsq(n, c->d_rhs, c->d_scalar + 1, c->d_scratch, c->d_counter, s);
+        CUDA_OK(c, cudaGetLastError());
+        double ss[2];
+        int rc = read_scalar(c, c->d_scalar, 2, ss);
+        if (rc != OCP_OK) return rc;
+        if (ss[0] == ss[0] && ss[0] <= 1e-24 * ss[1]) {      // ||b - A z|| <= 1e-12 ||b||
+            c->n_adj_reused++;
+            return OCP_OK;
+        }
+        c->n_adj_fallback++;
     }
     {
         PhaseTimer t(c, &c->stats.factor_ms);

@@ -311,8 +311,14 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
 // loaded into registers while the current one is being applied.
 constexpr int TS = 512;    // threads per CTA in the solve kernels
 
+// element (i, c) of the triangular factor a sweep works with: the stored factor, or its transpose (TR) for solves
+// with A^T = U^T L^T (the adjoint system reuses the factors of the last Newton matrix that way)
+#define MF_E(i, c) (TR ? __ldcg(F + (c) + (size_t)(i) * m) : __ldcg(F + (i) + (size_t)(c) * m))
+#define MF_DI(row, col) (TR ? (col) * NB + (row) : (row) * NB + (col))
+
 // forward: y_P = L11^{-1} b_P,  b_U -= L21 y_P      (RS = rows per thread: 1 for fronts <= 512, 2 up to 1024)
-template <int RS>
+// TR: the same sweep with U^T in place of L:  y_P = U11^{-T} b_P,  b_U -= U12^T y_P
+template <int RS, bool TR>
 __global__ void __launch_bounds__(TS)
 mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x) {
     extern __shared__ double y[];
@@ -322,18 +328,18 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
     if (np == 0) return;
     const double *F = d.F + d.front_ptr[s];
     const int *I = d.idx + d.idx_ptr[s];
-    const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB);
+    const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + (TR ? NB * NB : 0);
     for (int k = tid; k < m; k += TS) y[k] = k < np ? x[I[k]] : 0.0;
     double lc[RS][NB], ln[RS][NB];
 #pragma unroll
     for (int q = 0; q < RS; ++q) {
         const int i = tid + q * TS;
 #pragma unroll
-        for (int t = 0; t < NB; ++t) lc[q][t] = (i < m && i >= min(NB, np) && t < np) ? __ldcg(F + i + (size_t)t * m) : 0.0;
+        for (int t = 0; t < NB; ++t) lc[q][t] = (i < m && i >= min(NB, np) && t < np) ? MF_E(i, t) : 0.0;
     }
     double dl[NB];
 #pragma unroll
-    for (int t = 0; t < NB; ++t) dl[t] = (tid < NB) ? __ldcg(Dinv + tid * NB + t) : 0.0;
+    for (int t = 0; t < NB; ++t) dl[t] = (tid < NB) ? __ldcg(Dinv + MF_DI(tid, t)) : 0.0;
     __syncthreads();
     const int nblk = (np + NB - 1) / NB;
     for (int b = 0; b < nblk; ++b) {
@@ -346,7 +352,7 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
                 const int i = tid + q * TS;
 #pragma unroll
                 for (int t = 0; t < NB; ++t)
-                    ln[q][t] = (i < m && i >= rnext && k1 + t < np) ? __ldcg(F + i + (size_t)(k1 + t) * m) : 0.0;
+                    ln[q][t] = (i < m && i >= rnext && k1 + t < np) ? MF_E(i, k1 + t) : 0.0;
             }
         }
         if (tid < NB) {
@@ -360,7 +366,7 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
             }
             if (b + 1 < nblk) {
 #pragma unroll
-                for (int t = 0; t < NB; ++t) dl[t] = __ldcg(Dinv + (size_t)(b + 1) * (2 * NB * NB) + tid * NB + t);
+                for (int t = 0; t < NB; ++t) dl[t] = __ldcg(Dinv + (size_t)(b + 1) * (2 * NB * NB) + MF_DI(tid, t));
             }
         }
         __syncthreads();
@@ -384,8 +390,8 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
     for (int i = np + tid; i < m; i += TS) atomicAdd(x + I[i], y[i]);
 }
 
-// backward: x_P = U11^{-1} (y_P - U12 x_U)
-template <int RS>
+// backward: x_P = U11^{-1} (y_P - U12 x_U);   TR: x_P = L11^{-T} (y_P - L21^T x_U)
+template <int RS, bool TR>
 __global__ void __launch_bounds__(TS)
 mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x) {
     extern __shared__ double y[];
@@ -395,7 +401,7 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
     if (np == 0) return;
     const double *F = d.F + d.front_ptr[s];
     const int *I = d.idx + d.idx_ptr[s];
-    const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + NB * NB;
+    const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + (TR ? 0 : NB * NB);
     for (int k = tid; k < m; k += TS) y[k] = x[I[k]];
     const int nblk = (np + NB - 1) / NB;
     double uc[RS][NB], un[RS][NB];
@@ -405,22 +411,22 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
         for (int q = 0; q < RS; ++q) {
             const int i = tid + q * TS;
 #pragma unroll
-            for (int t = 0; t < NB; ++t) uc[q][t] = (i < k0 && k0 + t < np) ? __ldcg(F + i + (size_t)(k0 + t) * m) : 0.0;
+            for (int t = 0; t < NB; ++t) uc[q][t] = (i < k0 && k0 + t < np) ? MF_E(i, k0 + t) : 0.0;
         }
     }
     double du[NB];
 #pragma unroll
-    for (int t = 0; t < NB; ++t) du[t] = (tid < NB) ? __ldcg(Dinv + (size_t)(nblk - 1) * (2 * NB * NB) + tid * NB + t) : 0.0;
+    for (int t = 0; t < NB; ++t) du[t] = (tid < NB) ? __ldcg(Dinv + (size_t)(nblk - 1) * (2 * NB * NB) + MF_DI(tid, t)) : 0.0;
     __syncthreads();
     // y_P -= U12 x_U: thread per pivot row, x_U in shared memory
     for (int k = tid; k < np; k += TS) {
         double a0 = 0.0, a1 = 0.0;
         int j = np;
         for (; j + 1 < m; j += 2) {
-            a0 = fma(__ldcg(F + k + (size_t)j * m), y[j], a0);
-            a1 = fma(__ldcg(F + k + (size_t)(j + 1) * m), y[j + 1], a1);
+            a0 = fma(MF_E(k, j), y[j], a0);
+            a1 = fma(MF_E(k, j + 1), y[j + 1], a1);
         }
-        if (j < m) a0 = fma(__ldcg(F + k + (size_t)j * m), y[j], a0);
+        if (j < m) a0 = fma(MF_E(k, j), y[j], a0);
         y[k] -= a0 + a1;
     }
     __syncthreads();
@@ -432,7 +438,7 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
             for (int q = 0; q < RS; ++q) {
                 const int i = tid + q * TS;
 #pragma unroll
-                for (int t = 0; t < NB; ++t) un[q][t] = (i < kp) ? __ldcg(F + i + (size_t)(kp + t) * m) : 0.0;
+                for (int t = 0; t < NB; ++t) un[q][t] = (i < kp) ? MF_E(i, kp + t) : 0.0;
             }
         }
         if (tid < NB) {
@@ -446,7 +452,7 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
             }
             if (b > 0) {
 #pragma unroll
-                for (int t = 0; t < NB; ++t) du[t] = __ldcg(Dinv + (size_t)(b - 1) * (2 * NB * NB) + tid * NB + t);
+                for (int t = 0; t < NB; ++t) du[t] = __ldcg(Dinv + (size_t)(b - 1) * (2 * NB * NB) + MF_DI(tid, t));
             }
         }
         __syncthreads();
@@ -502,7 +508,7 @@ struct MultifrontalLU::Impl {
     long long *prof = nullptr;   // optional per-level phase cycle counters (OCP_MF_PROF=1)
     std::vector<int> level_max_m, level_cluster;
     // CUDA graphs of the factor / solve launch sequences, keyed by the (fixed) device pointer they operate on
-    std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs;
+    std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs, solve_t_graphs;
     cudaStream_t cap_stream = nullptr;
     bool use_graphs = true;
     int *h_info = nullptr;       // pinned: zero-pivot flag of the most recent factorisations (checked lazily)
@@ -513,11 +519,12 @@ struct MultifrontalLU::Impl {
         for (void *q : p) cudaFree(q);
         for (auto &kv : factor_graphs) cudaGraphExecDestroy(kv.second);
         for (auto &kv : solve_graphs) cudaGraphExecDestroy(kv.second);
+        for (auto &kv : solve_t_graphs) cudaGraphExecDestroy(kv.second);
         if (cap_stream) cudaStreamDestroy(cap_stream);
         if (h_info) cudaFreeHost(h_info);
     }
     bool enqueue_factor(const double *d_vals, int nnz, cudaStream_t s, std::string &err);
-    bool enqueue_solve(double *d_x, cudaStream_t s, std::string &err);
+    bool enqueue_solve(double *d_x, bool trans, cudaStream_t s, std::string &err);
     template <class Fn>
     bool run(std::map<const void *, cudaGraphExec_t> &cache, const void *key, cudaStream_t s, std::string &err, Fn enqueue) {
         if (!use_graphs || prof) return enqueue(s);
@@ -734,26 +741,38 @@ bool MultifrontalLU::check(std::string &err) {
     return true;
 }
 
-bool MultifrontalLU::Impl::enqueue_solve(double *d_x, cudaStream_t s, std::string &err) {
+template <bool TR>
+static void launch_level_fwd(const MFDev &dev, const int *nodes, int nf, int max_m, double *d_x, cudaStream_t s) {
+    if (max_m <= TS)
+        mf_forward_kernel<1, TR><<<nf, TS, sizeof(double) * max_m, s>>>(dev, nodes, d_x);
+    else
+        mf_forward_kernel<2, TR><<<nf, TS, sizeof(double) * max_m, s>>>(dev, nodes, d_x);
+}
+
+template <bool TR>
+static void launch_level_bwd(const MFDev &dev, const int *nodes, int nf, int max_m, double *d_x, cudaStream_t s) {
+    if (max_m <= TS)
+        mf_backward_kernel<1, TR><<<nf, TS, sizeof(double) * max_m, s>>>(dev, nodes, d_x);
+    else
+        mf_backward_kernel<2, TR><<<nf, TS, sizeof(double) * max_m, s>>>(dev, nodes, d_x);
+}
+
+bool MultifrontalLU::Impl::enqueue_solve(double *d_x, bool trans, cudaStream_t s, std::string &err) {
     const MFSymbolic &S = this->S;
     for (int l = 0; l < S.nlevels; ++l) {
         const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
-        if (level_max_m[l] <= TS)
-            mf_forward_kernel<1><<<nf, TS, sizeof(double) * level_max_m[l], s>>>(dev, level_nodes + S.level_ptr[l], d_x);
-        else
-            mf_forward_kernel<2><<<nf, TS, sizeof(double) * level_max_m[l], s>>>(dev, level_nodes + S.level_ptr[l], d_x);
+        if (trans) launch_level_fwd<true>(dev, level_nodes + S.level_ptr[l], nf, level_max_m[l], d_x, s);
+        else launch_level_fwd<false>(dev, level_nodes + S.level_ptr[l], nf, level_max_m[l], d_x, s);
     }
     for (int l = S.nlevels - 1; l >= 0; --l) {
         const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
-        if (level_max_m[l] <= TS)
-            mf_backward_kernel<1><<<nf, TS, sizeof(double) * level_max_m[l], s>>>(dev, level_nodes + S.level_ptr[l], d_x);
-        else
-            mf_backward_kernel<2><<<nf, TS, sizeof(double) * level_max_m[l], s>>>(dev, level_nodes + S.level_ptr[l], d_x);
+        if (trans) launch_level_bwd<true>(dev, level_nodes + S.level_ptr[l], nf, level_max_m[l], d_x, s);
+        else launch_level_bwd<false>(dev, level_nodes + S.level_ptr[l], nf, level_max_m[l], d_x, s);
     }
     return true;
 }
 
-bool MultifrontalLU::solve(double *d_x, cudaStream_t s, std::string &err) {
+bool MultifrontalLU::solve(double *d_x, cudaStream_t s, std::string &err, bool transposed) {
     if (!impl_) {
         err = "MultifrontalLU::solve before configure";
         return false;
@@ -761,7 +780,8 @@ bool MultifrontalLU::solve(double *d_x, cudaStream_t s, std::string &err) {
     Impl &I = *impl_;
     if (!check(err)) return false;
     g_launch_count.fetch_add(2 * I.S.nlevels, std::memory_order_relaxed);
-    if (!I.run(I.solve_graphs, d_x, s, err, [&](cudaStream_t q) { return I.enqueue_solve(d_x, q, err); })) return false;
+    auto &cache = transposed ? I.solve_t_graphs : I.solve_graphs;
+    if (!I.run(cache, d_x, s, err, [&](cudaStream_t q) { return I.enqueue_solve(d_x, transposed, q, err); })) return false;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         err = std::string("multifrontal solve: ") + cudaGetErrorString(e);

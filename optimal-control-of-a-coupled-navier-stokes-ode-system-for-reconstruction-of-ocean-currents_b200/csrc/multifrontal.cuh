@@ -20,7 +20,8 @@ class MultifrontalLU {
     bool configure(int n, int nnz, const int *h_rowptr, const int *h_col, const double *xy, const unsigned char *kind,
                    std::string &err);
     bool factor(const double *d_vals, cudaStream_t s, std::string &err);   // numeric factorisation on the GPU
-    bool solve(double *d_x, cudaStream_t s, std::string &err);             // in place
+    // in place; transposed: solves A^T x = b with the same factors
+    bool solve(double *d_x, cudaStream_t s, std::string &err, bool transposed = false);
     bool check(std::string &err);   // zero-pivot flag of completed factorisations (non-blocking)
     long long factor_nnz() const { return factor_nnz_; }
     double flops() const { return flops_; }
