@@ -53,6 +53,12 @@ struct DirectSolver {
     bool solve(double *d_x, cudaStream_t s, std::string &err) {
         return use_mf ? mf.solve(d_x, s, err) : rf.solve(d_x, s, err);
     }
+    bool solve4(double *d_x, int n, cudaStream_t s, std::string &err) {   // four right-hand sides, stride n
+        if (use_mf) return mf.solve4(d_x, s, err);
+        for (int j = 0; j < 4; ++j)
+            if (!rf.solve(d_x + (size_t)j * n, s, err)) return false;
+        return true;
+    }
     bool solve_transposed(double *d_x, cudaStream_t s, std::string &err) {
         if (!use_mf) {
             err = "transposed solve needs the multifrontal solver";
@@ -552,10 +558,8 @@ int ocp_project_grad(ocp_ctx *c, const double *d_w, double *d_g) {
     }
     {
         PhaseTimer t(c, &c->stats.solve_ms);
-        for (int j = 0; j < 4; ++j) {
-            if (!c->lu_mass.solve(c->d_rhs4 + (size_t)j * nv, s, c->err)) return OCP_ERR_SOLVER;
-            c->stats.n_solve++;
-        }
+        if (!c->lu_mass.solve4(c->d_rhs4, nv, s, c->err)) return OCP_ERR_SOLVER;   // the four components at once
+        c->stats.n_solve++;
         launch_transpose4(nv, c->d_rhs4, d_g, s);
         CUDA_OK(c, cudaGetLastError());
     }

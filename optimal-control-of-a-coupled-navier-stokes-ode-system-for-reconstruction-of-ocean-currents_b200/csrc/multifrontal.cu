@@ -318,18 +318,20 @@ constexpr int TS = 512;    // threads per CTA in the solve kernels
 
 // forward: y_P = L11^{-1} b_P,  b_U -= L21 y_P      (RS = rows per thread: 1 for fronts <= 512, 2 up to 1024)
 // TR: the same sweep with U^T in place of L:  y_P = U11^{-T} b_P,  b_U -= U12^T y_P
-template <int RS, bool TR>
+// NR right-hand sides at once (vector r starts at x + r * ldx): the factor entries are loaded once for all of them.
+template <int RS, bool TR, int NR>
 __global__ void __launch_bounds__(TS)
-mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x) {
-    extern __shared__ double y[];
-    __shared__ double yb[NB];
+mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x, int ldx) {
+    extern __shared__ double y[];          // NR vectors of length m
+    __shared__ double yb[NR][NB];
     const int s = nodes[blockIdx.x];
     const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
     if (np == 0) return;
     const double *F = d.F + d.front_ptr[s];
     const int *I = d.idx + d.idx_ptr[s];
     const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + (TR ? NB * NB : 0);
-    for (int k = tid; k < m; k += TS) y[k] = k < np ? x[I[k]] : 0.0;
+    for (int r = 0; r < NR; ++r)
+        for (int k = tid; k < m; k += TS) y[r * m + k] = k < np ? x[(size_t)r * ldx + I[k]] : 0.0;
     double lc[RS][NB], ln[RS][NB];
 #pragma unroll
     for (int q = 0; q < RS; ++q) {
@@ -356,13 +358,20 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
             }
         }
         if (tid < NB) {
-            double v = 0.0;
+            double v[NR];
 #pragma unroll
-            for (int t = 0; t < NB; ++t) v = fma(dl[t], (t < kb) ? y[k0 + t] : 0.0, v);
+            for (int r = 0; r < NR; ++r) {
+                v[r] = 0.0;
+#pragma unroll
+                for (int t = 0; t < NB; ++t) v[r] = fma(dl[t], (t < kb) ? y[r * m + k0 + t] : 0.0, v[r]);
+            }
             __syncwarp(0xffffu);
             if (tid < kb) {
-                yb[tid] = v;
-                y[k0 + tid] = v;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    yb[r][tid] = v[r];
+                    y[r * m + k0 + tid] = v[r];
+                }
             }
             if (b + 1 < nblk) {
 #pragma unroll
@@ -374,10 +383,13 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
         for (int q = 0; q < RS; ++q) {
             const int i = tid + q * TS;
             if (i < m && i >= k0 + kb) {
-                double acc = 0.0;
 #pragma unroll
-                for (int t = 0; t < NB; ++t) acc = fma(lc[q][t], (t < kb) ? yb[t] : 0.0, acc);
-                y[i] -= acc;
+                for (int r = 0; r < NR; ++r) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) acc = fma(lc[q][t], (t < kb) ? yb[r][t] : 0.0, acc);
+                    y[r * m + i] -= acc;
+                }
             }
         }
         __syncthreads();
@@ -386,23 +398,26 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
 #pragma unroll
             for (int t = 0; t < NB; ++t) lc[q][t] = ln[q][t];
     }
-    for (int k = tid; k < np; k += TS) x[I[k]] = y[k];
-    for (int i = np + tid; i < m; i += TS) atomicAdd(x + I[i], y[i]);
+    for (int r = 0; r < NR; ++r) {
+        for (int k = tid; k < np; k += TS) x[(size_t)r * ldx + I[k]] = y[r * m + k];
+        for (int i = np + tid; i < m; i += TS) atomicAdd(x + (size_t)r * ldx + I[i], y[r * m + i]);
+    }
 }
 
 // backward: x_P = U11^{-1} (y_P - U12 x_U);   TR: x_P = L11^{-T} (y_P - L21^T x_U)
-template <int RS, bool TR>
+template <int RS, bool TR, int NR>
 __global__ void __launch_bounds__(TS)
-mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x) {
+mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x, int ldx) {
     extern __shared__ double y[];
-    __shared__ double yb[NB];
+    __shared__ double yb[NR][NB];
     const int s = nodes[blockIdx.x];
     const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
     if (np == 0) return;
     const double *F = d.F + d.front_ptr[s];
     const int *I = d.idx + d.idx_ptr[s];
     const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + (TR ? 0 : NB * NB);
-    for (int k = tid; k < m; k += TS) y[k] = x[I[k]];
+    for (int r = 0; r < NR; ++r)
+        for (int k = tid; k < m; k += TS) y[r * m + k] = x[(size_t)r * ldx + I[k]];
     const int nblk = (np + NB - 1) / NB;
     double uc[RS][NB], un[RS][NB];
     {
@@ -420,14 +435,25 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
     __syncthreads();
     // y_P -= U12 x_U: thread per pivot row, x_U in shared memory
     for (int k = tid; k < np; k += TS) {
-        double a0 = 0.0, a1 = 0.0;
+        double a0[NR], a1[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) a0[r] = a1[r] = 0.0;
         int j = np;
         for (; j + 1 < m; j += 2) {
-            a0 = fma(MF_E(k, j), y[j], a0);
-            a1 = fma(MF_E(k, j + 1), y[j + 1], a1);
+            const double e0 = MF_E(k, j), e1 = MF_E(k, j + 1);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                a0[r] = fma(e0, y[r * m + j], a0[r]);
+                a1[r] = fma(e1, y[r * m + j + 1], a1[r]);
+            }
         }
-        if (j < m) a0 = fma(MF_E(k, j), y[j], a0);
-        y[k] -= a0 + a1;
+        if (j < m) {
+            const double e0 = MF_E(k, j);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) a0[r] = fma(e0, y[r * m + j], a0[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) y[r * m + k] -= a0[r] + a1[r];
     }
     __syncthreads();
     for (int b = nblk - 1; b >= 0; --b) {
@@ -442,13 +468,20 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
             }
         }
         if (tid < NB) {
-            double v = 0.0;
+            double v[NR];
 #pragma unroll
-            for (int t = 0; t < NB; ++t) v = fma(du[t], (t < kb) ? y[k0 + t] : 0.0, v);
+            for (int r = 0; r < NR; ++r) {
+                v[r] = 0.0;
+#pragma unroll
+                for (int t = 0; t < NB; ++t) v[r] = fma(du[t], (t < kb) ? y[r * m + k0 + t] : 0.0, v[r]);
+            }
             __syncwarp(0xffffu);
             if (tid < kb) {
-                yb[tid] = v;
-                y[k0 + tid] = v;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    yb[r][tid] = v[r];
+                    y[r * m + k0 + tid] = v[r];
+                }
             }
             if (b > 0) {
 #pragma unroll
@@ -460,10 +493,13 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
         for (int q = 0; q < RS; ++q) {
             const int i = tid + q * TS;
             if (i < k0) {
-                double acc = 0.0;
 #pragma unroll
-                for (int t = 0; t < NB; ++t) acc = fma(uc[q][t], (t < kb) ? yb[t] : 0.0, acc);
-                y[i] -= acc;
+                for (int r = 0; r < NR; ++r) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) acc = fma(uc[q][t], (t < kb) ? yb[r][t] : 0.0, acc);
+                    y[r * m + i] -= acc;
+                }
             }
         }
         __syncthreads();
@@ -472,7 +508,8 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
 #pragma unroll
             for (int t = 0; t < NB; ++t) uc[q][t] = un[q][t];
     }
-    for (int k = tid; k < np; k += TS) x[I[k]] = y[k];
+    for (int r = 0; r < NR; ++r)
+        for (int k = tid; k < np; k += TS) x[(size_t)r * ldx + I[k]] = y[r * m + k];
 }
 
 // kernel variants: <threads, panel rows per thread>
@@ -508,7 +545,7 @@ struct MultifrontalLU::Impl {
     long long *prof = nullptr;   // optional per-level phase cycle counters (OCP_MF_PROF=1)
     std::vector<int> level_max_m, level_cluster;
     // CUDA graphs of the factor / solve launch sequences, keyed by the (fixed) device pointer they operate on
-    std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs, solve_t_graphs;
+    std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs, solve_t_graphs, solve4_graphs;
     cudaStream_t cap_stream = nullptr;
     bool use_graphs = true;
     int *h_info = nullptr;       // pinned: zero-pivot flag of the most recent factorisations (checked lazily)
@@ -520,11 +557,12 @@ struct MultifrontalLU::Impl {
         for (auto &kv : factor_graphs) cudaGraphExecDestroy(kv.second);
         for (auto &kv : solve_graphs) cudaGraphExecDestroy(kv.second);
         for (auto &kv : solve_t_graphs) cudaGraphExecDestroy(kv.second);
+        for (auto &kv : solve4_graphs) cudaGraphExecDestroy(kv.second);
         if (cap_stream) cudaStreamDestroy(cap_stream);
         if (h_info) cudaFreeHost(h_info);
     }
     bool enqueue_factor(const double *d_vals, int nnz, cudaStream_t s, std::string &err);
-    bool enqueue_solve(double *d_x, bool trans, cudaStream_t s, std::string &err);
+    bool enqueue_solve(double *d_x, int variant, cudaStream_t s, std::string &err);
     template <class Fn>
     bool run(std::map<const void *, cudaGraphExec_t> &cache, const void *key, cudaStream_t s, std::string &err, Fn enqueue) {
         if (!use_graphs || prof) return enqueue(s);
@@ -741,33 +779,56 @@ bool MultifrontalLU::check(std::string &err) {
     return true;
 }
 
-template <bool TR>
-static void launch_level_fwd(const MFDev &dev, const int *nodes, int nf, int max_m, double *d_x, cudaStream_t s) {
+template <bool TR, int NR>
+static void launch_level_fwd(const MFDev &dev, const int *nodes, int nf, int max_m, double *d_x, int ldx, cudaStream_t s) {
     if (max_m <= TS)
-        mf_forward_kernel<1, TR><<<nf, TS, sizeof(double) * max_m, s>>>(dev, nodes, d_x);
+        mf_forward_kernel<1, TR, NR><<<nf, TS, sizeof(double) * max_m * NR, s>>>(dev, nodes, d_x, ldx);
     else
-        mf_forward_kernel<2, TR><<<nf, TS, sizeof(double) * max_m, s>>>(dev, nodes, d_x);
+        mf_forward_kernel<2, TR, NR><<<nf, TS, sizeof(double) * max_m * NR, s>>>(dev, nodes, d_x, ldx);
 }
 
-template <bool TR>
-static void launch_level_bwd(const MFDev &dev, const int *nodes, int nf, int max_m, double *d_x, cudaStream_t s) {
+template <bool TR, int NR>
+static void launch_level_bwd(const MFDev &dev, const int *nodes, int nf, int max_m, double *d_x, int ldx, cudaStream_t s) {
     if (max_m <= TS)
-        mf_backward_kernel<1, TR><<<nf, TS, sizeof(double) * max_m, s>>>(dev, nodes, d_x);
+        mf_backward_kernel<1, TR, NR><<<nf, TS, sizeof(double) * max_m * NR, s>>>(dev, nodes, d_x, ldx);
     else
-        mf_backward_kernel<2, TR><<<nf, TS, sizeof(double) * max_m, s>>>(dev, nodes, d_x);
+        mf_backward_kernel<2, TR, NR><<<nf, TS, sizeof(double) * max_m * NR, s>>>(dev, nodes, d_x, ldx);
 }
 
-bool MultifrontalLU::Impl::enqueue_solve(double *d_x, bool trans, cudaStream_t s, std::string &err) {
+// variant: 0 plain, 1 transposed, 2 plain with four right-hand sides
+bool MultifrontalLU::Impl::enqueue_solve(double *d_x, int variant, cudaStream_t s, std::string &err) {
     const MFSymbolic &S = this->S;
+    const int ldx = S.n;
     for (int l = 0; l < S.nlevels; ++l) {
         const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
-        if (trans) launch_level_fwd<true>(dev, level_nodes + S.level_ptr[l], nf, level_max_m[l], d_x, s);
-        else launch_level_fwd<false>(dev, level_nodes + S.level_ptr[l], nf, level_max_m[l], d_x, s);
+        const int *nodes = level_nodes + S.level_ptr[l];
+        if (variant == 1) launch_level_fwd<true, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+        else if (variant == 2) launch_level_fwd<false, 4>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+        else launch_level_fwd<false, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
     }
     for (int l = S.nlevels - 1; l >= 0; --l) {
         const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
-        if (trans) launch_level_bwd<true>(dev, level_nodes + S.level_ptr[l], nf, level_max_m[l], d_x, s);
-        else launch_level_bwd<false>(dev, level_nodes + S.level_ptr[l], nf, level_max_m[l], d_x, s);
+        const int *nodes = level_nodes + S.level_ptr[l];
+        if (variant == 1) launch_level_bwd<true, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+        else if (variant == 2) launch_level_bwd<false, 4>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+        else launch_level_bwd<false, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+    }
+    return true;
+}
+
+bool MultifrontalLU::solve4(double *d_x, cudaStream_t s, std::string &err) {
+    if (!impl_) {
+        err = "MultifrontalLU::solve4 before configure";
+        return false;
+    }
+    Impl &I = *impl_;
+    if (!check(err)) return false;
+    g_launch_count.fetch_add(2 * I.S.nlevels, std::memory_order_relaxed);
+    if (!I.run(I.solve4_graphs, d_x, s, err, [&](cudaStream_t q) { return I.enqueue_solve(d_x, 2, q, err); })) return false;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        err = std::string("multifrontal solve4: ") + cudaGetErrorString(e);
+        return false;
     }
     return true;
 }
@@ -781,7 +842,7 @@ bool MultifrontalLU::solve(double *d_x, cudaStream_t s, std::string &err, bool t
     if (!check(err)) return false;
     g_launch_count.fetch_add(2 * I.S.nlevels, std::memory_order_relaxed);
     auto &cache = transposed ? I.solve_t_graphs : I.solve_graphs;
-    if (!I.run(cache, d_x, s, err, [&](cudaStream_t q) { return I.enqueue_solve(d_x, transposed, q, err); })) return false;
+    if (!I.run(cache, d_x, s, err, [&](cudaStream_t q) { return I.enqueue_solve(d_x, transposed ? 1 : 0, q, err); })) return false;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         err = std::string("multifrontal solve: ") + cudaGetErrorString(e);

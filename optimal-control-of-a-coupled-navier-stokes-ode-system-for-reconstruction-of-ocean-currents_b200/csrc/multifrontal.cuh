@@ -22,6 +22,8 @@ class MultifrontalLU {
     bool factor(const double *d_vals, cudaStream_t s, std::string &err);   // numeric factorisation on the GPU
     // in place; transposed: solves A^T x = b with the same factors
     bool solve(double *d_x, cudaStream_t s, std::string &err, bool transposed = false);
+    // four right-hand sides at once: vector r occupies d_x[r * n .. r * n + n)
+    bool solve4(double *d_x, cudaStream_t s, std::string &err);
     bool check(std::string &err);   // zero-pivot flag of completed factorisations (non-blocking)
     long long factor_nnz() const { return factor_nnz_; }
     double flops() const { return flops_; }
