@@ -433,27 +433,55 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
 #pragma unroll
     for (int t = 0; t < NB; ++t) du[t] = (tid < NB) ? __ldcg(Dinv + (size_t)(nblk - 1) * (2 * NB * NB) + MF_DI(tid, t)) : 0.0;
     __syncthreads();
-    // y_P -= U12 x_U: thread per pivot row, x_U in shared memory
-    for (int k = tid; k < np; k += TS) {
-        double a0[NR], a1[NR];
+    // y_P -= U12 x_U (TR: L21^T x_U): all 16 warps share the (np x nu) mat-vec so that no thread walks a long
+    // dependent chain of L2 loads.  Plain: warp w takes the columns j = np + w, np + w + 16, ... with its lanes over
+    // the rows (coalesced), partial sums meet in shared memory.  Transposed: the factor is contiguous along j, so warp
+    // w takes rows k = w, w + 16, ... with its lanes over j and a shuffle reduction.
+    {
+        const int lane = tid & 31, wid = tid >> 5, NW = TS / 32;
+        if (!TR) {
+            double *part = y + (size_t)NR * m;                 // NW x (NR x np) partial sums (dynamic smem sized by the host)
+            for (int k0 = 0; k0 < np; k0 += 32) {
+                const int k = k0 + lane;
+                double a[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) a0[r] = a1[r] = 0.0;
-        int j = np;
-        for (; j + 1 < m; j += 2) {
-            const double e0 = MF_E(k, j), e1 = MF_E(k, j + 1);
+                for (int r = 0; r < NR; ++r) a[r] = 0.0;
+                if (k < np) {
+                    for (int j = np + wid; j < m; j += NW) {
+                        const double e = __ldcg(F + k + (size_t)j * m);
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                a0[r] = fma(e0, y[r * m + j], a0[r]);
-                a1[r] = fma(e1, y[r * m + j + 1], a1[r]);
+                        for (int r = 0; r < NR; ++r) a[r] = fma(e, y[r * m + j], a[r]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) part[((size_t)wid * NR + r) * np + k] = a[r];
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < NR * np; e += TS) {
+                const int r = e / np, k = e % np;
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) sum += part[((size_t)w * NR + r) * np + k];
+                y[r * m + k] -= sum;
+            }
+        } else {
+            for (int k = wid; k < np; k += NW) {
+                double a[NR];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) a[r] = 0.0;
+                for (int j = np + lane; j < m; j += 32) {
+                    const double e = __ldcg(F + j + (size_t)k * m);
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) a[r] = fma(e, y[r * m + j], a[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
+                    if (lane == 0) y[r * m + k] -= a[r];
+                }
             }
         }
-        if (j < m) {
-            const double e0 = MF_E(k, j);
-#pragma unroll
-            for (int r = 0; r < NR; ++r) a0[r] = fma(e0, y[r * m + j], a0[r]);
-        }
-#pragma unroll
-        for (int r = 0; r < NR; ++r) y[r * m + k] -= a0[r] + a1[r];
     }
     __syncthreads();
     for (int b = nblk - 1; b >= 0; --b) {
@@ -543,7 +571,7 @@ struct MultifrontalLU::Impl {
     double *F = nullptr, *dinv = nullptr;
     int *dinv_ptr = nullptr;
     long long *prof = nullptr;   // optional per-level phase cycle counters (OCP_MF_PROF=1)
-    std::vector<int> level_max_m, level_cluster;
+    std::vector<int> level_max_m, level_max_np, level_cluster;
     // CUDA graphs of the factor / solve launch sequences, keyed by the (fixed) device pointer they operate on
     std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs, solve_t_graphs, solve4_graphs;
     cudaStream_t cap_stream = nullptr;
@@ -614,9 +642,12 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
             return false;
         }
     I.level_max_m.assign(S.nlevels, 0);
+    I.level_max_np.assign(S.nlevels, 0);
     for (int l = 0; l < S.nlevels; ++l)
-        for (int k = S.level_ptr[l]; k < S.level_ptr[l + 1]; ++k)
+        for (int k = S.level_ptr[l]; k < S.level_ptr[l + 1]; ++k) {
             I.level_max_m[l] = std::max(I.level_max_m[l], S.m[S.level_nodes[k]]);
+            I.level_max_np[l] = std::max(I.level_max_np[l], S.np[S.level_nodes[k]]);
+        }
     const size_t need = (size_t)NB * (2 * (size_t)((S.max_front + 3) & ~3) + CWO + 4) * sizeof(double);
     if (need > 200 * 1024 || S.max_front > 1024) {
         err = "multifrontal: largest front (" + std::to_string(S.max_front) + ") exceeds the shared-memory panel";
@@ -633,6 +664,10 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     if (e == cudaSuccess) e = cudaMalloc((void **)&I.info, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(I.info, 0, sizeof(int));
     // the attributes are per kernel, not per solver instance: always allow the full opt-in budget
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_kernel<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_kernel<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_kernel<1, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_kernel<2, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int v = 0; v < 3 && e == cudaSuccess; ++v) {
         e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -788,11 +823,14 @@ static void launch_level_fwd(const MFDev &dev, const int *nodes, int nf, int max
 }
 
 template <bool TR, int NR>
-static void launch_level_bwd(const MFDev &dev, const int *nodes, int nf, int max_m, double *d_x, int ldx, cudaStream_t s) {
+static void launch_level_bwd(const MFDev &dev, const int *nodes, int nf, int max_m, int max_np, double *d_x, int ldx,
+                             cudaStream_t s) {
+    // y (NR x m) plus, for the plain sweep, the per-warp partial sums of the U12 mat-vec (16 x NR x np)
+    const size_t smem = sizeof(double) * NR * ((size_t)max_m + (TR ? 0 : (size_t)(TS / 32) * max_np));
     if (max_m <= TS)
-        mf_backward_kernel<1, TR, NR><<<nf, TS, sizeof(double) * max_m * NR, s>>>(dev, nodes, d_x, ldx);
+        mf_backward_kernel<1, TR, NR><<<nf, TS, smem, s>>>(dev, nodes, d_x, ldx);
     else
-        mf_backward_kernel<2, TR, NR><<<nf, TS, sizeof(double) * max_m * NR, s>>>(dev, nodes, d_x, ldx);
+        mf_backward_kernel<2, TR, NR><<<nf, TS, smem, s>>>(dev, nodes, d_x, ldx);
 }
 
 // variant: 0 plain, 1 transposed, 2 plain with four right-hand sides
@@ -809,9 +847,9 @@ bool MultifrontalLU::Impl::enqueue_solve(double *d_x, int variant, cudaStream_t 
     for (int l = S.nlevels - 1; l >= 0; --l) {
         const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
         const int *nodes = level_nodes + S.level_ptr[l];
-        if (variant == 1) launch_level_bwd<true, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
-        else if (variant == 2) launch_level_bwd<false, 4>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
-        else launch_level_bwd<false, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+        if (variant == 1) launch_level_bwd<true, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
+        else if (variant == 2) launch_level_bwd<false, 4>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
+        else launch_level_bwd<false, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
     }
     return true;
 }
