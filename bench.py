@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -385,7 +385,7 @@ def run_ours(args):
                          "note": "in-step launch at K=10000 is latency-bound (64 MB of trajectories); "
                                  "see roofline_sweep for the same kernel at 2^20 buoys"},
             "roofline_sweep": sweep,
-            "dominant_by_time": "mf_factor_kernel (multifrontal LU, ~64% of the step; latency / fp64-pipe bound, no "
+            "dominant_by_time": "mf_factor_kernel (multifrontal LU, ~52% of kernel time; latency / fp64-pipe bound, no "
                                 "bandwidth roofline - see profiles/launches_r1_final_summary.txt)",
             "cpu_baseline": cpu,
             "J_after_update": J, "J_at_q0_e2e": J2,
