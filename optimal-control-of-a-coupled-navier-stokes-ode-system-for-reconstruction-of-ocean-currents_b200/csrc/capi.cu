@@ -848,12 +848,14 @@ void ocp_host_mf_set_pivot_window(int rows) { ocp::g_mf_host_window = rows < 1 ?
 
 int64_t ocp_host_mf_probe(int32_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *xy,
                           const uint8_t *kind, double *rhs_inout, double *stats8) {
-    if (n <= 0 || !rowptr || !col || !val || !xy || !kind) return OCP_ERR_INVALID;
+    if (n <= 0 || !rowptr || !col || !xy || !kind) return OCP_ERR_INVALID;
     MFSymbolic S;
     mf_analyse(n, rowptr, col, xy, kind, 48, S);
     MFHostNumeric N;
-    if (!mf_factor_host(S, val, N)) return OCP_ERR_SOLVER;
-    if (rhs_inout) mf_solve_host(S, N, rhs_inout);
+    if (val) {   // val == NULL: symbolic analysis only (statistics of large meshes)
+        if (!mf_factor_host(S, val, N)) return OCP_ERR_SOLVER;
+        if (rhs_inout) mf_solve_host(S, N, rhs_inout);
+    }
     if (stats8) {
         stats8[0] = S.nnodes; stats8[1] = S.nlevels; stats8[2] = S.max_front; stats8[3] = S.max_np;
         stats8[4] = S.flops; stats8[5] = N.min_pivot; stats8[6] = (double)S.fsize; stats8[7] = 0.0;

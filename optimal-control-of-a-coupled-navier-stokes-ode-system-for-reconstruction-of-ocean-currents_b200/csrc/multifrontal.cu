@@ -540,6 +540,414 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
         for (int k = tid; k < np; k += TS) x[(size_t)r * ldx + I[k]] = y[r * m + k];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Large fronts (m > kBigM: the top of the tree on refined meshes, cfg5).  A front no longer fits a cluster's shared
+// memory, so a GROUP of G co-resident CTAs (cooperative launch, G = #SMs / #large fronts of the level) works on it
+// out of L2 / HBM with a right-looking blocked LU, panel width 32, static pivoting as above:
+//   phase A  every CTA factors the 32 x 32 diagonal block redundantly (warp 0, shuffles) and turns its share of the
+//            rows below it into L = A U11^{-1} (one row per thread, in registers)
+//   -- group barrier --
+//   phase B  the CTA owning a column (4-column blocks, cyclic over the group) solves U12 for it and applies the
+//            rank-32 update to it: L is streamed through shared memory in 256-row chunks, 32 own columns per pass,
+//            4 x 4 register tiles, a warp covering 32 rows x 16 columns so that both operands are shared-memory
+//            broadcasts
+//   -- group barrier --
+// Column ownership is static, so a column is only ever read and written by its owner between barriers.
+constexpr int BB = 32;        // panel width
+constexpr int BIG_T = 512;    // threads per CTA
+constexpr int BIG_RC = 256;   // rows of L per shared-memory chunk
+constexpr int BIG_NC = 32;    // own columns per update pass
+constexpr int kBigM = 768;    // fronts above this order take the group path
+constexpr size_t kBigSmem = sizeof(double) * (BB * BIG_RC + BB * BIG_NC);
+
+__device__ __forceinline__ void group_barrier(unsigned *cnt, unsigned target, int G) {
+    __syncthreads();
+    if (G > 1) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(cnt, 1u);
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+            } while (v < target);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
+// inverse of the unit-lower (which = 1) or upper (which = 0) factor of the 16 x 16 diagonal sub-block at offset o of
+// the factored panel block D (kbs live rows), one row per lane, for the blocked triangular solves
+__device__ __forceinline__ void invert_diag16(const double (*D)[BB + 1], const double *rd, int o, int kbs, int which,
+                                              int lane, double *dst) {
+    double X[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) X[c] = (c == lane) ? 1.0 : 0.0;
+    if (which) {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const double lik = (lane > k && lane < kbs && k < kbs) ? D[o + (lane < NB ? lane : 0)][o + k] : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c <= k) {
+                    const double xkc = __shfl_sync(0xffffffffu, X[c], k);
+                    X[c] = fma(-lik, xkc, X[c]);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = NB - 1; k >= 0; --k) {
+            const bool live = k < kbs;
+            if (lane == k && live) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) X[c] *= rd[o + k];
+            }
+            const double uik = (lane < k && live) ? D[o + lane][o + k] : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c >= k) {
+                    const double ykc = __shfl_sync(0xffffffffu, X[c], k);
+                    X[c] = fma(-uik, ykc, X[c]);
+                }
+            }
+        }
+    }
+    if (lane < NB) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) dst[lane * NB + c] = X[c];
+    }
+}
+
+__global__ void __launch_bounds__(BIG_T, 1)
+mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, int G, unsigned *bar, int *info) {
+    extern __shared__ double sm[];
+    double *Ls = sm;                      // BB x BIG_RC: Ls[t * BIG_RC + i]
+    double *Us = sm + BB * BIG_RC;        // BB x BIG_NC: Us[t * BIG_NC + c]
+    __shared__ double s_D[BB][BB + 1];
+    __shared__ double s_rd[BB];
+    const int grp = blockIdx.x / G, g = blockIdx.x % G, tid = threadIdx.x;
+    const int s = nodes[grp];
+    const int m = d.m[s], np = d.np[s];
+    double *F = d.F + d.front_ptr[s];
+    unsigned *cnt = bar + grp;
+    unsigned target = 0;
+    // ---- extend-add of the children's update matrices
+    for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
+        const int c = d.child[ci], mc = d.m[c], npc = d.np[c], nu = mc - npc;
+        const double *Fc = d.F + d.front_ptr[c];
+        const int *rel = d.rel + d.rel_ptr[c];
+        for (int j = g; j < nu; j += G) {
+            const double *src = Fc + npc + (size_t)(npc + j) * mc;
+            double *dst = F + (size_t)__ldg(rel + j) * m;
+            for (int i = tid; i < nu; i += BIG_T) atomicAdd(dst + __ldg(rel + i), __ldcg(src + i));
+        }
+    }
+    target += G;
+    group_barrier(cnt, target, G);
+    const int nblk_total = (m + 3) >> 2;
+    for (int k0 = 0; k0 < np; k0 += BB) {
+        const int kb = min(BB, np - k0), ctrail = k0 + kb, nrows = m - ctrail;
+        // ---- A1: diagonal block, lane = row (padded with the identity)
+        if (tid < 32) {
+            double r[BB];
+#pragma unroll
+            for (int jj = 0; jj < BB; ++jj)
+                r[jj] = (tid < kb && jj < kb) ? __ldcg(F + (k0 + tid) + (size_t)(k0 + jj) * m) : ((jj == tid) ? 1.0 : 0.0);
+#pragma unroll
+            for (int j = 0; j < BB; ++j) {
+                const double rinv = fast_rcp(__shfl_sync(0xffffffffu, r[j], j));
+                if (tid == j) {
+                    s_rd[j] = rinv;
+                    if (j < kb && !(fabs(rinv) < 1e280)) atomicExch(info, s + 1);
+                }
+                const bool below = tid > j;
+                const double l = r[j] * rinv;
+                if (below) r[j] = l;
+#pragma unroll
+                for (int jj = 0; jj < BB; ++jj) {
+                    if (jj > j) {
+                        const double u = __shfl_sync(0xffffffffu, r[jj], j);
+                        if (below) r[jj] = fma(-l, u, r[jj]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < BB; ++jj) s_D[tid][jj] = r[jj];
+        }
+        __syncthreads();
+        // ---- A2: this CTA's share of the rows below the block: L = A U11^{-1}
+        {
+            const int chunk = (((nrows + G - 1) / G) + 31) & ~31;
+            const int rbeg = g * chunk, rend = min(nrows, rbeg + chunk);
+            for (int i = rbeg + tid; i < rend; i += BIG_T) {
+                double *rowp = F + ctrail + i + (size_t)k0 * m;
+                double a[BB];
+#pragma unroll
+                for (int jj = 0; jj < BB; ++jj) a[jj] = jj < kb ? __ldcg(rowp + (size_t)jj * m) : 0.0;
+#pragma unroll
+                for (int t = 0; t < BB; ++t) {
+                    if (t < kb) {
+                        const double l = a[t] * s_rd[t];
+                        a[t] = l;
+#pragma unroll
+                        for (int jj = 0; jj < BB; ++jj)
+                            if (jj > t) a[jj] = fma(-l, s_D[t][jj], a[jj]);
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < BB; ++jj)
+                    if (jj < kb) __stcg(rowp + (size_t)jj * m, a[jj]);
+            }
+        }
+        target += G;
+        group_barrier(cnt, target, G);
+        // ---- B0: one CTA stores the factored block and the inverses of its two 16 x 16 diagonal sub-blocks
+        if (g == (k0 / BB) % G) {
+            for (int e = tid; e < kb * kb; e += BIG_T) {
+                const int i = e % kb, j = e / kb;
+                __stcg(F + (k0 + i) + (size_t)(k0 + j) * m, s_D[i][j]);
+            }
+            if (tid >= BIG_T - 128) {
+                const int w = (tid - (BIG_T - 128)) >> 5, lane = tid & 31;
+                const int sub = w >> 1, which = w & 1, o = sub * NB;
+                const int kbs = min(NB, kb - o);
+                if (kbs > 0) {
+                    double *dst = d.dinv + ((size_t)d.dinv_ptr[s] + k0 / NB + sub) * (2 * NB * NB) + (which ? 0 : NB * NB);
+                    invert_diag16(s_D, s_rd, o, kbs, which, lane, dst);
+                }
+            }
+        }
+        if (nrows > 0) {
+            // ---- B1: U12 = L11^{-1} F12 for the own trailing columns (one column per thread)
+            const int cb0 = ctrail >> 2;
+            const int cbf = cb0 + ((g - cb0 % G) + G) % G;                 // first own 4-column block
+            const int nown = cbf < nblk_total ? (nblk_total - 1 - cbf) / G + 1 : 0;
+            for (int idx = tid; idx < nown * 4; idx += BIG_T) {
+                const int c = (cbf + (idx >> 2) * G) * 4 + (idx & 3);
+                if (c >= ctrail && c < m) {
+                    double *colp = F + (size_t)c * m + k0;
+                    double u[BB];
+#pragma unroll
+                    for (int t = 0; t < BB; ++t) u[t] = t < kb ? __ldcg(colp + t) : 0.0;
+#pragma unroll
+                    for (int t = 0; t < BB; ++t) {
+                        if (t < kb) {
+#pragma unroll
+                            for (int tt = 0; tt < BB; ++tt)
+                                if (tt > t) u[tt] = fma(-s_D[tt][t], u[t], u[tt]);
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < BB; ++t)
+                        if (t < kb) __stcg(colp + t, u[t]);
+                }
+            }
+            // ---- B2: rank-kb update of the own columns
+            const int warp = tid >> 5, lane = tid & 31;
+            const int i0 = (warp >> 1) * 32 + (lane & 7) * 4;              // first row of this thread's tile in the chunk
+            const int j0 = (warp & 1) * 16 + (lane >> 3) * 4;              // first column of its tile in the pass
+            for (int p0 = 0; p0 < nown; p0 += BIG_NC / 4) {
+                __syncthreads();   // U12 written above / previous pass done with Us
+                for (int e = tid; e < BB * BIG_NC; e += BIG_T) {
+                    const int t = e % BB, ci = e / BB, q = p0 + (ci >> 2);
+                    const int c = (cbf + q * G) * 4 + (ci & 3);
+                    Us[t * BIG_NC + ci] = (q < nown && c >= ctrail && c < m && t < kb) ? __ldcg(F + (size_t)c * m + k0 + t) : 0.0;
+                }
+                const int q = p0 + (j0 >> 2);
+                const int cbase = (cbf + q * G) * 4;
+                for (int r0 = 0; r0 < nrows; r0 += BIG_RC) {
+                    __syncthreads();
+                    for (int e = tid; e < BB * BIG_RC; e += BIG_T) {
+                        const int i = e % BIG_RC, t = e / BIG_RC;
+                        Ls[e] = (r0 + i < nrows && t < kb) ? __ldcg(F + ctrail + r0 + i + (size_t)(k0 + t) * m) : 0.0;
+                    }
+                    __syncthreads();
+                    if (q < nown && r0 + i0 < nrows) {
+                        double f[4][4], acc[4][4];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const int c = cbase + b;
+                            const double *colp = F + (size_t)c * m + ctrail + r0 + i0;
+                            const bool cv = c >= ctrail && c < m;
+#pragma unroll
+                            for (int aa = 0; aa < 4; ++aa) {
+                                f[aa][b] = (cv && r0 + i0 + aa < nrows) ? __ldcg(colp + aa) : 0.0;
+                                acc[aa][b] = 0.0;
+                            }
+                        }
+#pragma unroll 8
+                        for (int t = 0; t < BB; ++t) {
+                            const double2 la = *reinterpret_cast<const double2 *>(Ls + t * BIG_RC + i0);
+                            const double2 lb = *reinterpret_cast<const double2 *>(Ls + t * BIG_RC + i0 + 2);
+                            const double2 ua = *reinterpret_cast<const double2 *>(Us + t * BIG_NC + j0);
+                            const double2 ub = *reinterpret_cast<const double2 *>(Us + t * BIG_NC + j0 + 2);
+                            const double l[4] = {la.x, la.y, lb.x, lb.y}, uu[4] = {ua.x, ua.y, ub.x, ub.y};
+#pragma unroll
+                            for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                                for (int b = 0; b < 4; ++b) acc[aa][b] = fma(l[aa], uu[b], acc[aa][b]);
+                        }
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const int c = cbase + b;
+                            if (c >= ctrail && c < m) {
+                                double *colp = F + (size_t)c * m + ctrail + r0 + i0;
+#pragma unroll
+                                for (int aa = 0; aa < 4; ++aa)
+                                    if (r0 + i0 + aa < nrows) __stcg(colp + aa, f[aa][b] - acc[aa][b]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        target += G;
+        group_barrier(cnt, target, G);
+    }
+}
+
+// Triangular solves of a large front: one CTA of 1024 threads, right-hand side(s) in shared memory, 16-row blocks
+// with the stored inverses of the diagonal blocks as in the small-front kernels, factor entries straight from L2.
+constexpr int TSB = 1024;
+
+template <bool TR, int NR>
+__global__ void __launch_bounds__(TSB)
+mf_forward_big_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x, int ldx) {
+    extern __shared__ double y[];          // NR vectors of length m
+    __shared__ double yb[NR][NB];
+    const int s = nodes[blockIdx.x];
+    const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
+    if (np == 0) return;
+    const double *F = d.F + d.front_ptr[s];
+    const int *I = d.idx + d.idx_ptr[s];
+    const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + (TR ? NB * NB : 0);
+    for (int r = 0; r < NR; ++r)
+        for (int k = tid; k < m; k += TSB) y[r * m + k] = k < np ? x[(size_t)r * ldx + I[k]] : 0.0;
+    __syncthreads();
+    const int nblk = (np + NB - 1) / NB;
+    for (int b = 0; b < nblk; ++b) {
+        const int k0 = b * NB, kb = min(NB, np - k0);
+        if (tid < NB * NR) {
+            const int r = tid / NB, row = tid % NB;
+            const double *Db = Dinv + (size_t)b * (2 * NB * NB);
+            double v = 0.0;
+#pragma unroll
+            for (int t = 0; t < NB; ++t) v = fma(__ldcg(Db + MF_DI(row, t)), (t < kb) ? y[r * m + k0 + t] : 0.0, v);
+            yb[r][row] = v;
+        }
+        __syncthreads();
+        if (tid < NB * NR && (tid % NB) < kb) y[(tid / NB) * m + k0 + (tid % NB)] = yb[tid / NB][tid % NB];
+        for (int i = k0 + kb + tid; i < m; i += TSB) {
+            double e[NB];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) e[t] = (t < kb) ? MF_E(i, k0 + t) : 0.0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                double acc = 0.0;
+#pragma unroll
+                for (int t = 0; t < NB; ++t) acc = fma(e[t], yb[r][t], acc);
+                y[r * m + i] -= acc;
+            }
+        }
+        __syncthreads();
+    }
+    for (int r = 0; r < NR; ++r) {
+        for (int k = tid; k < np; k += TSB) x[(size_t)r * ldx + I[k]] = y[r * m + k];
+        for (int i = np + tid; i < m; i += TSB) atomicAdd(x + (size_t)r * ldx + I[i], y[r * m + i]);
+    }
+}
+
+template <bool TR, int NR>
+__global__ void __launch_bounds__(TSB)
+mf_backward_big_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x, int ldx) {
+    extern __shared__ double y[];
+    __shared__ double yb[NR][NB];
+    const int s = nodes[blockIdx.x];
+    const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
+    if (np == 0) return;
+    const double *F = d.F + d.front_ptr[s];
+    const int *I = d.idx + d.idx_ptr[s];
+    const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + (TR ? 0 : NB * NB);
+    for (int r = 0; r < NR; ++r)
+        for (int k = tid; k < m; k += TSB) y[r * m + k] = x[(size_t)r * ldx + I[k]];
+    __syncthreads();
+    // y_P -= U12 x_U (TR: L21^T x_U)
+    if (!TR) {
+        for (int k = tid; k < np; k += TSB) {       // lanes over the rows: coalesced column reads
+            double a[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) a[r] = 0.0;
+            int j = np;
+            for (; j + 8 <= m; j += 8) {
+                double e[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) e[u] = __ldcg(F + k + (size_t)(j + u) * m);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) a[r] = fma(e[u], y[r * m + j + u], a[r]);
+            }
+            for (; j < m; ++j) {
+                const double e = __ldcg(F + k + (size_t)j * m);
+#pragma unroll
+                for (int r = 0; r < NR; ++r) a[r] = fma(e, y[r * m + j], a[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) y[r * m + k] -= a[r];
+        }
+    } else {
+        const int lane = tid & 31, wid = tid >> 5, NW = TSB / 32;
+        for (int k = wid; k < np; k += NW) {        // the transposed factor is contiguous along j
+            double a[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) a[r] = 0.0;
+            for (int j = np + lane; j < m; j += 32) {
+                const double e = __ldcg(F + j + (size_t)k * m);
+#pragma unroll
+                for (int r = 0; r < NR; ++r) a[r] = fma(e, y[r * m + j], a[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
+                if (lane == 0) y[r * m + k] -= a[r];
+            }
+        }
+    }
+    __syncthreads();
+    const int nblk = (np + NB - 1) / NB;
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int k0 = b * NB, kb = min(NB, np - k0);
+        if (tid < NB * NR) {
+            const int r = tid / NB, row = tid % NB;
+            const double *Db = Dinv + (size_t)b * (2 * NB * NB);
+            double v = 0.0;
+#pragma unroll
+            for (int t = 0; t < NB; ++t) v = fma(__ldcg(Db + MF_DI(row, t)), (t < kb) ? y[r * m + k0 + t] : 0.0, v);
+            yb[r][row] = v;
+        }
+        __syncthreads();
+        if (tid < NB * NR && (tid % NB) < kb) y[(tid / NB) * m + k0 + (tid % NB)] = yb[tid / NB][tid % NB];
+        for (int i = tid; i < k0; i += TSB) {
+            double e[NB];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) e[t] = (t < kb) ? MF_E(i, k0 + t) : 0.0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                double acc = 0.0;
+#pragma unroll
+                for (int t = 0; t < NB; ++t) acc = fma(e[t], yb[r][t], acc);
+                y[r * m + i] -= acc;
+            }
+        }
+        __syncthreads();
+    }
+    for (int r = 0; r < NR; ++r)
+        for (int k = tid; k < np; k += TSB) x[(size_t)r * ldx + I[k]] = y[r * m + k];
+}
+
 // kernel variants: <threads, panel rows per thread>
 enum { kVarSmall = 0, kVarMid = 1, kVarBig = 2 };
 inline int factor_variant(int max_m) { return max_m <= 256 ? kVarSmall : (max_m <= 512 ? kVarMid : kVarBig); }
@@ -571,7 +979,11 @@ struct MultifrontalLU::Impl {
     double *F = nullptr, *dinv = nullptr;
     int *dinv_ptr = nullptr;
     long long *prof = nullptr;   // optional per-level phase cycle counters (OCP_MF_PROF=1)
-    std::vector<int> level_max_m, level_max_np, level_cluster;
+    std::vector<int> level_max_m, level_max_np, level_cluster;   // over the SMALL fronts of a level
+    // per level the node list is [small fronts | large fronts]; large = order above kBigM (group kernels)
+    std::vector<int> level_off, level_nsmall, level_nbig, level_big_max_m;
+    unsigned *bar = nullptr;     // group-barrier counters of the large-front factor kernel
+    int big_ctas = 0;            // co-resident CTAs available to that kernel
     // CUDA graphs of the factor / solve launch sequences, keyed by the (fixed) device pointer they operate on
     std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs, solve_t_graphs, solve4_graphs;
     cudaStream_t cap_stream = nullptr;
@@ -580,7 +992,7 @@ struct MultifrontalLU::Impl {
     MFDev dev{};
     ~Impl() {
         void *p[] = {m, np, first, idx_ptr, idx, child_ptr, child, rel_ptr, rel, level_nodes, piv, info, front_ptr,
-                     a_dest, F, prof, dinv, dinv_ptr};
+                     a_dest, F, prof, dinv, dinv_ptr, bar};
         for (void *q : p) cudaFree(q);
         for (auto &kv : factor_graphs) cudaGraphExecDestroy(kv.second);
         for (auto &kv : solve_graphs) cudaGraphExecDestroy(kv.second);
@@ -641,26 +1053,47 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
             err = "multifrontal analysis: matrix entry outside its front";
             return false;
         }
+    // split every level into small fronts (cluster kernel, panel in shared memory) and large fronts (group kernel)
     I.level_max_m.assign(S.nlevels, 0);
     I.level_max_np.assign(S.nlevels, 0);
-    for (int l = 0; l < S.nlevels; ++l)
-        for (int k = S.level_ptr[l]; k < S.level_ptr[l + 1]; ++k) {
-            I.level_max_m[l] = std::max(I.level_max_m[l], S.m[S.level_nodes[k]]);
-            I.level_max_np[l] = std::max(I.level_max_np[l], S.np[S.level_nodes[k]]);
-        }
-    const size_t need = (size_t)NB * (2 * (size_t)((S.max_front + 3) & ~3) + CWO + 4) * sizeof(double);
-    if (need > 200 * 1024 || S.max_front > 1024) {
-        err = "multifrontal: largest front (" + std::to_string(S.max_front) + ") exceeds the shared-memory panel";
+    I.level_off.assign(S.nlevels, 0);
+    I.level_nsmall.assign(S.nlevels, 0);
+    I.level_nbig.assign(S.nlevels, 0);
+    I.level_big_max_m.assign(S.nlevels, 0);
+    std::vector<int> ordered(S.nnodes);
+    int big_limit = kBigM;
+    if (const char *eb = getenv("OCP_MF_BIG")) big_limit = std::max(32, atoi(eb));   // testing: force the group path
+    for (int l = 0; l < S.nlevels; ++l) {
+        int w = S.level_ptr[l];
+        I.level_off[l] = w;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int k = S.level_ptr[l]; k < S.level_ptr[l + 1]; ++k) {
+                const int nd = S.level_nodes[k];
+                const bool big = S.m[nd] > big_limit;
+                if (big != (pass == 1)) continue;
+                ordered[w++] = nd;
+                if (big) {
+                    I.level_nbig[l]++;
+                    I.level_big_max_m[l] = std::max(I.level_big_max_m[l], S.m[nd]);
+                } else {
+                    I.level_nsmall[l]++;
+                    I.level_max_m[l] = std::max(I.level_max_m[l], S.m[nd]);
+                    I.level_max_np[l] = std::max(I.level_max_np[l], S.np[nd]);
+                }
+            }
+    }
+    if (S.max_front > 24000) {   // right-hand side of a large front must fit the solve kernels' shared memory
+        err = "multifrontal: largest front (" + std::to_string(S.max_front) + ") exceeds the solve kernels' shared memory";
         return false;
     }
     if (!up(&I.m, S.m, err) || !up(&I.np, S.np, err) || !up(&I.first, S.first, err) ||
         !up(&I.idx_ptr, S.idx_ptr, err) || !up(&I.idx, S.idx, err) || !up(&I.child_ptr, S.child_ptr, err) ||
         !up(&I.child, S.child, err) || !up(&I.rel_ptr, S.rel_ptr, err) || !up(&I.rel, S.rel, err) ||
-        !up(&I.level_nodes, S.level_nodes, err) || !up(&I.front_ptr, S.front_ptr, err) ||
+        !up(&I.level_nodes, ordered, err) || !up(&I.front_ptr, S.front_ptr, err) ||
         !up(&I.a_dest, S.a_dest, err))
         return false;
-    cudaError_t e = cudaMalloc((void **)&I.F, sizeof(double) * S.fsize);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&I.piv, sizeof(int) * std::max(n, 1));
+    // the front workspace (the bulk of the memory: 5 GB at 256 x 256) is allocated by the first factorisation
+    cudaError_t e = cudaMalloc((void **)&I.piv, sizeof(int) * std::max(n, 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&I.info, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(I.info, 0, sizeof(int));
     // the attributes are per kernel, not per solver instance: always allow the full opt-in budget
@@ -672,12 +1105,34 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
         e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_big_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_forward_big_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_forward_big_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_forward_big_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_big_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_big_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_big_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) {
+        // the group kernel spins on barriers between its CTAs: never launch more of them than can be co-resident
+        int dev_id = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev_id);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mf_big_factor_kernel, BIG_T, kBigSmem);
+        I.big_ctas = sms * std::min(per_sm, 1);
+        if (const char *eg = getenv("OCP_MF_BIG_CTAS")) I.big_ctas = std::max(1, std::min(I.big_ctas, atoi(eg)));
+        if (e == cudaSuccess && I.big_ctas < 1) {
+            err = "multifrontal setup: the large-front kernel does not fit an SM";
+            return false;
+        }
+        if (e == cudaSuccess) e = cudaMalloc((void **)&I.bar, sizeof(unsigned) * 1024);
+    }
     // cluster size per level: as many CTAs per front as the chip has room for (powers of two, <= 16)
     int max_cluster = 16;
     if (const char *envc = getenv("OCP_MF_MAX_CLUSTER")) max_cluster = std::max(1, atoi(envc));
     I.level_cluster.assign(S.nlevels, 1);
     for (int l = 0; l < S.nlevels && e == cudaSuccess; ++l) {
-        const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
+        const int nf = I.level_nsmall[l];
+        if (nf == 0) continue;
         int c = 1;
         while (c * 2 <= max_cluster && nf * c * 2 <= 148 && c * 2 * 8 <= I.level_max_m[l]) c *= 2;
         while (c > 1) {   // make sure the cluster shape is launchable with this kernel's resources
@@ -742,28 +1197,54 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
     cudaMemsetAsync(F, 0, sizeof(double) * S.fsize, s);
     scatter_values_kernel<<<(nnz + 255) / 256, 256, 0, s>>>(nnz, a_dest, d_vals, F);
     for (int l = 0; l < S.nlevels; ++l) {
-        const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
-        const int c = level_cluster[l];
-        cudaLaunchConfig_t cfg = {};
-        const int var = factor_variant(level_max_m[l]);
-        cfg.gridDim = dim3(nf * c);
-        cfg.blockDim = dim3(variant_threads(var));
-        cfg.dynamicSmemBytes = (size_t)NB * (2 * (size_t)((level_max_m[l] + 3) & ~3) + CWO + 4) * sizeof(double);
-        cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = c;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        long long *lprof = this->prof ? this->prof + 8 * l : nullptr;
-        const int *lvl = level_nodes + S.level_ptr[l];
-        cudaError_t le = cudaLaunchKernelEx(&cfg, factor_kernel(var), dev, lvl, level_max_m[l], info, lprof);
-        if (le != cudaSuccess) {
-            err = std::string("multifrontal factor launch (level ") + std::to_string(l) + ", cluster " +
-                  std::to_string(c) + "): " + cudaGetErrorString(le);
-            return false;
+        const int nf = level_nsmall[l];
+        if (nf > 0) {
+            const int c = level_cluster[l];
+            cudaLaunchConfig_t cfg = {};
+            const int var = factor_variant(level_max_m[l]);
+            cfg.gridDim = dim3(nf * c);
+            cfg.blockDim = dim3(variant_threads(var));
+            cfg.dynamicSmemBytes = (size_t)NB * (2 * (size_t)((level_max_m[l] + 3) & ~3) + CWO + 4) * sizeof(double);
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = c;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            long long *lprof = this->prof ? this->prof + 8 * l : nullptr;
+            const int *lvl = level_nodes + level_off[l];
+            cudaError_t le = cudaLaunchKernelEx(&cfg, factor_kernel(var), dev, lvl, level_max_m[l], info, lprof);
+            if (le != cudaSuccess) {
+                err = std::string("multifrontal factor launch (level ") + std::to_string(l) + ", cluster " +
+                      std::to_string(c) + "): " + cudaGetErrorString(le);
+                return false;
+            }
+        }
+        // large fronts of the level: groups of co-resident CTAs, as many fronts per launch as there are CTAs
+        for (int done = 0; done < level_nbig[l];) {
+            const int nb = std::min(level_nbig[l] - done, std::min(big_ctas, 1024));
+            const int G = std::max(1, big_ctas / nb);
+            cudaMemsetAsync(bar, 0, sizeof(unsigned) * nb, s);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(nb * G);
+            cfg.blockDim = dim3(BIG_T);
+            cfg.dynamicSmemBytes = kBigSmem;
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeCooperative;
+            at[0].val.cooperative = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            const int *lvl = level_nodes + level_off[l] + level_nsmall[l] + done;
+            cudaError_t le = cudaLaunchKernelEx(&cfg, mf_big_factor_kernel, dev, lvl, G, bar, info);
+            if (le != cudaSuccess) {
+                err = std::string("multifrontal large-front launch (level ") + std::to_string(l) + ", " + std::to_string(nb) +
+                      " fronts x " + std::to_string(G) + " CTAs): " + cudaGetErrorString(le);
+                return false;
+            }
+            done += nb;
         }
     }
     cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, s);
@@ -777,6 +1258,14 @@ bool MultifrontalLU::factor(const double *d_vals, cudaStream_t s, std::string &e
     }
     Impl &I = *impl_;
     if (!check(err)) return false;
+    if (!I.F) {
+        if (cudaMalloc((void **)&I.F, sizeof(double) * I.S.fsize) != cudaSuccess) {
+            cudaGetLastError();
+            err = "multifrontal factor: out of memory for the front workspace (" + std::to_string(I.S.fsize * 8 >> 20) + " MiB)";
+            return false;
+        }
+        I.dev.F = I.F;
+    }
     g_launch_count.fetch_add(1 + I.S.nlevels, std::memory_order_relaxed);
     const int nnz = nnz_;
     if (!I.run(I.factor_graphs, d_vals, s, err, [&](cudaStream_t q) { return I.enqueue_factor(d_vals, nnz, q, err); }))
@@ -789,7 +1278,7 @@ bool MultifrontalLU::factor(const double *d_vals, cudaStream_t s, std::string &e
         cudaMemset(I.prof, 0, sizeof(long long) * h.size());
         for (int l = 0; l < S.nlevels; ++l)
             fprintf(stderr, "[mf prof] level %d fronts %d cluster %d | CTA0 cycles: load %lld diag %lld trsm %lld u12 %lld trail %lld sync %lld\n",
-                    l, S.level_ptr[l + 1] - S.level_ptr[l], I.level_cluster[l], h[8 * l], h[8 * l + 1], h[8 * l + 2],
+                    l, I.level_nsmall[l], I.level_cluster[l], h[8 * l], h[8 * l + 1], h[8 * l + 2],
                     h[8 * l + 3], h[8 * l + 4], h[8 * l + 5]);
     }
     cudaError_t e = cudaGetLastError();
@@ -816,6 +1305,7 @@ bool MultifrontalLU::check(std::string &err) {
 
 template <bool TR, int NR>
 static void launch_level_fwd(const MFDev &dev, const int *nodes, int nf, int max_m, double *d_x, int ldx, cudaStream_t s) {
+    if (nf <= 0) return;
     if (max_m <= TS)
         mf_forward_kernel<1, TR, NR><<<nf, TS, sizeof(double) * max_m * NR, s>>>(dev, nodes, d_x, ldx);
     else
@@ -825,6 +1315,7 @@ static void launch_level_fwd(const MFDev &dev, const int *nodes, int nf, int max
 template <bool TR, int NR>
 static void launch_level_bwd(const MFDev &dev, const int *nodes, int nf, int max_m, int max_np, double *d_x, int ldx,
                              cudaStream_t s) {
+    if (nf <= 0) return;
     // y (NR x m) plus, for the plain sweep, the per-warp partial sums of the U12 mat-vec (16 x NR x np)
     const size_t smem = sizeof(double) * NR * ((size_t)max_m + (TR ? 0 : (size_t)(TS / 32) * max_np));
     if (max_m <= TS)
@@ -833,23 +1324,60 @@ static void launch_level_bwd(const MFDev &dev, const int *nodes, int nf, int max
         mf_backward_kernel<2, TR, NR><<<nf, TS, smem, s>>>(dev, nodes, d_x, ldx);
 }
 
+// large fronts: one CTA each; four right-hand sides that do not fit shared memory together go one at a time
+template <bool TR>
+static void launch_big_fwd(const MFDev &dev, const int *nodes, int nf, int max_m, int nr, double *d_x, int ldx, cudaStream_t s) {
+    if (nf <= 0) return;
+    if (nr == 4 && sizeof(double) * 4 * (size_t)max_m <= 196 * 1024) {
+        mf_forward_big_kernel<false, 4><<<nf, TSB, sizeof(double) * 4 * max_m, s>>>(dev, nodes, d_x, ldx);
+        return;
+    }
+    for (int r = 0; r < nr; ++r)
+        mf_forward_big_kernel<TR, 1><<<nf, TSB, sizeof(double) * max_m, s>>>(dev, nodes, d_x + (size_t)r * ldx, ldx);
+}
+
+template <bool TR>
+static void launch_big_bwd(const MFDev &dev, const int *nodes, int nf, int max_m, int nr, double *d_x, int ldx, cudaStream_t s) {
+    if (nf <= 0) return;
+    if (nr == 4 && sizeof(double) * 4 * (size_t)max_m <= 196 * 1024) {
+        mf_backward_big_kernel<false, 4><<<nf, TSB, sizeof(double) * 4 * max_m, s>>>(dev, nodes, d_x, ldx);
+        return;
+    }
+    for (int r = 0; r < nr; ++r)
+        mf_backward_big_kernel<TR, 1><<<nf, TSB, sizeof(double) * max_m, s>>>(dev, nodes, d_x + (size_t)r * ldx, ldx);
+}
+
 // variant: 0 plain, 1 transposed, 2 plain with four right-hand sides
 bool MultifrontalLU::Impl::enqueue_solve(double *d_x, int variant, cudaStream_t s, std::string &err) {
     const MFSymbolic &S = this->S;
     const int ldx = S.n;
     for (int l = 0; l < S.nlevels; ++l) {
-        const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
-        const int *nodes = level_nodes + S.level_ptr[l];
-        if (variant == 1) launch_level_fwd<true, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
-        else if (variant == 2) launch_level_fwd<false, 4>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
-        else launch_level_fwd<false, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+        const int nf = level_nsmall[l], nbg = level_nbig[l];
+        const int *nodes = level_nodes + level_off[l], *big = nodes + nf;
+        if (variant == 1) {
+            launch_level_fwd<true, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+            launch_big_fwd<true>(dev, big, nbg, level_big_max_m[l], 1, d_x, ldx, s);
+        } else if (variant == 2) {
+            launch_level_fwd<false, 4>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+            launch_big_fwd<false>(dev, big, nbg, level_big_max_m[l], 4, d_x, ldx, s);
+        } else {
+            launch_level_fwd<false, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+            launch_big_fwd<false>(dev, big, nbg, level_big_max_m[l], 1, d_x, ldx, s);
+        }
     }
     for (int l = S.nlevels - 1; l >= 0; --l) {
-        const int nf = S.level_ptr[l + 1] - S.level_ptr[l];
-        const int *nodes = level_nodes + S.level_ptr[l];
-        if (variant == 1) launch_level_bwd<true, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
-        else if (variant == 2) launch_level_bwd<false, 4>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
-        else launch_level_bwd<false, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
+        const int nf = level_nsmall[l], nbg = level_nbig[l];
+        const int *nodes = level_nodes + level_off[l], *big = nodes + nf;
+        if (variant == 1) {
+            launch_level_bwd<true, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
+            launch_big_bwd<true>(dev, big, nbg, level_big_max_m[l], 1, d_x, ldx, s);
+        } else if (variant == 2) {
+            launch_level_bwd<false, 4>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
+            launch_big_bwd<false>(dev, big, nbg, level_big_max_m[l], 4, d_x, ldx, s);
+        } else {
+            launch_level_bwd<false, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
+            launch_big_bwd<false>(dev, big, nbg, level_big_max_m[l], 1, d_x, ldx, s);
+        }
     }
     return true;
 }
@@ -861,6 +1389,10 @@ bool MultifrontalLU::solve4(double *d_x, cudaStream_t s, std::string &err) {
     }
     Impl &I = *impl_;
     if (!check(err)) return false;
+    if (!I.F) {
+        err = "MultifrontalLU::solve4 before factor";
+        return false;
+    }
     g_launch_count.fetch_add(2 * I.S.nlevels, std::memory_order_relaxed);
     if (!I.run(I.solve4_graphs, d_x, s, err, [&](cudaStream_t q) { return I.enqueue_solve(d_x, 2, q, err); })) return false;
     cudaError_t e = cudaGetLastError();
@@ -878,6 +1410,10 @@ bool MultifrontalLU::solve(double *d_x, cudaStream_t s, std::string &err, bool t
     }
     Impl &I = *impl_;
     if (!check(err)) return false;
+    if (!I.F) {
+        err = "MultifrontalLU::solve before factor";
+        return false;
+    }
     g_launch_count.fetch_add(2 * I.S.nlevels, std::memory_order_relaxed);
     auto &cache = transposed ? I.solve_t_graphs : I.solve_graphs;
     if (!I.run(cache, d_x, s, err, [&](cudaStream_t q) { return I.enqueue_solve(d_x, transposed ? 1 : 0, q, err); })) return false;
