@@ -860,6 +860,20 @@ int64_t ocp_host_mf_probe(int32_t n, const int32_t *rowptr, const int32_t *col, 
         stats8[0] = S.nnodes; stats8[1] = S.nlevels; stats8[2] = S.max_front; stats8[3] = S.max_np;
         stats8[4] = S.flops; stats8[5] = N.min_pivot; stats8[6] = (double)S.fsize; stats8[7] = 0.0;
     }
+    if (getenv("OCP_MF_DUMP")) {   // per-level front statistics of the symbolic analysis (tools/check_bigfront.py)
+        for (int l = 0; l < S.nlevels; ++l) {
+            int mx = 0, mn = 1 << 30, mxp = 0;
+            double fl = 0.0;
+            for (int k = S.level_ptr[l]; k < S.level_ptr[l + 1]; ++k) {
+                const int nd = S.level_nodes[k];
+                const double p = S.np[nd], mm = S.m[nd];
+                mx = std::max(mx, S.m[nd]); mn = std::min(mn, S.m[nd]); mxp = std::max(mxp, S.np[nd]);
+                fl += 2.0 * p * mm * mm - 2.0 * p * p * mm + 2.0 / 3.0 * p * p * p;
+            }
+            fprintf(stderr, "[mf] level %2d: %5d fronts, order %d..%d, max pivots %d, %.2f GFlop\n", l,
+                    S.level_ptr[l + 1] - S.level_ptr[l], mn, mx, mxp, fl * 1e-9);
+        }
+    }
     return (int64_t)S.fsize;
 }
 

@@ -556,10 +556,76 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
 // Column ownership is static, so a column is only ever read and written by its owner between barriers.
 constexpr int BB = 32;        // panel width
 constexpr int BIG_T = 512;    // threads per CTA
-constexpr int BIG_RC = 256;   // rows of L per shared-memory chunk
-constexpr int BIG_NC = 32;    // own columns per update pass
+constexpr int BIG_RC = 256;   // rows of L per shared-memory chunk (double buffered)
+constexpr int BIG_UC = 256;   // own columns whose U12 rows are resident in shared memory at a time
 constexpr int kBigM = 768;    // fronts above this order take the group path
-constexpr size_t kBigSmem = sizeof(double) * (BB * BIG_RC + BB * BIG_NC);
+constexpr size_t kBigSmem = sizeof(double) * (2 * BB * BIG_RC + BB * BIG_UC);
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const unsigned bytes = valid ? 8u : 0u;      // 0: zero-fill, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Rank-32 update of one 256-row chunk of the own columns.  A warp covers a block of 32 R rows (lane = row, R rows per
+// thread 32 apart: every global access of a warp is 256 contiguous bytes) x 8 columns per pass; L comes from the
+// shared chunk (conflict-free), U from the resident U12 rows (broadcast).  R is chosen per panel so that all 16 warps
+// have columns to work on: 4 (64 columns per pass), 2 (32) or 1 (16).
+template <int R>
+__device__ __forceinline__ void big_update_chunk(const double *__restrict__ Lb, const double *__restrict__ Us, double *F,
+                                                 int m, int ctrail, int r0, int nrows, int ncols, int qbase, int cbf,
+                                                 int G, int tid) {
+    constexpr int NRB = BIG_RC / (32 * R);      // row blocks per chunk
+    constexpr int NCG = (BIG_T / 32) / NRB;     // column groups (of 8) per pass
+    const int warp = tid >> 5, lane = tid & 31;
+    const int rb = warp % NRB, cg = warp / NRB;
+    const int ib = rb * 32 * R + lane;          // first row of this thread inside the chunk
+    if (r0 + rb * 32 * R >= nrows) return;
+    for (int ci0 = cg * 8; ci0 < ncols; ci0 += NCG * 8) {
+        double acc[R][8];
+#pragma unroll
+        for (int a = 0; a < R; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+#pragma unroll 4
+        for (int t = 0; t < BB; ++t) {
+            double l[R];
+#pragma unroll
+            for (int a = 0; a < R; ++a) l[a] = Lb[t * BIG_RC + ib + 32 * a];
+            const double2 *up = reinterpret_cast<const double2 *>(Us + t * BIG_UC + ci0);
+            const double2 u0 = up[0], u1 = up[1], u2 = up[2], u3 = up[3];
+            const double u[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
+#pragma unroll
+            for (int a = 0; a < R; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = fma(l[a], u[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {           // two columns at a time: load C, subtract, store
+            const int ci = ci0 + 2 * h;
+            const int cc = (cbf + (qbase + (ci >> 2)) * G) * 4 + (ci & 3);
+            double *colp = F + (size_t)cc * m + ctrail + r0 + ib;
+            double f[R][2];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const bool cv = ci < ncols && cc + b >= ctrail && cc + b < m;
+#pragma unroll
+                for (int a = 0; a < R; ++a)
+                    f[a][b] = (cv && r0 + ib + 32 * a < nrows) ? __ldcg(colp + (size_t)b * m + 32 * a) : 0.0;
+            }
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const bool cv = ci < ncols && cc + b >= ctrail && cc + b < m;
+#pragma unroll
+                for (int a = 0; a < R; ++a)
+                    if (cv && r0 + ib + 32 * a < nrows) __stcg(colp + (size_t)b * m + 32 * a, f[a][b] - acc[a][2 * h + b]);
+            }
+        }
+    }
+}
 
 __device__ __forceinline__ void group_barrier(unsigned *cnt, unsigned target, int G) {
     __syncthreads();
@@ -621,13 +687,14 @@ __device__ __forceinline__ void invert_diag16(const double (*D)[BB + 1], const d
 }
 
 __global__ void __launch_bounds__(BIG_T, 1)
-mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, int G, unsigned *bar, int *info) {
-    extern __shared__ double sm[];
-    double *Ls = sm;                      // BB x BIG_RC: Ls[t * BIG_RC + i]
-    double *Us = sm + BB * BIG_RC;        // BB x BIG_NC: Us[t * BIG_NC + c]
+mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restrict__ cta_map, unsigned *bar, int *info) {
+    extern __shared__ __align__(16) double sm[];
+    double *Ls = sm;                      // 2 x (BB x BIG_RC): Ls[buf][t * BIG_RC + i]
+    double *Us = sm + 2 * BB * BIG_RC;    // BB x BIG_UC: Us[t * BIG_UC + c]
     __shared__ double s_D[BB][BB + 1];
     __shared__ double s_rd[BB];
-    const int grp = blockIdx.x / G, g = blockIdx.x % G, tid = threadIdx.x;
+    const int4 me = cta_map[blockIdx.x];  // (group = front of this launch, rank in the group, group size)
+    const int grp = me.x, g = me.y, G = me.z, tid = threadIdx.x;
     const int s = nodes[grp];
     const int m = d.m[s], np = d.np[s];
     double *F = d.F + d.front_ptr[s];
@@ -745,61 +812,44 @@ mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, int G, unsigned *ba
                 }
             }
             // ---- B2: rank-kb update of the own columns
-            const int warp = tid >> 5, lane = tid & 31;
-            const int i0 = (warp >> 1) * 32 + (lane & 7) * 4;              // first row of this thread's tile in the chunk
-            const int j0 = (warp & 1) * 16 + (lane >> 3) * 4;              // first column of its tile in the pass
-            for (int p0 = 0; p0 < nown; p0 += BIG_NC / 4) {
-                __syncthreads();   // U12 written above / previous pass done with Us
-                for (int e = tid; e < BB * BIG_NC; e += BIG_T) {
-                    const int t = e % BB, ci = e / BB, q = p0 + (ci >> 2);
-                    const int c = (cbf + q * G) * 4 + (ci & 3);
-                    Us[t * BIG_NC + ci] = (q < nown && c >= ctrail && c < m && t < kb) ? __ldcg(F + (size_t)c * m + k0 + t) : 0.0;
+            const int ncols_all = nown * 4;
+            const int nch = (nrows + BIG_RC - 1) / BIG_RC;
+            for (int sp0 = 0; sp0 < ncols_all; sp0 += BIG_UC) {
+                const int ncols = min(BIG_UC, ncols_all - sp0), qbase = sp0 >> 2;
+                __syncthreads();   // U12 written above / previous super-pass done with Us and Ls
+                for (int e = tid; e < BB * ncols; e += BIG_T) {
+                    const int t = e % BB, ci = e / BB;
+                    const int c = (cbf + (qbase + (ci >> 2)) * G) * 4 + (ci & 3);
+                    Us[t * BIG_UC + ci] = (c >= ctrail && c < m && t < kb) ? __ldcg(F + (size_t)c * m + k0 + t) : 0.0;
                 }
-                const int q = p0 + (j0 >> 2);
-                const int cbase = (cbf + q * G) * 4;
-                for (int r0 = 0; r0 < nrows; r0 += BIG_RC) {
-                    __syncthreads();
+                auto prefetch = [&](int ch) {
+                    double *dstb = Ls + (ch & 1) * (BB * BIG_RC);
+                    const int r0 = ch * BIG_RC;
+#pragma unroll 4
                     for (int e = tid; e < BB * BIG_RC; e += BIG_T) {
                         const int i = e % BIG_RC, t = e / BIG_RC;
-                        Ls[e] = (r0 + i < nrows && t < kb) ? __ldcg(F + ctrail + r0 + i + (size_t)(k0 + t) * m) : 0.0;
+                        const bool v = r0 + i < nrows && t < kb;
+                        cp_async8(dstb + e, v ? F + ctrail + r0 + i + (size_t)(k0 + t) * m : F, v);
+                    }
+                    cp_async_commit();
+                };
+                prefetch(0);
+                for (int ch = 0; ch < nch; ++ch) {
+                    if (ch + 1 < nch) {
+                        prefetch(ch + 1);
+                        cp_async_wait<1>();
+                    } else {
+                        cp_async_wait<0>();
                     }
                     __syncthreads();
-                    if (q < nown && r0 + i0 < nrows) {
-                        double f[4][4], acc[4][4];
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const int c = cbase + b;
-                            const double *colp = F + (size_t)c * m + ctrail + r0 + i0;
-                            const bool cv = c >= ctrail && c < m;
-#pragma unroll
-                            for (int aa = 0; aa < 4; ++aa) {
-                                f[aa][b] = (cv && r0 + i0 + aa < nrows) ? __ldcg(colp + aa) : 0.0;
-                                acc[aa][b] = 0.0;
-                            }
-                        }
-#pragma unroll 8
-                        for (int t = 0; t < BB; ++t) {
-                            const double2 la = *reinterpret_cast<const double2 *>(Ls + t * BIG_RC + i0);
-                            const double2 lb = *reinterpret_cast<const double2 *>(Ls + t * BIG_RC + i0 + 2);
-                            const double2 ua = *reinterpret_cast<const double2 *>(Us + t * BIG_NC + j0);
-                            const double2 ub = *reinterpret_cast<const double2 *>(Us + t * BIG_NC + j0 + 2);
-                            const double l[4] = {la.x, la.y, lb.x, lb.y}, uu[4] = {ua.x, ua.y, ub.x, ub.y};
-#pragma unroll
-                            for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-                                for (int b = 0; b < 4; ++b) acc[aa][b] = fma(l[aa], uu[b], acc[aa][b]);
-                        }
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const int c = cbase + b;
-                            if (c >= ctrail && c < m) {
-                                double *colp = F + (size_t)c * m + ctrail + r0 + i0;
-#pragma unroll
-                                for (int aa = 0; aa < 4; ++aa)
-                                    if (r0 + i0 + aa < nrows) __stcg(colp + aa, f[aa][b] - acc[aa][b]);
-                            }
-                        }
-                    }
+                    const double *Lb = Ls + (ch & 1) * (BB * BIG_RC);
+                    if (ncols > 32)
+                        big_update_chunk<4>(Lb, Us, F, m, ctrail, ch * BIG_RC, nrows, ncols, qbase, cbf, G, tid);
+                    else if (ncols > 16)
+                        big_update_chunk<2>(Lb, Us, F, m, ctrail, ch * BIG_RC, nrows, ncols, qbase, cbf, G, tid);
+                    else
+                        big_update_chunk<1>(Lb, Us, F, m, ctrail, ch * BIG_RC, nrows, ncols, qbase, cbf, G, tid);
+                    __syncthreads();
                 }
             }
         }
@@ -984,6 +1034,11 @@ struct MultifrontalLU::Impl {
     std::vector<int> level_off, level_nsmall, level_nbig, level_big_max_m;
     unsigned *bar = nullptr;     // group-barrier counters of the large-front factor kernel
     int big_ctas = 0;            // co-resident CTAs available to that kernel
+    struct BigLaunch {           // one cooperative launch: fronts [first, first + nb) of the level's large list
+        int level, first, nb, grid, map_off;
+    };
+    std::vector<BigLaunch> big_launches;
+    int4 *cta_map = nullptr;     // per CTA of every large-front launch: (front of the launch, rank in its group, group size)
     // CUDA graphs of the factor / solve launch sequences, keyed by the (fixed) device pointer they operate on
     std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs, solve_t_graphs, solve4_graphs;
     cudaStream_t cap_stream = nullptr;
@@ -992,7 +1047,7 @@ struct MultifrontalLU::Impl {
     MFDev dev{};
     ~Impl() {
         void *p[] = {m, np, first, idx_ptr, idx, child_ptr, child, rel_ptr, rel, level_nodes, piv, info, front_ptr,
-                     a_dest, F, prof, dinv, dinv_ptr, bar};
+                     a_dest, F, prof, dinv, dinv_ptr, bar, cta_map};
         for (void *q : p) cudaFree(q);
         for (auto &kv : factor_graphs) cudaGraphExecDestroy(kv.second);
         for (auto &kv : solve_graphs) cudaGraphExecDestroy(kv.second);
@@ -1125,6 +1180,49 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
             return false;
         }
         if (e == cudaSuccess) e = cudaMalloc((void **)&I.bar, sizeof(unsigned) * 1024);
+        // CTAs are shared out among the large fronts of a launch in proportion to their flops (the orders inside one
+        // level differ by more than 2x), at least one each
+        std::vector<int4> map;
+        for (int l = 0; l < S.nlevels && e == cudaSuccess; ++l) {
+            const int *lst = ordered.data() + I.level_off[l] + I.level_nsmall[l];
+            for (int done = 0; done < I.level_nbig[l];) {
+                const int nb = std::min(I.level_nbig[l] - done, std::min(I.big_ctas, 1024));
+                std::vector<double> w(nb);
+                double W = 0.0;
+                for (int k = 0; k < nb; ++k) {
+                    const double pp = S.np[lst[done + k]], mm = S.m[lst[done + k]];
+                    w[k] = 2.0 * pp * mm * mm - 2.0 * pp * pp * mm + 2.0 / 3.0 * pp * pp * pp + 1.0;
+                    W += w[k];
+                }
+                std::vector<int> Gk(nb);
+                int used = 0;
+                for (int k = 0; k < nb; ++k) {
+                    Gk[k] = std::max(1, (int)std::floor((I.big_ctas - nb) * w[k] / W) + 1);
+                    used += Gk[k];
+                }
+                while (used > I.big_ctas) {      // rounding overshoot: take from the best-served front
+                    int best = -1;
+                    for (int k = 0; k < nb; ++k)
+                        if (Gk[k] > 1 && (best < 0 || w[k] / Gk[k] < w[best] / Gk[best])) best = k;
+                    if (best < 0) break;
+                    Gk[best]--;
+                    used--;
+                }
+                while (used < I.big_ctas) {      // leftovers to the front with the most work per CTA
+                    int best = 0;
+                    for (int k = 1; k < nb; ++k)
+                        if (w[k] / Gk[k] > w[best] / Gk[best]) best = k;
+                    Gk[best]++;
+                    used++;
+                }
+                Impl::BigLaunch bl{l, done, nb, used, (int)map.size()};
+                for (int k = 0; k < nb; ++k)
+                    for (int r = 0; r < Gk[k]; ++r) map.push_back(make_int4(k, r, Gk[k], 0));
+                I.big_launches.push_back(bl);
+                done += nb;
+            }
+        }
+        if (e == cudaSuccess && !up(&I.cta_map, map, err)) return false;
     }
     // cluster size per level: as many CTAs per front as the chip has room for (powers of two, <= 16)
     int max_cluster = 16;
@@ -1222,13 +1320,12 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
                 return false;
             }
         }
-        // large fronts of the level: groups of co-resident CTAs, as many fronts per launch as there are CTAs
-        for (int done = 0; done < level_nbig[l];) {
-            const int nb = std::min(level_nbig[l] - done, std::min(big_ctas, 1024));
-            const int G = std::max(1, big_ctas / nb);
-            cudaMemsetAsync(bar, 0, sizeof(unsigned) * nb, s);
+        // large fronts of the level: groups of co-resident CTAs (cooperative launch)
+        for (const BigLaunch &bl : big_launches) {
+            if (bl.level != l) continue;
+            cudaMemsetAsync(bar, 0, sizeof(unsigned) * bl.nb, s);
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(nb * G);
+            cfg.gridDim = dim3(bl.grid);
             cfg.blockDim = dim3(BIG_T);
             cfg.dynamicSmemBytes = kBigSmem;
             cfg.stream = s;
@@ -1237,14 +1334,13 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
             at[0].val.cooperative = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            const int *lvl = level_nodes + level_off[l] + level_nsmall[l] + done;
-            cudaError_t le = cudaLaunchKernelEx(&cfg, mf_big_factor_kernel, dev, lvl, G, bar, info);
+            const int *lvl = level_nodes + level_off[l] + level_nsmall[l] + bl.first;
+            cudaError_t le = cudaLaunchKernelEx(&cfg, mf_big_factor_kernel, dev, lvl, (const int4 *)(cta_map + bl.map_off), bar, info);
             if (le != cudaSuccess) {
-                err = std::string("multifrontal large-front launch (level ") + std::to_string(l) + ", " + std::to_string(nb) +
-                      " fronts x " + std::to_string(G) + " CTAs): " + cudaGetErrorString(le);
+                err = std::string("multifrontal large-front launch (level ") + std::to_string(l) + ", " + std::to_string(bl.nb) +
+                      " fronts on " + std::to_string(bl.grid) + " CTAs): " + cudaGetErrorString(le);
                 return false;
             }
-            done += nb;
         }
     }
     cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, s);
