@@ -501,7 +501,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "sweep"],
                     help="cfg3 (default, the headline GD iteration) or the cfg5 synthetic drifter sweep")
     ap.add_argument("--sweep-buoys", type=int, default=10_000_000)
-    ap.add_argument("--sweep-mesh", type=int, default=32)
+    ap.add_argument("--sweep-mesh", type=int, default=128,
+                    help="x_resolution of the sweep mesh (cfg5: a refined mesh; 32 = the reference mesh and its stored field)")
     args = ap.parse_args()
     if args.workload == "sweep" and args.impl == "ours":
         run_sweep(args)

@@ -549,83 +549,17 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
 //            rows below it into L = A U11^{-1} (one row per thread, in registers)
 //   -- group barrier --
 //   phase B  the CTA owning a column (4-column blocks, cyclic over the group) solves U12 for it and applies the
-//            rank-32 update to it: L is streamed through shared memory in 256-row chunks, 32 own columns per pass,
-//            4 x 4 register tiles, a warp covering 32 rows x 16 columns so that both operands are shared-memory
-//            broadcasts
+//            rank-32 update to it: U12 of the own columns sits in shared memory, every thread keeps the L rows of
+//            two matrix rows in registers (2 x 32) and streams along them through the own columns, four at a time -
+//            C in, 256 DFMAs, C out - with the next four columns' C values already in flight.  Lanes are
+//            consecutive rows, so every global access of a warp is 256 contiguous bytes and U is a broadcast.
 //   -- group barrier --
 // Column ownership is static, so a column is only ever read and written by its owner between barriers.
 constexpr int BB = 32;        // panel width
-constexpr int BIG_T = 512;    // threads per CTA
-constexpr int BIG_RC = 256;   // rows of L per shared-memory chunk (double buffered)
-constexpr int BIG_UC = 256;   // own columns whose U12 rows are resident in shared memory at a time
+constexpr int BIG_T = 256;    // threads per CTA (up to 255 registers each: two L rows of 32 live in registers)
+constexpr int BIG_UC = 640;   // own columns whose U12 column blocks are resident in shared memory at a time
 constexpr int kBigM = 768;    // fronts above this order take the group path
-constexpr size_t kBigSmem = sizeof(double) * (2 * BB * BIG_RC + BB * BIG_UC);
-
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const unsigned bytes = valid ? 8u : 0u;      // 0: zero-fill, nothing is read
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gsrc), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Rank-32 update of one 256-row chunk of the own columns.  A warp covers a block of 32 R rows (lane = row, R rows per
-// thread 32 apart: every global access of a warp is 256 contiguous bytes) x 8 columns per pass; L comes from the
-// shared chunk (conflict-free), U from the resident U12 rows (broadcast).  R is chosen per panel so that all 16 warps
-// have columns to work on: 4 (64 columns per pass), 2 (32) or 1 (16).
-template <int R>
-__device__ __forceinline__ void big_update_chunk(const double *__restrict__ Lb, const double *__restrict__ Us, double *F,
-                                                 int m, int ctrail, int r0, int nrows, int ncols, int qbase, int cbf,
-                                                 int G, int tid) {
-    constexpr int NRB = BIG_RC / (32 * R);      // row blocks per chunk
-    constexpr int NCG = (BIG_T / 32) / NRB;     // column groups (of 8) per pass
-    const int warp = tid >> 5, lane = tid & 31;
-    const int rb = warp % NRB, cg = warp / NRB;
-    const int ib = rb * 32 * R + lane;          // first row of this thread inside the chunk
-    if (r0 + rb * 32 * R >= nrows) return;
-    for (int ci0 = cg * 8; ci0 < ncols; ci0 += NCG * 8) {
-        double acc[R][8];
-#pragma unroll
-        for (int a = 0; a < R; ++a)
-#pragma unroll
-            for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
-#pragma unroll 4
-        for (int t = 0; t < BB; ++t) {
-            double l[R];
-#pragma unroll
-            for (int a = 0; a < R; ++a) l[a] = Lb[t * BIG_RC + ib + 32 * a];
-            const double2 *up = reinterpret_cast<const double2 *>(Us + t * BIG_UC + ci0);
-            const double2 u0 = up[0], u1 = up[1], u2 = up[2], u3 = up[3];
-            const double u[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
-#pragma unroll
-            for (int a = 0; a < R; ++a)
-#pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = fma(l[a], u[b], acc[a][b]);
-        }
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {           // two columns at a time: load C, subtract, store
-            const int ci = ci0 + 2 * h;
-            const int cc = (cbf + (qbase + (ci >> 2)) * G) * 4 + (ci & 3);
-            double *colp = F + (size_t)cc * m + ctrail + r0 + ib;
-            double f[R][2];
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const bool cv = ci < ncols && cc + b >= ctrail && cc + b < m;
-#pragma unroll
-                for (int a = 0; a < R; ++a)
-                    f[a][b] = (cv && r0 + ib + 32 * a < nrows) ? __ldcg(colp + (size_t)b * m + 32 * a) : 0.0;
-            }
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const bool cv = ci < ncols && cc + b >= ctrail && cc + b < m;
-#pragma unroll
-                for (int a = 0; a < R; ++a)
-                    if (cv && r0 + ib + 32 * a < nrows) __stcg(colp + (size_t)b * m + 32 * a, f[a][b] - acc[a][2 * h + b]);
-            }
-        }
-    }
-}
+constexpr size_t kBigSmem = sizeof(double) * (BB * BIG_UC);
 
 __device__ __forceinline__ void group_barrier(unsigned *cnt, unsigned target, int G) {
     __syncthreads();
@@ -687,10 +621,10 @@ __device__ __forceinline__ void invert_diag16(const double (*D)[BB + 1], const d
 }
 
 __global__ void __launch_bounds__(BIG_T, 1)
-mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restrict__ cta_map, unsigned *bar, int *info) {
+mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restrict__ cta_map, unsigned *bar, int *info,
+                     long long *prof) {
     extern __shared__ __align__(16) double sm[];
-    double *Ls = sm;                      // 2 x (BB x BIG_RC): Ls[buf][t * BIG_RC + i]
-    double *Us = sm + 2 * BB * BIG_RC;    // BB x BIG_UC: Us[t * BIG_UC + c]
+    double *Us = sm;                      // BIG_UC x BB: Us[c * BB + t], U12 of own column slot c
     __shared__ double s_D[BB][BB + 1];
     __shared__ double s_rd[BB];
     const int4 me = cta_map[blockIdx.x];  // (group = front of this launch, rank in the group, group size)
@@ -700,7 +634,12 @@ mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restr
     double *F = d.F + d.front_ptr[s];
     unsigned *cnt = bar + grp;
     unsigned target = 0;
-    // ---- extend-add of the children's update matrices
+    long long tq0 = 0, pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // optional phase timing (OCP_MF_PROF): CTA 0 of group 0
+    const bool timing = prof != nullptr && blockIdx.x == 0 && tid == 0;
+#define BIG_TICK(k) do { if (timing) { long long t_ = clock64(); pacc[k] += t_ - tq0; tq0 = t_; } } while (0)
+    if (timing) tq0 = clock64();
+    // ---- extend-add of the children's update matrices: one child at a time, so that every entry of the front has a
+    // single writer (plain read-modify-write streams at L2 bandwidth; fp64 atomics are several times slower)
     for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
         const int c = d.child[ci], mc = d.m[c], npc = d.np[c], nu = mc - npc;
         const double *Fc = d.F + d.front_ptr[c];
@@ -708,11 +647,32 @@ mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restr
         for (int j = g; j < nu; j += G) {
             const double *src = Fc + npc + (size_t)(npc + j) * mc;
             double *dst = F + (size_t)__ldg(rel + j) * m;
-            for (int i = tid; i < nu; i += BIG_T) atomicAdd(dst + __ldg(rel + i), __ldcg(src + i));
+            for (int i = tid; i < nu; i += 4 * BIG_T) {      // four independent read-modify-writes in flight per thread
+                double *p[4];
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int iu = i + u * BIG_T;
+                    p[u] = dst + (iu < nu ? __ldg(rel + iu) : 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int iu = i + u * BIG_T;
+                    v[u] = iu < nu ? __ldcg(p[u]) + __ldcg(src + iu) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i + u * BIG_T < nu) __stcg(p[u], v[u]);
+            }
         }
+        target += G;
+        group_barrier(cnt, target, G);
     }
-    target += G;
-    group_barrier(cnt, target, G);
+    if (d.child_ptr[s] == d.child_ptr[s + 1]) {
+        target += G;
+        group_barrier(cnt, target, G);
+    }
+    BIG_TICK(0);
     const int nblk_total = (m + 3) >> 2;
     for (int k0 = 0; k0 < np; k0 += BB) {
         const int kb = min(BB, np - k0), ctrail = k0 + kb, nrows = m - ctrail;
@@ -722,9 +682,11 @@ mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restr
 #pragma unroll
             for (int jj = 0; jj < BB; ++jj)
                 r[jj] = (tid < kb && jj < kb) ? __ldcg(F + (k0 + tid) + (size_t)(k0 + jj) * m) : ((jj == tid) ? 1.0 : 0.0);
+            // dependent chain per step: pivot -> reciprocal -> multiplier -> next pivot; the next pivot column is updated
+            // first and its reciprocal started before the rest of the row is touched (as in the small-front kernel)
+            double rinv = fast_rcp(__shfl_sync(0xffffffffu, r[0], 0));
 #pragma unroll
             for (int j = 0; j < BB; ++j) {
-                const double rinv = fast_rcp(__shfl_sync(0xffffffffu, r[j], j));
                 if (tid == j) {
                     s_rd[j] = rinv;
                     if (j < kb && !(fabs(rinv) < 1e280)) atomicExch(info, s + 1);
@@ -732,18 +694,26 @@ mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restr
                 const bool below = tid > j;
                 const double l = r[j] * rinv;
                 if (below) r[j] = l;
+                double rnext = 0.0;
+                if (j + 1 < BB) {
+                    const double u1 = __shfl_sync(0xffffffffu, r[j + 1], j);
+                    if (below) r[j + 1] = fma(-l, u1, r[j + 1]);
+                    rnext = fast_rcp(__shfl_sync(0xffffffffu, r[j + 1], j + 1));
+                }
 #pragma unroll
                 for (int jj = 0; jj < BB; ++jj) {
-                    if (jj > j) {
+                    if (jj > j + 1) {
                         const double u = __shfl_sync(0xffffffffu, r[jj], j);
                         if (below) r[jj] = fma(-l, u, r[jj]);
                     }
                 }
+                rinv = rnext;
             }
 #pragma unroll
             for (int jj = 0; jj < BB; ++jj) s_D[tid][jj] = r[jj];
         }
         __syncthreads();
+        BIG_TICK(1);
         // ---- A2: this CTA's share of the rows below the block: L = A U11^{-1}
         {
             const int chunk = (((nrows + G - 1) / G) + 31) & ~31;
@@ -768,8 +738,11 @@ mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restr
                     if (jj < kb) __stcg(rowp + (size_t)jj * m, a[jj]);
             }
         }
+        if (prof != nullptr && blockIdx.x == 0) __syncthreads();
+        BIG_TICK(2);
         target += G;
         group_barrier(cnt, target, G);
+        BIG_TICK(3);
         // ---- B0: one CTA stores the factored block and the inverses of its two 16 x 16 diagonal sub-blocks
         if (g == (k0 / BB) % G) {
             for (int e = tid; e < kb * kb; e += BIG_T) {
@@ -811,51 +784,101 @@ mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restr
                         if (t < kb) __stcg(colp + t, u[t]);
                 }
             }
+            if (prof != nullptr && blockIdx.x == 0) __syncthreads();
+            BIG_TICK(4);
             // ---- B2: rank-kb update of the own columns
             const int ncols_all = nown * 4;
-            const int nch = (nrows + BIG_RC - 1) / BIG_RC;
+            const int npass = (nrows + 2 * BIG_T - 1) / (2 * BIG_T);
+            const int rpp = ((((nrows + npass - 1) / npass) + 63) & ~63) >> 1;    // rows per pass / 2 (multiple of 32)
             for (int sp0 = 0; sp0 < ncols_all; sp0 += BIG_UC) {
-                const int ncols = min(BIG_UC, ncols_all - sp0), qbase = sp0 >> 2;
-                __syncthreads();   // U12 written above / previous super-pass done with Us and Ls
-                for (int e = tid; e < BB * ncols; e += BIG_T) {
+                const int ncols = min(BIG_UC, ncols_all - sp0), qbase = sp0 >> 2, nq = ncols >> 2;
+                __syncthreads();   // U12 written above / previous super-pass done with Us
+                for (int e = tid; e < BB * ((ncols + 7) & ~7); e += BIG_T) {     // (an odd block count is padded with zeros)
                     const int t = e % BB, ci = e / BB;
                     const int c = (cbf + (qbase + (ci >> 2)) * G) * 4 + (ci & 3);
-                    Us[t * BIG_UC + ci] = (c >= ctrail && c < m && t < kb) ? __ldcg(F + (size_t)c * m + k0 + t) : 0.0;
+                    Us[e] = (ci < ncols && c >= ctrail && c < m && t < kb) ? __ldcg(F + (size_t)c * m + k0 + t) : 0.0;
                 }
-                auto prefetch = [&](int ch) {
-                    double *dstb = Ls + (ch & 1) * (BB * BIG_RC);
-                    const int r0 = ch * BIG_RC;
-#pragma unroll 4
-                    for (int e = tid; e < BB * BIG_RC; e += BIG_T) {
-                        const int i = e % BIG_RC, t = e / BIG_RC;
-                        const bool v = r0 + i < nrows && t < kb;
-                        cp_async8(dstb + e, v ? F + ctrail + r0 + i + (size_t)(k0 + t) * m : F, v);
+                __syncthreads();
+                for (int rp = 0; rp < npass; ++rp) {
+                    const int ia = rp * 2 * rpp + tid, ib2 = ia + rpp;             // the two rows of this thread
+                    if (tid >= rpp || ia >= nrows) continue;                       // (no barrier inside this loop)
+                    const bool vb = ib2 < nrows;
+                    double la[BB], lb[BB];                                        // negated L rows
+                    {
+                        const double *lp = F + ctrail + (size_t)k0 * m;
+#pragma unroll
+                        for (int t = 0; t < BB; ++t) {
+                            la[t] = t < kb ? -__ldcg(lp + ia + (size_t)t * m) : 0.0;
+                            lb[t] = (t < kb && vb) ? -__ldcg(lp + ib2 + (size_t)t * m) : 0.0;
+                        }
                     }
-                    cp_async_commit();
-                };
-                prefetch(0);
-                for (int ch = 0; ch < nch; ++ch) {
-                    if (ch + 1 < nch) {
-                        prefetch(ch + 1);
-                        cp_async_wait<1>();
-                    } else {
-                        cp_async_wait<0>();
+                    double *rowa = F + ctrail + ia, *rowb = F + ctrail + ib2;
+                    double fa[8], fb[8];
+                    auto fetch = [&](int q2, double *xa, double *xb) {           // C values of the block pair q2
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int q = 2 * q2 + h;
+                            const int cb = (cbf + (qbase + q) * G) * 4;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                const bool cv = q < nq && cb + b >= ctrail && cb + b < m;
+                                xa[4 * h + b] = cv ? __ldcg(rowa + (size_t)(cb + b) * m) : 0.0;
+                                xb[4 * h + b] = (cv && vb) ? __ldcg(rowb + (size_t)(cb + b) * m) : 0.0;
+                            }
+                        }
+                    };
+                    fetch(0, fa, fb);
+                    const int nq2 = (nq + 1) >> 1;
+                    for (int q2 = 0; q2 < nq2; ++q2) {
+                        double xa[8], xb[8], na[8], nb[8];
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) {
+                            xa[b] = fa[b];
+                            xb[b] = fb[b];
+                        }
+                        fetch(q2 + 1, na, nb);                                     // next pair's C values in flight
+                        const double *up = Us + (size_t)q2 * 8 * BB;              // (an odd block count is zero padded)
+#pragma unroll
+                        for (int t = 0; t < BB; t += 2) {
+#pragma unroll
+                            for (int b = 0; b < 8; ++b) {
+                                const double2 u = *reinterpret_cast<const double2 *>(up + b * BB + t);
+                                xa[b] = fma(la[t], u.x, xa[b]);
+                                xb[b] = fma(lb[t], u.x, xb[b]);
+                                xa[b] = fma(la[t + 1], u.y, xa[b]);
+                                xb[b] = fma(lb[t + 1], u.y, xb[b]);
+                            }
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int q = 2 * q2 + h;
+                            const int cb = (cbf + (qbase + q) * G) * 4;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                if (q < nq && cb + b >= ctrail && cb + b < m) {
+                                    __stcg(rowa + (size_t)(cb + b) * m, xa[4 * h + b]);
+                                    if (vb) __stcg(rowb + (size_t)(cb + b) * m, xb[4 * h + b]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) {
+                            fa[b] = na[b];
+                            fb[b] = nb[b];
+                        }
                     }
-                    __syncthreads();
-                    const double *Lb = Ls + (ch & 1) * (BB * BIG_RC);
-                    if (ncols > 32)
-                        big_update_chunk<4>(Lb, Us, F, m, ctrail, ch * BIG_RC, nrows, ncols, qbase, cbf, G, tid);
-                    else if (ncols > 16)
-                        big_update_chunk<2>(Lb, Us, F, m, ctrail, ch * BIG_RC, nrows, ncols, qbase, cbf, G, tid);
-                    else
-                        big_update_chunk<1>(Lb, Us, F, m, ctrail, ch * BIG_RC, nrows, ncols, qbase, cbf, G, tid);
-                    __syncthreads();
                 }
             }
         }
+        if (prof != nullptr && blockIdx.x == 0) __syncthreads();
+        BIG_TICK(5);
         target += G;
         group_barrier(cnt, target, G);
+        BIG_TICK(6);
     }
+    if (timing)
+        for (int k = 0; k < 7; ++k) prof[k] = pacc[k];
+#undef BIG_TICK
 }
 
 // Triangular solves of a large front: one CTA of 1024 threads, right-hand side(s) in shared memory, 16-row blocks
@@ -1335,7 +1358,8 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
             cfg.attrs = at;
             cfg.numAttrs = 1;
             const int *lvl = level_nodes + level_off[l] + level_nsmall[l] + bl.first;
-            cudaError_t le = cudaLaunchKernelEx(&cfg, mf_big_factor_kernel, dev, lvl, (const int4 *)(cta_map + bl.map_off), bar, info);
+            long long *bprof = this->prof ? this->prof + 8 * l : nullptr;
+            cudaError_t le = cudaLaunchKernelEx(&cfg, mf_big_factor_kernel, dev, lvl, (const int4 *)(cta_map + bl.map_off), bar, info, bprof);
             if (le != cudaSuccess) {
                 err = std::string("multifrontal large-front launch (level ") + std::to_string(l) + ", " + std::to_string(bl.nb) +
                       " fronts on " + std::to_string(bl.grid) + " CTAs): " + cudaGetErrorString(le);
@@ -1372,6 +1396,10 @@ bool MultifrontalLU::factor(const double *d_vals, cudaStream_t s, std::string &e
         std::vector<long long> h(8 * S.nlevels);
         cudaMemcpy(h.data(), I.prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
         cudaMemset(I.prof, 0, sizeof(long long) * h.size());
+        for (int l = 0; l < S.nlevels; ++l)
+            if (I.level_nbig[l] > 0 && I.level_nsmall[l] == 0)
+                fprintf(stderr, "[mf prof] level %d large fronts %d | CTA0 cycles: extend-add %lld diag %lld Lrows %lld bar1 %lld u12 %lld update %lld bar2 %lld\n",
+                        l, I.level_nbig[l], h[8 * l], h[8 * l + 1], h[8 * l + 2], h[8 * l + 3], h[8 * l + 4], h[8 * l + 5], h[8 * l + 6]);
         for (int l = 0; l < S.nlevels; ++l)
             fprintf(stderr, "[mf prof] level %d fronts %d cluster %d | CTA0 cycles: load %lld diag %lld trsm %lld u12 %lld trail %lld sync %lld\n",
                     l, I.level_nsmall[l], I.level_cluster[l], h[8 * l], h[8 * l + 1], h[8 * l + 2],

@@ -508,3 +508,37 @@ def test_run_writes_the_reference_output_files_and_resumes(tmp_path):
     w = checkpoint.read_state(os.path.join(out, "paraview/checkpoint/u.h5"), V, "u")
     assert w.shape == (V.ndofs,)
     ocp.close()
+
+
+@pytest.mark.parametrize("n,big", [(48, 160), (32, 96)])
+def test_refined_mesh_large_front_solver_matches_oracle(n, big, monkeypatch):
+    """Refined square meshes (cfg5) take the large-front group kernels of the multifrontal LU.  OCP_MF_BIG lowers the
+    front order at which a front is 'large' so that the path is exercised at a size the oracle finishes in seconds:
+    one full gradient evaluation (Newton, projection with four right-hand sides, transposed adjoint solve) against
+    the oracle pipeline on the same mesh."""
+    from ocp_b200.fespace import TaylorHood
+    from ocp_b200.mesh import square_mesh
+    monkeypatch.setenv("OCP_MF_BIG", str(big))
+    V = H.square32() if n == 32 else TaylorHood(square_mesh(n))
+    rng = np.random.default_rng(3)
+    K = 64
+    x0 = np.stack([rng.uniform(0.2, 1.0, K), rng.uniform(0.3, 1.7, K)], 1)
+    f = initial_control(V, "PL")
+    P = H.OraclePipeline(V, 1.0, x0, np.zeros((K, 200, 2)), 1e-6 * K)
+    _, ud, _, _, _ = P.primal(P.O.newton_solve(1.3 * f))          # twin observations from a different control
+    P.ud = ud
+    s = P.gradient_step(f)
+    ocp = OCP(V, Parameters(), x0, ud, device=dev())
+    ocp.ctx.set_observations_host(x0, ud)
+    w, z, mask, sc = ocp.ctx.gradient_host(f)
+    assert sc["newton_its"] == s["its"] and sc["n_masked"] == int(s["mask"].sum())
+    assert H.rel(w, s["w"]) < 1e-11
+    assert H.rel(z, s["z"]) < 1e-9
+    g = ocp.project_grad(State(T(s["w"])))
+    assert H.rel(g.cpu().numpy(), s["g"]) < 1e-11
+    J = sc["misfit"] + 0.5 * 1e-6 * K * sc["f_norm2"]
+    Jo = P.cost(s["u"], f)
+    assert abs(J - Jo) <= COST_TOL * abs(Jo)
+    st = ocp.ctx.solver_stats()
+    assert st["n_factor"] >= 2
+    ocp.close()
