@@ -1496,7 +1496,12 @@ bool MultifrontalLU::Impl::enqueue_solve(double *d_x, int variant, cudaStream_t 
             launch_level_bwd<true, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
             launch_big_bwd<true>(dev, big, nbg, level_big_max_m[l], 1, d_x, ldx, s);
         } else if (variant == 2) {
-            launch_level_bwd<false, 4>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
+            // four right-hand sides at once unless their shared-memory footprint (y + per-warp partial sums) is too large
+            if (sizeof(double) * 4 * ((size_t)level_max_m[l] + (size_t)(TS / 32) * level_max_np[l]) <= 200 * 1024)
+                launch_level_bwd<false, 4>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
+            else
+                for (int r = 0; r < 4; ++r)
+                    launch_level_bwd<false, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x + (size_t)r * ldx, ldx, s);
             launch_big_bwd<false>(dev, big, nbg, level_big_max_m[l], 4, d_x, ldx, s);
         } else {
             launch_level_bwd<false, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
