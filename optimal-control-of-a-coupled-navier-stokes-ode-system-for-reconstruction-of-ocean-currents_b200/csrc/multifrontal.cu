@@ -63,12 +63,74 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return r;
 }
 
+
+// Inverses of the 16 x 16 diagonal blocks of the factors (unit-lower L11 and upper U11 of every 16-pivot block), used
+// by the blocked triangular solves.  One launch after the numeric factorisation, one warp per (block, factor): the
+// inversions are shuffle-heavy and used to sit on the critical path of every panel.
+__global__ void __launch_bounds__(256)
+mf_dinv_kernel(MFDev d, const int *__restrict__ panel_node, int npanels) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int p = w >> 1, which = w & 1;                 // which = 1: L11^{-1}, 0: U11^{-1}
+    if (p >= npanels) return;
+    const int s = panel_node[p];
+    const int m = d.m[s], np = d.np[s];
+    const int k0 = (p - d.dinv_ptr[s]) * NB, kb = min(NB, np - k0);
+    const double *F = d.F + d.front_ptr[s];
+    double r[NB];                                        // row `lane` of the factored block
+#pragma unroll
+    for (int c = 0; c < NB; ++c) r[c] = (lane < kb && c < kb) ? __ldcg(F + (k0 + lane) + (size_t)(k0 + c) * m) : 0.0;
+    double X[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) X[c] = (c == lane) ? 1.0 : 0.0;
+    if (which) {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const double lik = (lane > k && lane < kb && k < kb) ? r[k] : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c <= k) {
+                    const double xkc = __shfl_sync(0xffffffffu, X[c], k);
+                    X[c] = fma(-lik, xkc, X[c]);
+                }
+            }
+        }
+    } else {
+        double diag = 1.0;
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+            if (c == lane && lane < kb) diag = r[c];
+        const double rdiag = fast_rcp(diag);             // same reciprocal as the factorisation used
+#pragma unroll
+        for (int k = NB - 1; k >= 0; --k) {
+            const bool live = k < kb;
+            if (lane == k && live) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) X[c] *= rdiag;
+            }
+            const double uik = (lane < k && live) ? r[k] : 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (c >= k) {
+                    const double ykc = __shfl_sync(0xffffffffu, X[c], k);
+                    X[c] = fma(-uik, ykc, X[c]);
+                }
+            }
+        }
+    }
+    if (lane < NB) {
+        double *dst = d.dinv + (size_t)p * (2 * NB * NB) + (which ? 0 : NB * NB) + lane * NB;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) dst[c] = X[c];
+    }
+}
+
 template <int TF, int RMAX>
 __global__ void __launch_bounds__(TF)
 mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, long long *prof) {
     extern __shared__ double sm[];
     __shared__ double s_D[NB][NB + 1];            // factored diagonal block: L below, U on/above the diagonal
     __shared__ double s_rd[NB];                   // reciprocals of its diagonal
+    __shared__ __align__(16) double s_prow[2][NB];   // pivot row of the current / next elimination step
     cg::cluster_group cl = cg::this_cluster();
     const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     const int ldu = (max_m + CWO + 3) & ~3;       // leading dimension of the U12 staging area (multiple of 4)
@@ -115,26 +177,33 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
             double r[NB];
 #pragma unroll
             for (int jj = 0; jj < NB; ++jj) r[jj] = (tid < kb) ? a[0][jj] : ((jj == tid) ? 1.0 : 0.0);   // pad with identity
+            // The pivot row travels through shared memory (lane j stores it once, everybody reads it back as
+            // broadcasts) - 16 x 64-bit shuffles per step cost more issue slots than the whole rest of the step.
             double rinv = fast_rcp(__shfl_sync(0xffffffffu, r[0], 0));
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
+                double *prow = s_prow[j & 1];
                 if (tid == j) {
                     s_rd[j] = rinv;
                     if (j < kb && !(fabs(rinv) < 1e280)) atomicExch(info, s + 1);
+#pragma unroll
+                    for (int jj = 0; jj < NB; jj += 2)
+                        if (jj + 1 > j) *reinterpret_cast<double2 *>(prow + jj) = make_double2(r[jj], r[jj + 1]);
                 }
+                __syncwarp();
                 const bool below = tid > j;
                 const double l = r[j] * rinv;
                 if (below) r[j] = l;
                 double rnext = 0.0;
                 if (j + 1 < NB) {
-                    const double u1 = __shfl_sync(0xffffffffu, r[j + 1], j);
+                    const double u1 = prow[j + 1];
                     if (below) r[j + 1] = fma(-l, u1, r[j + 1]);
                     rnext = fast_rcp(__shfl_sync(0xffffffffu, r[j + 1], j + 1));
                 }
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) {
                     if (jj > j + 1) {
-                        const double u = __shfl_sync(0xffffffffu, r[jj], j);
+                        const double u = prow[jj];
                         if (below) r[jj] = fma(-l, u, r[jj]);
                     }
                 }
@@ -151,49 +220,6 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
         }
         __syncthreads();
         MF_TICK(acc_diag);
-        // (b') CTA 0: its two last warps invert the diagonal block (unit-lower and upper factor) for the triangular
-        // solves, which then need no sequential substitution inside a block
-        if (rank == 0 && tid >= TF - 64) {
-            const int lane = tid & 31, which = (tid >> 5) & 1;      // 1: L^{-1}, 0: U^{-1}
-            double X[NB];
-#pragma unroll
-            for (int c = 0; c < NB; ++c) X[c] = (c == lane) ? 1.0 : 0.0;
-            if (which) {
-#pragma unroll
-                for (int k = 0; k < NB; ++k) {
-                    const double lik = (lane > k && lane < kb && k < kb) ? s_D[lane < NB ? lane : 0][k] : 0.0;
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) {
-                        if (c <= k) {
-                            const double xkc = __shfl_sync(0xffffffffu, X[c], k);
-                            X[c] = fma(-lik, xkc, X[c]);
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int k = NB - 1; k >= 0; --k) {
-                    const bool live = k < kb;
-                    if (lane == k && live) {
-#pragma unroll
-                        for (int c = 0; c < NB; ++c) X[c] *= s_rd[k];
-                    }
-                    const double uik = (lane < k && live) ? s_D[lane][k] : 0.0;
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) {
-                        if (c >= k) {
-                            const double ykc = __shfl_sync(0xffffffffu, X[c], k);
-                            X[c] = fma(-uik, ykc, X[c]);
-                        }
-                    }
-                }
-            }
-            if (lane < NB) {
-                double *dst = d.dinv + ((size_t)d.dinv_ptr[s] + k0 / NB) * (2 * NB * NB) + (which ? 0 : NB * NB) + lane * NB;
-#pragma unroll
-                for (int c = 0; c < NB; ++c) dst[c] = X[c];
-            }
-        }
         // (c) rows below the block: L = A U11^{-1}; every row goes to the shared panel, CTA 0 also writes the factor
 #pragma unroll
         for (int q = 0; q < RMAX; ++q) {
@@ -315,6 +341,7 @@ constexpr int TS = 512;    // threads per CTA in the solve kernels
 // with A^T = U^T L^T (the adjoint system reuses the factors of the last Newton matrix that way)
 #define MF_E(i, c) (TR ? __ldcg(F + (c) + (size_t)(i) * m) : __ldcg(F + (i) + (size_t)(c) * m))
 #define MF_DI(row, col) (TR ? (col) * NB + (row) : (row) * NB + (col))
+
 
 // forward: y_P = L11^{-1} b_P,  b_U -= L21 y_P      (RS = rows per thread: 1 for fronts <= 512, 2 up to 1024)
 // TR: the same sweep with U^T in place of L:  y_P = U11^{-T} b_P,  b_U -= U12^T y_P
@@ -577,49 +604,6 @@ __device__ __forceinline__ void group_barrier(unsigned *cnt, unsigned target, in
     }
 }
 
-// inverse of the unit-lower (which = 1) or upper (which = 0) factor of the 16 x 16 diagonal sub-block at offset o of
-// the factored panel block D (kbs live rows), one row per lane, for the blocked triangular solves
-__device__ __forceinline__ void invert_diag16(const double (*D)[BB + 1], const double *rd, int o, int kbs, int which,
-                                              int lane, double *dst) {
-    double X[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) X[c] = (c == lane) ? 1.0 : 0.0;
-    if (which) {
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-            const double lik = (lane > k && lane < kbs && k < kbs) ? D[o + (lane < NB ? lane : 0)][o + k] : 0.0;
-#pragma unroll
-            for (int c = 0; c < NB; ++c) {
-                if (c <= k) {
-                    const double xkc = __shfl_sync(0xffffffffu, X[c], k);
-                    X[c] = fma(-lik, xkc, X[c]);
-                }
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = NB - 1; k >= 0; --k) {
-            const bool live = k < kbs;
-            if (lane == k && live) {
-#pragma unroll
-                for (int c = 0; c < NB; ++c) X[c] *= rd[o + k];
-            }
-            const double uik = (lane < k && live) ? D[o + lane][o + k] : 0.0;
-#pragma unroll
-            for (int c = 0; c < NB; ++c) {
-                if (c >= k) {
-                    const double ykc = __shfl_sync(0xffffffffu, X[c], k);
-                    X[c] = fma(-uik, ykc, X[c]);
-                }
-            }
-        }
-    }
-    if (lane < NB) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) dst[lane * NB + c] = X[c];
-    }
-}
-
 __global__ void __launch_bounds__(BIG_T, 1)
 mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restrict__ cta_map, unsigned *bar, int *info,
                      long long *prof) {
@@ -627,6 +611,7 @@ mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restr
     double *Us = sm;                      // BIG_UC x BB: Us[c * BB + t], U12 of own column slot c
     __shared__ double s_D[BB][BB + 1];
     __shared__ double s_rd[BB];
+    __shared__ __align__(16) double s_prow[2][BB];
     const int4 me = cta_map[blockIdx.x];  // (group = front of this launch, rank in the group, group size)
     const int grp = me.x, g = me.y, G = me.z, tid = threadIdx.x;
     const int s = nodes[grp];
@@ -687,23 +672,28 @@ mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restr
             double rinv = fast_rcp(__shfl_sync(0xffffffffu, r[0], 0));
 #pragma unroll
             for (int j = 0; j < BB; ++j) {
+                double *prow = s_prow[j & 1];                 // the pivot row goes through shared memory (see mf_factor_kernel)
                 if (tid == j) {
                     s_rd[j] = rinv;
                     if (j < kb && !(fabs(rinv) < 1e280)) atomicExch(info, s + 1);
+#pragma unroll
+                    for (int jj = 0; jj < BB; jj += 2)
+                        if (jj + 1 > j) *reinterpret_cast<double2 *>(prow + jj) = make_double2(r[jj], r[jj + 1]);
                 }
+                __syncwarp();
                 const bool below = tid > j;
                 const double l = r[j] * rinv;
                 if (below) r[j] = l;
                 double rnext = 0.0;
                 if (j + 1 < BB) {
-                    const double u1 = __shfl_sync(0xffffffffu, r[j + 1], j);
+                    const double u1 = prow[j + 1];
                     if (below) r[j + 1] = fma(-l, u1, r[j + 1]);
                     rnext = fast_rcp(__shfl_sync(0xffffffffu, r[j + 1], j + 1));
                 }
 #pragma unroll
                 for (int jj = 0; jj < BB; ++jj) {
                     if (jj > j + 1) {
-                        const double u = __shfl_sync(0xffffffffu, r[jj], j);
+                        const double u = prow[jj];
                         if (below) r[jj] = fma(-l, u, r[jj]);
                     }
                 }
@@ -743,20 +733,11 @@ mf_big_factor_kernel(MFDev d, const int *__restrict__ nodes, const int4 *__restr
         target += G;
         group_barrier(cnt, target, G);
         BIG_TICK(3);
-        // ---- B0: one CTA stores the factored block and the inverses of its two 16 x 16 diagonal sub-blocks
+        // ---- B0: one CTA stores the factored block
         if (g == (k0 / BB) % G) {
             for (int e = tid; e < kb * kb; e += BIG_T) {
                 const int i = e % kb, j = e / kb;
                 __stcg(F + (k0 + i) + (size_t)(k0 + j) * m, s_D[i][j]);
-            }
-            if (tid >= BIG_T - 128) {
-                const int w = (tid - (BIG_T - 128)) >> 5, lane = tid & 31;
-                const int sub = w >> 1, which = w & 1, o = sub * NB;
-                const int kbs = min(NB, kb - o);
-                if (kbs > 0) {
-                    double *dst = d.dinv + ((size_t)d.dinv_ptr[s] + k0 / NB + sub) * (2 * NB * NB) + (which ? 0 : NB * NB);
-                    invert_diag16(s_D, s_rd, o, kbs, which, lane, dst);
-                }
             }
         }
         if (nrows > 0) {
@@ -1061,6 +1042,8 @@ struct MultifrontalLU::Impl {
         int level, first, nb, grid, map_off;
     };
     std::vector<BigLaunch> big_launches;
+    int *panel_node = nullptr;   // front of every 16-pivot block (mf_dinv_kernel)
+    int npanels = 0;
     int4 *cta_map = nullptr;     // per CTA of every large-front launch: (front of the launch, rank in its group, group size)
     // CUDA graphs of the factor / solve launch sequences, keyed by the (fixed) device pointer they operate on
     std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs, solve_t_graphs, solve4_graphs;
@@ -1070,7 +1053,7 @@ struct MultifrontalLU::Impl {
     MFDev dev{};
     ~Impl() {
         void *p[] = {m, np, first, idx_ptr, idx, child_ptr, child, rel_ptr, rel, level_nodes, piv, info, front_ptr,
-                     a_dest, F, prof, dinv, dinv_ptr, bar, cta_map};
+                     a_dest, F, prof, dinv, dinv_ptr, bar, cta_map, panel_node};
         for (void *q : p) cudaFree(q);
         for (auto &kv : factor_graphs) cudaGraphExecDestroy(kv.second);
         for (auto &kv : solve_graphs) cudaGraphExecDestroy(kv.second);
@@ -1296,6 +1279,11 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
         std::vector<int> dp(S.nnodes + 1, 0);
         for (int k = 0; k < S.nnodes; ++k) dp[k + 1] = dp[k] + (S.np[k] + NB - 1) / NB;
         if (!up(&I.dinv_ptr, dp, err)) return false;
+        std::vector<int> pn(dp[S.nnodes]);
+        for (int k = 0; k < S.nnodes; ++k)
+            for (int q = dp[k]; q < dp[k + 1]; ++q) pn[q] = k;
+        I.npanels = dp[S.nnodes];
+        if (!up(&I.panel_node, pn, err)) return false;
         if (cudaMalloc((void **)&I.dinv, sizeof(double) * 2 * NB * NB * std::max(dp[S.nnodes], 1)) != cudaSuccess) {
             err = "multifrontal setup: out of memory";
             return false;
@@ -1367,6 +1355,7 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
             }
         }
     }
+    if (npanels > 0) mf_dinv_kernel<<<(2 * npanels * 32 + 255) / 256, 256, 0, s>>>(dev, panel_node, npanels);
     cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, s);
     return true;
 }
@@ -1386,7 +1375,7 @@ bool MultifrontalLU::factor(const double *d_vals, cudaStream_t s, std::string &e
         }
         I.dev.F = I.F;
     }
-    g_launch_count.fetch_add(1 + I.S.nlevels, std::memory_order_relaxed);
+    g_launch_count.fetch_add(2 + I.S.nlevels + (int)I.big_launches.size(), std::memory_order_relaxed);
     const int nnz = nnz_;
     if (!I.run(I.factor_graphs, d_vals, s, err, [&](cudaStream_t q) { return I.enqueue_factor(d_vals, nnz, q, err); }))
         return false;
