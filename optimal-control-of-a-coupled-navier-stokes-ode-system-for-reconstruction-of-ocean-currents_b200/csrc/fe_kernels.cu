@@ -55,7 +55,7 @@ __device__ __forceinline__ void block_finish3(double a, double b, double c, doub
 
 // 16 lanes per cell, lane r < 15 owns row r of the 15x15 element matrix.
 template <bool kTranspose>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 assemble_cells_kernel(int nc, const double *__restrict__ geom, const int *__restrict__ cell_dofs,
                       const int *__restrict__ slots, const double *__restrict__ w, double nu,
                       double *__restrict__ vals, double *__restrict__ res) {
