@@ -490,6 +490,91 @@ def run_sweep(args):
         dist.destroy_process_group()
 
 
+def run_ensemble(args):
+    """--workload ensemble: BASELINE.json cfg4 on ONE GPU - initial_control_test.py cases 0-3 (6 buoys) plus the
+    Pipeline_limits.py sweep over 10 / 100 / 400 / 10 000 buoys = 8 independent cases, each with its own context,
+    CUDA stream and host thread, one gradient evaluation per case per step through the C-ABI host-buffer call.
+    Reports aggregate GD iterations/s for the concurrent run and for the same cases run one after the other."""
+    import torch
+    import ocp_b200  # noqa: F401
+    from ocp_b200.ensemble import Case, Ensemble
+    from ocp_b200.fespace import TaylorHood
+    from ocp_b200.mesh import square_mesh
+    from ocp_b200.pipeline import OCP, Parameters, initial_control
+    import torch.distributed as dist
+    from ocp_b200.sharding import init_from_env
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        group, rank, world, local = init_from_env("nccl")
+        if group is not None:
+            dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local)), group=group)
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    V = TaylorHood(square_mesh(32))
+    gold = os.path.join(ROOT, "tests", "golden")
+    cases = []
+    t6 = np.load(os.path.join(gold, "traj_6_buoys.npz"))
+    for c in range(4):
+        cases.append(Case(f"ICT case {c}", t6["x_0_array"][:, 0, :].copy(), t6["u_d_array"], initial_control(V, "ICT", c)))
+    for K in (10, 100, 400):
+        t = np.load(os.path.join(gold, f"traj_{K}_buoys.npz"))
+        cases.append(Case(f"PL {K} buoys", t["x_0_array"][:, 0, :].copy(), t["u_d_array"], initial_control(V, "PL")))
+    x0 = reference_grid()
+    ocp = OCP(V, Parameters(), x0, np.zeros((x0.shape[0], NT, 2)), device=dev)
+    ocp._primal(torch.from_numpy(golden_field()).to(dev), ocp.d_x, ocp.d_u, ocp.d_mask)
+    ud = ocp._to_reference_layout(ocp.d_u)
+    ocp.close()
+    cases.append(Case("PL 10000 buoys", x0, ud, initial_control(V, "PL")))
+    n_total = len(cases)
+    cases = cases[rank::world]                 # independent cases: sharded over the ranks, no collective on the data path
+    E = Ensemble(V, cases, device=dev)
+    warm = max(args.warmup, 3)
+
+    def timed(concurrent):
+        for _ in range(warm):
+            res = E.gradients(concurrent=concurrent)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = E.gradients(concurrent=concurrent)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / args.steps * 1e3, res
+
+    ms_seq, r_seq = timed(False)
+    if group is not None:
+        dist.barrier(group=group)
+    ms_con, r_con = timed(True)
+    dJ = max(abs(a["J"] - b["J"]) / max(abs(a["J"]), 1e-300) for a, b in zip(r_seq, r_con))
+    if group is not None:                      # whole-job time = the slowest rank
+        t = torch.tensor([ms_seq, ms_con, dJ], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        ms_seq, ms_con, dJ = (float(v) for v in t.tolist())
+    n = n_total
+    if rank != 0:
+        E.close()
+        dist.destroy_process_group()
+        return
+    print(json.dumps({
+        "metric": "ensemble_gd_iters_per_sec", "value": n / (ms_con * 1e-3), "unit": "GD iterations/s (aggregate over the cases)",
+        "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_con, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "reference fixtures (tests/golden) + synthetic 10000-buoy grid",
+        "config": {"workload": "cfg4 ensemble: ICT cases 0-3 + PL 10/100/400/10000 buoys, square 32x32, one context/stream/thread per case",
+                   "cases": [c.name for c in cases], "timing": "host wall clock around one gradient evaluation of every case"},
+        "sequential_ms_per_step": ms_seq, "sequential_gd_iters_per_sec": n / (ms_seq * 1e-3),
+        "concurrency_gain": ms_seq / ms_con, "max_rel_cost_difference_concurrent_vs_sequential": dJ,
+        "J_rank0": [r["J"] for r in r_con], "newton_its_rank0": [r["newton_its"] for r in r_con]}), flush=True)
+    E.close()
+    if group is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -498,12 +583,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 2^20-buoy kernel sweep")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "sweep"],
-                    help="cfg3 (default, the headline GD iteration) or the cfg5 synthetic drifter sweep")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "sweep", "ensemble"],
+                    help="cfg3 (default, the headline GD iteration), the cfg5 synthetic drifter sweep, or the cfg4 ensemble of "
+                         "independent cases run concurrently on one GPU")
     ap.add_argument("--sweep-buoys", type=int, default=10_000_000)
     ap.add_argument("--sweep-mesh", type=int, default=128,
                     help="x_resolution of the sweep mesh (cfg5: a refined mesh; 32 = the reference mesh and its stored field)")
     args = ap.parse_args()
+    if args.workload == "ensemble" and args.impl == "ours":
+        run_ensemble(args)
+        return
     if args.workload == "sweep" and args.impl == "ours":
         run_sweep(args)
         return

@@ -542,3 +542,30 @@ def test_refined_mesh_large_front_solver_matches_oracle(n, big, monkeypatch):
     st = ocp.ctx.solver_stats()
     assert st["n_factor"] >= 2
     ocp.close()
+
+
+def test_ensemble_of_independent_cases_runs_concurrently_with_identical_results():
+    """cfg4: independent cases on one GPU, one context / stream / host thread each (ocp_b200.ensemble).  The concurrent
+    run must reproduce the one-after-the-other run and the oracle's cost of every case."""
+    from ocp_b200.ensemble import Case, Ensemble
+    V = H.square32()
+    xr6, ud6 = H.traj(6)
+    xr10, ud10 = H.traj(10)
+    cases = [Case(f"ICT {c}", xr6[:, 0, :].copy(), ud6, initial_control(V, "ICT", c)) for c in range(4)]
+    cases.append(Case("PL 10", xr10[:, 0, :].copy(), ud10, initial_control(V, "PL")))
+    E = Ensemble(V, cases, device=dev())
+    seq = E.gradients(concurrent=False)
+    for _ in range(3):
+        con = E.gradients(concurrent=True)
+        for a, b in zip(seq, con):
+            assert a["newton_its"] == b["newton_its"] and a["n_masked"] == b["n_masked"]
+            assert abs(a["J"] - b["J"]) <= 1e-12 * abs(a["J"])
+            assert H.rel(b["w"], a["w"]) < 1e-13 and H.rel(b["z"], a["z"]) < 1e-10
+    s = H.OraclePipeline(V, 1.0, xr10[:, 0, :].copy(), ud10, 1e-5).gradient_step(cases[4].f0)
+    assert abs(con[4]["J"] - 0.025045819440590228) < COST_TOL * 0.025
+    g1 = np.unique(V.g1_nodes)
+    assert H.rel(con[4]["grad"][g1], s["grad"][g1]) < 1e-8
+    h2 = E.descend(2, concurrent=True)
+    h1 = E.descend(2, concurrent=False)
+    assert np.allclose(np.array(h1), np.array(h2), rtol=1e-11, atol=0)
+    E.close()
