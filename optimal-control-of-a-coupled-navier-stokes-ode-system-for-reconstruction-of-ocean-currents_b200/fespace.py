@@ -44,7 +44,6 @@ class TaylorHood:
     ndofs: int = 0
     csr_rowptr: np.ndarray = field(default=None, repr=False)    # (ndofs+1,) i4
     csr_col: np.ndarray = field(default=None, repr=False)       # (nnz,) i4
-    cell_slots: np.ndarray = field(default=None, repr=False)    # (nc, 225) i4: CSR position of (i,j)
     dirichlet_dofs: np.ndarray = field(default=None, repr=False)
     # Gamma_1 facet tables
     g1_cell: np.ndarray = field(default=None, repr=False)       # (n1,) i4
@@ -118,17 +117,36 @@ class TaylorHood:
 
     # -- sparsity -------------------------------------------------------------
     def _build_csr(self):
-        cd = self.cell_dofs.astype(np.int64)
-        n = self.ndofs
-        rows = np.repeat(cd, 15, axis=1).reshape(-1)
-        cols = np.tile(cd, (1, 15)).reshape(-1)
-        key = rows * n + cols
-        uniq = np.unique(key)
-        r = (uniq // n).astype(np.int64)
-        self.csr_col = (uniq % n).astype(np.int32)
+        """CSR pattern = union over cells of dofs x dofs (equal to dolfin's count on the reference mesh).  Built from the
+        unique NODE pairs that share a cell (36 + 18 + 9 per cell instead of 225 dof pairs: 512 x 512 cells would
+        otherwise mean sorting 1.2e8 keys), expanded to dof pairs through the (injective) dof maps."""
+        cn = self.cell_nodes.astype(np.int64)
+        nn, n = self.num_nodes, self.ndofs
+
+        def unique_pairs(a, b):
+            """unique (a_i, b_j) over the cells; a (nc, p), b (nc, q) node ids"""
+            key = np.sort((a[:, :, None] * nn + b[:, None, :]).reshape(-1))      # (sort + compare: numpy's hash-based
+            key = key[np.r_[True, key[1:] != key[:-1]]]                          #  unique is 10x slower on 1e7 keys)
+            return key // nn, key % nn
+
+        ux, uy, pp = (d.astype(np.int64) for d in (self.dof_ux, self.dof_uy, self.dof_p))
+        a, b = unique_pairs(cn, cn)                      # P2 node - P2 node
+        c, v = unique_pairs(cn, cn[:, :3])               # P2 node - vertex
+        v1, v2 = unique_pairs(cn[:, :3], cn[:, :3])      # vertex - vertex (the structurally present, zero p-p block)
+        rows = np.concatenate([ux[a], ux[a], uy[a], uy[a], ux[c], uy[c], pp[v], pp[v], pp[v1]])
+        cols = np.concatenate([ux[b], uy[b], ux[b], uy[b], pp[v], pp[v], ux[c], uy[c], pp[v2]])
+        key = np.sort(rows * n + cols)
+        self.csr_col = (key % n).astype(np.int32)
         self.csr_rowptr = np.zeros(n + 1, dtype=np.int32)
-        np.cumsum(np.bincount(r, minlength=n), out=self.csr_rowptr[1:])
-        self.cell_slots = np.searchsorted(uniq, key).reshape(-1, 225).astype(np.int32)
+        np.cumsum(np.bincount(key // n, minlength=n), out=self.csr_rowptr[1:])
+
+    @property
+    def cell_slots(self) -> np.ndarray:
+        """(nc, 225) i4: CSR position of element entry (i, j) (the library builds its own copy in ocp_create)"""
+        cd = self.cell_dofs.astype(np.int64)
+        key = (np.repeat(cd, 15, axis=1) * self.ndofs + np.tile(cd, (1, 15))).reshape(-1)
+        full = np.repeat(np.arange(self.ndofs, dtype=np.int64), np.diff(self.csr_rowptr)) * self.ndofs + self.csr_col
+        return np.searchsorted(full, key).reshape(-1, 225).astype(np.int32)
 
     # -- boundary -------------------------------------------------------------
     def _build_boundary_tables(self):
