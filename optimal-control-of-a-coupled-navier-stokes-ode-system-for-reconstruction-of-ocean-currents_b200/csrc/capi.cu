@@ -28,12 +28,12 @@ struct DirectSolver {
     bool use_mf = true, factored_once = false;
     double analyse_ms = 0.0;
     bool configure(int n, int nnz, const int *h_rowptr, const int *h_col, const int *d_rowptr, const int *d_col,
-                   const double *xy, const unsigned char *kind, std::string &err) {
+                   const double *xy, const unsigned char *kind, std::string &err, const DirectSolver *share = nullptr) {
         const char *env = getenv("OCP_SOLVER");
         use_mf = !(env && std::string(env) == "rf");
         if (use_mf) {
             std::string e2;
-            if (mf.configure(n, nnz, h_rowptr, h_col, xy, kind, e2)) {
+            if (mf.configure(n, nnz, h_rowptr, h_col, xy, kind, e2, share && share->use_mf ? &share->mf : nullptr)) {
                 analyse_ms = mf.analyse_ms;
                 return true;
             }
@@ -432,8 +432,8 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     }
     std::vector<unsigned char> kind0(nv, 0);
     if (!c->lu_fwd.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data(), c->err) ||
-        !c->lu_adj.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data(), c->err) ||
-        !c->lu_stokes.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data(), c->err) ||
+        !c->lu_adj.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data(), c->err, &c->lu_fwd) ||
+        !c->lu_stokes.configure(n, d->nnz, d->csr_rowptr, d->csr_col, c->d_rowptr, c->d_col, xy.data(), kind.data(), c->err, &c->lu_fwd) ||
         !c->lu_mass.configure(nv, c->m_nnz, m_rowptr.data(), m_col.data(), c->d_m_rowptr, c->d_m_col, d->node_coords,
                               kind0.data(), c->err))
         return OCP_ERR_SOLVER;

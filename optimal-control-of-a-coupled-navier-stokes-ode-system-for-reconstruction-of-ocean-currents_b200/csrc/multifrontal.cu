@@ -1100,14 +1100,17 @@ MultifrontalLU::MultifrontalLU() = default;
 MultifrontalLU::~MultifrontalLU() { delete impl_; }
 
 bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h_col, const double *xy,
-                               const unsigned char *kind, std::string &err) {
+                               const unsigned char *kind, std::string &err, const MultifrontalLU *share) {
     auto t0 = std::chrono::steady_clock::now();
     delete impl_;
     impl_ = new Impl();
     Impl &I = *impl_;
     n_ = n;
     nnz_ = nnz;
-    mf_analyse(n, h_rowptr, h_col, xy, kind, 48, I.S);
+    if (share && share->impl_ && share->n_ == n && share->nnz_ == nnz)
+        I.S = share->impl_->S;
+    else
+        mf_analyse(n, h_rowptr, h_col, xy, kind, 48, I.S);
     const MFSymbolic &S = I.S;
     for (long long dd : S.a_dest)
         if (dd < 0) {

@@ -17,8 +17,10 @@ class MultifrontalLU {
     MultifrontalLU &operator=(const MultifrontalLU &) = delete;
 
     // symbolic analysis (host, pattern + coordinates only) and upload of the schedule
+    // `share`: another solver already configured for the SAME pattern, coordinates and kinds - its symbolic analysis
+    // is copied instead of being recomputed (the forward, adjoint and Stokes matrices of a context share one pattern)
     bool configure(int n, int nnz, const int *h_rowptr, const int *h_col, const double *xy, const unsigned char *kind,
-                   std::string &err);
+                   std::string &err, const MultifrontalLU *share = nullptr);
     bool factor(const double *d_vals, cudaStream_t s, std::string &err);   // numeric factorisation on the GPU
     // in place; transposed: solves A^T x = b with the same factors
     bool solve(double *d_x, cudaStream_t s, std::string &err, bool transposed = false);
