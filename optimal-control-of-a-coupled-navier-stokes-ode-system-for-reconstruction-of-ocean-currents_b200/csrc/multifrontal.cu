@@ -1,8 +1,13 @@
-// GPU numeric phase of the multifrontal LU (see multifrontal.hpp): one CTA per front, one launch per level of
-// the nested-dissection tree.  Fronts are dense column-major m x m blocks in one HBM workspace (L2 resident for
-// the reference meshes); each CTA extend-adds its children's Schur complements, then runs a right-looking
-// blocked LU of the np fully-summed columns (panel of 16 columns in shared memory, 4x4 register tiles for the
-// trailing update) with partial pivoting restricted to the fully-summed rows.
+// GPU numeric phase of the multifrontal LU (see multifrontal.hpp).  Fronts are dense column-major m x m blocks in one
+// HBM workspace (L2 resident for the reference meshes); one launch per level of the nested-dissection tree, the whole
+// factorisation / solve replayed as a CUDA graph.
+//   small fronts (order <= 768): one thread-block CLUSTER per front - extend-add of the children's Schur complements,
+//     then a right-looking blocked LU of the np fully-summed columns (16-column panel in shared memory / registers,
+//     4 x 4 register tiles for the trailing update, one cluster barrier per panel);
+//   large fronts (refined meshes): a GROUP of co-resident CTAs per front working out of L2 / HBM with 32-column
+//     panels and group barriers in global memory (mf_big_factor_kernel).
+// Pivoting is static (see the comment above mf_factor_kernel); the triangular solves work in 16-row blocks with the
+// inverses of the diagonal blocks (mf_dinv_kernel).
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 

@@ -99,3 +99,34 @@ def test_h5lite_reads_reference_checkpoints():
     assert np.array_equal(ds["vector"], H.fields()["u_bar"])
     q = h5lite.read_checkpoint("/root/reference/reference_runs/u_bar_chapter_6.3.3/q_backup/q.h5", "f")
     assert q["vector"].size == 8450
+
+
+@pytest.mark.parametrize("which", ["square8", "square32", "lshape"])
+def test_csr_pattern_is_the_union_of_element_patterns(which):
+    """The pattern is built from unique NODE pairs (fespace._build_csr); it must equal the brute-force union over the
+    cells of dofs x dofs - also in dolfin's numbering of the reference mesh - and cell_slots must address it."""
+    V = {"square8": lambda: TaylorHood(square_mesh(8)), "square32": H.square32,
+         "lshape": lambda: TaylorHood(lshape_mesh(6, jitter=0.2))}[which]()
+    cd = V.cell_dofs.astype(np.int64)
+    n = V.ndofs
+    key = (np.repeat(cd, 15, axis=1) * n + np.tile(cd, (1, 15))).reshape(-1)
+    uniq = np.unique(key)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(V.csr_rowptr))
+    assert np.array_equal(rows * n + V.csr_col, uniq)
+    assert V.csr_rowptr[0] == 0 and V.csr_rowptr[-1] == uniq.size
+    sl = V.cell_slots
+    assert sl.shape == (V.mesh.num_cells, 225)
+    assert np.array_equal(uniq[sl.reshape(-1)], key)
+
+
+def test_ensemble_needs_a_gpu():
+    """ocp_b200.ensemble (cfg4) has no CPU path either."""
+    import torch
+    from ocp_b200 import capi
+    from ocp_b200.ensemble import Case, Ensemble
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    V = TaylorHood(square_mesh(4))
+    c = Case("x", np.array([[0.5, 0.5]]), np.zeros((1, 200, 2)), np.zeros((V.num_nodes, 2)))
+    with pytest.raises(capi.OcpError):
+        Ensemble(V, [c])
