@@ -174,6 +174,20 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
             for (int jj = 0; jj < NB; ++jj)
                 a[q][jj] = (i < mp && jj < kb) ? __ldcg(F + (k0 + i) + (size_t)(k0 + jj) * m) : 0.0;
         }
+        // (a') the few threads that will solve U12 (phase d) fetch their first column now: the loads are in flight
+        // while warp 0 factors the diagonal block
+        const int idx0 = TF - 1 - tid;
+        double u0[NB];
+        bool u0_valid = false;
+        if (idx0 < nown * CWO) {
+            const int c = (rank + (idx0 / CWO) * C) * CWO + (idx0 % CWO);
+            if (c >= ctrail && c < m) {
+                u0_valid = true;
+                const double *colp = F + (size_t)c * m + k0;
+#pragma unroll
+                for (int t = 0; t < NB; ++t) u0[t] = t < kb ? __ldcg(colp + t) : 0.0;
+            }
+        }
         if (prof) { __syncthreads(); MF_TICK(acc_load); }
         // (b) diagonal block inside warp 0: lane i holds row i.  The dependent chain per step is
         // pivot -> reciprocal -> multiplier -> update of the NEXT pivot, so the next pivot column is updated first
@@ -225,6 +239,36 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
         }
         __syncthreads();
         MF_TICK(acc_diag);
+        // (d) U12 = L11^{-1} F12 for the own trailing columns.  Runs on the highest thread ids, whose panel rows (phase
+        // c below) mostly do not exist (m < TF), so this serial 16-step substitution overlaps phase (c) of the others.
+        for (int idx = idx0; idx < nown * CWO; idx += TF) {
+            const int c = (rank + (idx / CWO) * C) * CWO + (idx % CWO);
+            if (c >= ctrail && c < m) {
+                double *colp = F + (size_t)c * m + k0;
+                double u[NB];
+                if (idx == idx0 && u0_valid) {
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) u[t] = u0[t];
+                } else {
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) u[t] = t < kb ? __ldcg(colp + t) : 0.0;
+                }
+#pragma unroll
+                for (int t = 0; t < NB; ++t) {
+                    if (t < kb) {
+#pragma unroll
+                        for (int tt = 0; tt < NB; ++tt)
+                            if (tt > t && tt < kb) u[tt] = fma(-s_D[tt][t], u[t], u[tt]);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < NB; ++t) {
+                    if (t < kb) __stcg(colp + t, u[t]);
+                    Uc[t * ldu + idx] = u[t];
+                }
+            }
+        }
+        if (prof) { __syncthreads(); MF_TICK(acc_trsm); }
         // (c) rows below the block: L = A U11^{-1}; every row goes to the shared panel, CTA 0 also writes the factor
 #pragma unroll
         for (int q = 0; q < RMAX; ++q) {
@@ -248,30 +292,6 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
                         P[i + jj * ldp] = a[q][jj];
                         if (rank == 0) __stcg(F + (k0 + i) + (size_t)(k0 + jj) * m, a[q][jj]);
                     }
-                }
-            }
-        }
-        if (prof) { __syncthreads(); MF_TICK(acc_trsm); }
-        // (d) U12 = L11^{-1} F12 for the own trailing columns
-        for (int idx = TF - 1 - tid; idx < nown * CWO; idx += TF) {
-            const int c = (rank + (idx / CWO) * C) * CWO + (idx % CWO);
-            if (c >= ctrail && c < m) {
-                double *colp = F + (size_t)c * m + k0;
-                double u[NB];
-#pragma unroll
-                for (int t = 0; t < NB; ++t) u[t] = t < kb ? __ldcg(colp + t) : 0.0;
-#pragma unroll
-                for (int t = 0; t < NB; ++t) {
-                    if (t < kb) {
-#pragma unroll
-                        for (int tt = 0; tt < NB; ++tt)
-                            if (tt > t && tt < kb) u[tt] = fma(-s_D[tt][t], u[t], u[tt]);
-                    }
-                }
-#pragma unroll
-                for (int t = 0; t < NB; ++t) {
-                    if (t < kb) __stcg(colp + t, u[t]);
-                    Uc[t * ldu + idx] = u[t];
                 }
             }
         }
@@ -1398,7 +1418,7 @@ bool MultifrontalLU::factor(const double *d_vals, cudaStream_t s, std::string &e
                 fprintf(stderr, "[mf prof] level %d large fronts %d | CTA0 cycles: extend-add %lld diag %lld Lrows %lld bar1 %lld u12 %lld update %lld bar2 %lld\n",
                         l, I.level_nbig[l], h[8 * l], h[8 * l + 1], h[8 * l + 2], h[8 * l + 3], h[8 * l + 4], h[8 * l + 5], h[8 * l + 6]);
         for (int l = 0; l < S.nlevels; ++l)
-            fprintf(stderr, "[mf prof] level %d fronts %d cluster %d | CTA0 cycles: load %lld diag %lld trsm %lld u12 %lld trail %lld sync %lld\n",
+            fprintf(stderr, "[mf prof] level %d fronts %d cluster %d | CTA0 cycles: load %lld diag %lld u12 %lld Lrows %lld trail %lld sync %lld\n",
                     l, I.level_nsmall[l], I.level_cluster[l], h[8 * l], h[8 * l + 1], h[8 * l + 2],
                     h[8 * l + 3], h[8 * l + 4], h[8 * l + 5]);
     }
