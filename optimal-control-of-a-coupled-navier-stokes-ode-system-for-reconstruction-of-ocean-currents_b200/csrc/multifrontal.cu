@@ -129,13 +129,67 @@ mf_dinv_kernel(MFDev d, const int *__restrict__ panel_node, int npanels) {
     }
 }
 
+// Split-phase cluster barrier and a barrier over the worker warps only (the look-ahead warp does not take part).
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
+
+// LU of a 16 x 16 block held one row per lane (rows >= kb are identity padding), static pivoting.  The dependent chain
+// per step is pivot -> reciprocal -> multiplier -> update of the NEXT pivot, so the next pivot column is updated first
+// and its reciprocal is started before the remaining columns of the step are touched; the pivot row travels through
+// shared memory (lane j stores it once, everybody reads it back as broadcasts).
+__device__ __forceinline__ void diag16_factor(double (&r)[NB], int lane, int kb, double (*prow2)[NB], double *rd, int *info,
+                                              int front) {
+    double rinv = fast_rcp(__shfl_sync(0xffffffffu, r[0], 0));
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        double *prow = prow2[j & 1];
+        if (lane == j) {
+            rd[j] = rinv;
+            if (j < kb && !(fabs(rinv) < 1e280)) atomicExch(info, front + 1);
+#pragma unroll
+            for (int jj = 0; jj < NB; jj += 2)
+                if (jj + 1 > j) *reinterpret_cast<double2 *>(prow + jj) = make_double2(r[jj], r[jj + 1]);
+        }
+        __syncwarp();
+        const bool below = lane > j;
+        const double l = r[j] * rinv;
+        if (below) r[j] = l;
+        double rnext = 0.0;
+        if (j + 1 < NB) {
+            const double u1 = prow[j + 1];
+            if (below) r[j + 1] = fma(-l, u1, r[j + 1]);
+            rnext = fast_rcp(__shfl_sync(0xffffffffu, r[j + 1], j + 1));
+        }
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj) {
+            if (jj > j + 1) {
+                const double u = prow[jj];
+                if (below) r[jj] = fma(-l, u, r[jj]);
+            }
+        }
+        rinv = rnext;
+    }
+}
+
+// TF threads = TF - 32 workers + one LOOK-AHEAD warp.  While the workers run panel k (rows below the block, U12, trailing
+// update), the look-ahead warp of every CTA produces the factored diagonal block of panel k+1 on its own: it reads the
+// 32 x 32 corner [A11 A12; A21 A22] of the trailing matrix right after the cluster barrier, forms U12' = L11^{-1} A12,
+// L21' = A21 U11^{-1} and A22 - L21' U12' with exactly the arithmetic of phases (d), (c), (e) below (so the result is
+// bit-identical to what the trailing update stores) and factors it.  The serial 16-step elimination - the longest
+// single-warp section of a panel - is thereby off the critical path.  All global stores of a panel are issued after
+// a split-phase cluster barrier whose arrival the look-ahead warps signal once they hold their corner in registers,
+// so no CTA can overwrite an entry another CTA's look-ahead warp still has to read.
 template <int TF, int RMAX>
-__global__ void __launch_bounds__(TF)
+__global__ void __launch_bounds__(TF, 1)
 mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, long long *prof) {
+    constexpr int TW = TF - 32;                   // worker threads
     extern __shared__ double sm[];
-    __shared__ double s_D[NB][NB + 1];            // factored diagonal block: L below, U on/above the diagonal
-    __shared__ double s_rd[NB];                   // reciprocals of its diagonal
+    __shared__ double s_D[2][NB][NB + 1];         // factored diagonal block of the current / next panel: L below, U on/above
+    __shared__ double s_rd[2][NB];                // reciprocals of its diagonal
     __shared__ __align__(16) double s_prow[2][NB];   // pivot row of the current / next elimination step
+    __shared__ double s_T[NB][NB + 1];            // U12' of the look-ahead corner
     cg::cluster_group cl = cg::this_cluster();
     const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     const int ldu = (max_m + CWO + 3) & ~3;       // leading dimension of the U12 staging area (multiple of 4)
@@ -143,6 +197,8 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
     double *Uc = sm + (size_t)((max_m + 3) & ~3) * NB;   // NB x ldu, row-major, indexed by "own column" number
     const int s = nodes[blockIdx.x / C];
     const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
+    const bool worker = tid < TW;
+    const int lane = tid & 31;
     double *F = d.F + d.front_ptr[s];
     // ---- extend-add the children's update matrices (atomic: two children may hit the same entry)
     for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
@@ -160,192 +216,222 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
     long long tp0 = 0, acc_panel = 0, acc_trail = 0, acc_sync = 0, acc_load = 0, acc_diag = 0, acc_trsm = 0;
 #define MF_TICK(accv) do { if (prof && tid == 0) { long long t_ = clock64(); accv += t_ - tp0; tp0 = t_; } } while (0)
     if (prof && tid == 0) tp0 = clock64();
-    // own columns: chunk q covers absolute columns [(rank + q C) 16, +16); "own column number" = 16 q + (c % 16)
+    // ---- prologue: the look-ahead warp factors the first diagonal block
+    if (!worker) {
+        const int kb = min(NB, np);
+        double r[NB];
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj)
+            r[jj] = (lane < kb && jj < kb) ? __ldcg(F + lane + (size_t)jj * m) : ((jj == lane) ? 1.0 : 0.0);
+        diag16_factor(r, lane, kb, s_prow, s_rd[0], info, s);
+        if (lane < NB) {
+#pragma unroll
+            for (int jj = 0; jj < NB; ++jj) s_D[0][lane][jj] = r[jj];
+        }
+    }
+    __syncthreads();
+    MF_TICK(acc_diag);
+    // own columns: chunk q covers absolute columns [(rank + q C) 4, +4); "own column number" = 4 q + (c % 4)
     const int nown = (m > rank * CWO) ? (m - rank * CWO + C * CWO - 1) / (C * CWO) : 0;
-    for (int k0 = 0; k0 < np; k0 += NB) {
+    for (int k0 = 0, cur = 0; k0 < np; k0 += NB, cur ^= 1) {
         const int kb = min(NB, np - k0), mp = m - k0, ctrail = k0 + kb;
         const int ldp = (mp + 3) & ~3;          // panel leading dimension, multiple of 4 so that tiles load as 2 x 16 B
-        // (a) panel rows into registers
-        double a[RMAX][NB];
+        const double (*D)[NB + 1] = s_D[cur];
+        const double *rd = s_rd[cur];
+        if (!worker) {
+            // ================= look-ahead warp: diagonal block of the NEXT panel =================
+            const int k1 = k0 + NB;
+            const bool more = k1 < np;                       // (then kb == NB)
+            const int kb2 = more ? min(NB, np - k1) : 0;
+            double r[NB];                                    // row `lane` of A22, then of its factors
+            if (more) {
+                double u[NB], a21[NB];
+                // lane = column j of A12 (16 rows of the current pivot block), lane = row i of A21 and A22
 #pragma unroll
-        for (int q = 0; q < RMAX; ++q) {
-            const int i = tid + q * TF;
-#pragma unroll
-            for (int jj = 0; jj < NB; ++jj)
-                a[q][jj] = (i < mp && jj < kb) ? __ldcg(F + (k0 + i) + (size_t)(k0 + jj) * m) : 0.0;
-        }
-        // (a') the few threads that will solve U12 (phase d) fetch their first column now: the loads are in flight
-        // while warp 0 factors the diagonal block
-        const int idx0 = TF - 1 - tid;
-        double u0[NB];
-        bool u0_valid = false;
-        if (idx0 < nown * CWO) {
-            const int c = (rank + (idx0 / CWO) * C) * CWO + (idx0 % CWO);
-            if (c >= ctrail && c < m) {
-                u0_valid = true;
-                const double *colp = F + (size_t)c * m + k0;
-#pragma unroll
-                for (int t = 0; t < NB; ++t) u0[t] = t < kb ? __ldcg(colp + t) : 0.0;
-            }
-        }
-        if (prof) { __syncthreads(); MF_TICK(acc_load); }
-        // (b) diagonal block inside warp 0: lane i holds row i.  The dependent chain per step is
-        // pivot -> reciprocal -> multiplier -> update of the NEXT pivot, so the next pivot column is updated first
-        // and its reciprocal is started before the remaining columns of the step are touched.
-        if (tid < 32) {
-            double r[NB];
-#pragma unroll
-            for (int jj = 0; jj < NB; ++jj) r[jj] = (tid < kb) ? a[0][jj] : ((jj == tid) ? 1.0 : 0.0);   // pad with identity
-            // The pivot row travels through shared memory (lane j stores it once, everybody reads it back as
-            // broadcasts) - 16 x 64-bit shuffles per step cost more issue slots than the whole rest of the step.
-            double rinv = fast_rcp(__shfl_sync(0xffffffffu, r[0], 0));
-#pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                double *prow = s_prow[j & 1];
-                if (tid == j) {
-                    s_rd[j] = rinv;
-                    if (j < kb && !(fabs(rinv) < 1e280)) atomicExch(info, s + 1);
-#pragma unroll
-                    for (int jj = 0; jj < NB; jj += 2)
-                        if (jj + 1 > j) *reinterpret_cast<double2 *>(prow + jj) = make_double2(r[jj], r[jj + 1]);
-                }
-                __syncwarp();
-                const bool below = tid > j;
-                const double l = r[j] * rinv;
-                if (below) r[j] = l;
-                double rnext = 0.0;
-                if (j + 1 < NB) {
-                    const double u1 = prow[j + 1];
-                    if (below) r[j + 1] = fma(-l, u1, r[j + 1]);
-                    rnext = fast_rcp(__shfl_sync(0xffffffffu, r[j + 1], j + 1));
-                }
+                for (int t = 0; t < NB; ++t) u[t] = (lane < kb2) ? __ldcg(F + (k0 + t) + (size_t)(k1 + lane) * m) : 0.0;
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) {
-                    if (jj > j + 1) {
-                        const double u = prow[jj];
-                        if (below) r[jj] = fma(-l, u, r[jj]);
-                    }
+                    a21[jj] = (lane < kb2) ? __ldcg(F + (k1 + lane) + (size_t)(k0 + jj) * m) : 0.0;
+                    r[jj] = (lane < kb2 && jj < kb2) ? __ldcg(F + (k1 + lane) + (size_t)(k1 + jj) * m) : 0.0;
                 }
-                rinv = rnext;
-            }
-            if (tid < NB) {
+                // U12' = L11^{-1} A12 (phase d arithmetic), staged in shared memory
 #pragma unroll
-                for (int jj = 0; jj < NB; ++jj) s_D[tid][jj] = r[jj];
-            }
-            if (tid < kb) {
+                for (int t = 0; t < NB; ++t) {
 #pragma unroll
-                for (int jj = 0; jj < NB; ++jj) a[0][jj] = r[jj];
-            }
-        }
-        __syncthreads();
-        MF_TICK(acc_diag);
-        // (d) U12 = L11^{-1} F12 for the own trailing columns.  Runs on the highest thread ids, whose panel rows (phase
-        // c below) mostly do not exist (m < TF), so this serial 16-step substitution overlaps phase (c) of the others.
-        for (int idx = idx0; idx < nown * CWO; idx += TF) {
-            const int c = (rank + (idx / CWO) * C) * CWO + (idx % CWO);
-            if (c >= ctrail && c < m) {
-                double *colp = F + (size_t)c * m + k0;
-                double u[NB];
-                if (idx == idx0 && u0_valid) {
+                    for (int tt = 0; tt < NB; ++tt)
+                        if (tt > t) u[tt] = fma(-D[tt][t], u[t], u[tt]);
+                }
+                if (lane < NB) {
 #pragma unroll
-                    for (int t = 0; t < NB; ++t) u[t] = u0[t];
-                } else {
+                    for (int t = 0; t < NB; ++t) s_T[t][lane] = u[t];
+                }
+                // L21' = A21 U11^{-1} (phase c arithmetic)
+#pragma unroll
+                for (int t = 0; t < NB; ++t) {
+                    const double l = a21[t] * rd[t];
+                    a21[t] = l;
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj)
+                        if (jj > t) a21[jj] = fma(-l, D[t][jj], a21[jj]);
+                }
+                __syncwarp();
+                // A22 - L21' U12' (phase e arithmetic: accumulate over t, subtract once)
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) acc = fma(a21[t], s_T[t][jj], acc);
+                    r[jj] = r[jj] - acc;
+                }
+                // identity padding of a partial last block
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj)
+                    if (lane >= kb2 || jj >= kb2) r[jj] = (jj == lane) ? 1.0 : 0.0;
+            }
+            // every value read from the front is consumed above: its loads have completed
+            cluster_arrive();
+            if (more) {
+                diag16_factor(r, lane, kb2, s_prow, s_rd[cur ^ 1], info, s);
+                if (lane < NB) {
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) s_D[cur ^ 1][lane][jj] = r[jj];
+                }
+            }
+            cluster_wait();
+        } else {
+            // ================= workers: panel k =================
+            cluster_arrive();
+            // (a) panel rows into registers
+            double a[RMAX][NB];
+#pragma unroll
+            for (int q = 0; q < RMAX; ++q) {
+                const int i = tid + q * TW;
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj)
+                    a[q][jj] = (i < mp && jj < kb) ? __ldcg(F + (k0 + i) + (size_t)(k0 + jj) * m) : 0.0;
+            }
+            if (prof) { worker_sync<TW>(); MF_TICK(acc_load); }
+            // (d) U12 = L11^{-1} F12 for the own trailing columns.  Runs on the highest worker ids, whose panel rows
+            // (phase c) mostly do not exist (m < TW), so this serial 16-step substitution overlaps phase (c).
+            for (int idx = TW - 1 - tid; idx < nown * CWO; idx += TW) {
+                const int c = (rank + (idx / CWO) * C) * CWO + (idx % CWO);
+                if (c >= ctrail && c < m) {
+                    const double *colp = F + (size_t)c * m + k0;
+                    double u[NB];
 #pragma unroll
                     for (int t = 0; t < NB; ++t) u[t] = t < kb ? __ldcg(colp + t) : 0.0;
-                }
-#pragma unroll
-                for (int t = 0; t < NB; ++t) {
-                    if (t < kb) {
-#pragma unroll
-                        for (int tt = 0; tt < NB; ++tt)
-                            if (tt > t && tt < kb) u[tt] = fma(-s_D[tt][t], u[t], u[tt]);
-                    }
-                }
-#pragma unroll
-                for (int t = 0; t < NB; ++t) {
-                    if (t < kb) __stcg(colp + t, u[t]);
-                    Uc[t * ldu + idx] = u[t];
-                }
-            }
-        }
-        if (prof) { __syncthreads(); MF_TICK(acc_trsm); }
-        // (c) rows below the block: L = A U11^{-1}; every row goes to the shared panel, CTA 0 also writes the factor
-#pragma unroll
-        for (int q = 0; q < RMAX; ++q) {
-            const int i = tid + q * TF;
-            if (i < mp) {
-                if (i >= kb) {
 #pragma unroll
                     for (int t = 0; t < NB; ++t) {
                         if (t < kb) {
-                            const double l = a[q][t] * s_rd[t];
-                            a[q][t] = l;
 #pragma unroll
-                            for (int jj = 0; jj < NB; ++jj)
-                                if (jj > t && jj < kb) a[q][jj] = fma(-l, s_D[t][jj], a[q][jj]);
+                            for (int tt = 0; tt < NB; ++tt)
+                                if (tt > t && tt < kb) u[tt] = fma(-D[tt][t], u[t], u[tt]);
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) Uc[t * ldu + idx] = u[t];
+                }
+            }
+            if (prof) { worker_sync<TW>(); MF_TICK(acc_trsm); }
+            // (c) rows below the block: L = A U11^{-1}; every row goes to the shared panel
+#pragma unroll
+            for (int q = 0; q < RMAX; ++q) {
+                const int i = tid + q * TW;
+                if (i < mp) {
+                    if (i >= kb) {
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) {
+                            if (t < kb) {
+                                const double l = a[q][t] * rd[t];
+                                a[q][t] = l;
+#pragma unroll
+                                for (int jj = 0; jj < NB; ++jj)
+                                    if (jj > t && jj < kb) a[q][jj] = fma(-l, D[t][jj], a[q][jj]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < NB; ++jj) a[q][jj] = D[i][jj];     // the factored block itself
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj)
+                        if (jj < kb) P[i + jj * ldp] = a[q][jj];
+                }
+            }
+            worker_sync<TW>();
+            MF_TICK(acc_panel);
+            // every look-ahead warp of the cluster holds its corner: the front may be written now
+            cluster_wait();
+            if (rank == 0) {
+#pragma unroll
+                for (int q = 0; q < RMAX; ++q) {
+                    const int i = tid + q * TW;
+                    if (i < mp) {
+#pragma unroll
+                        for (int jj = 0; jj < NB; ++jj)
+                            if (jj < kb) __stcg(F + (k0 + i) + (size_t)(k0 + jj) * m, a[q][jj]);
+                    }
+                }
+            }
+            for (int idx = TW - 1 - tid; idx < nown * CWO; idx += TW) {
+                const int c = (rank + (idx / CWO) * C) * CWO + (idx % CWO);
+                if (c >= ctrail && c < m) {
+                    double *colp = F + (size_t)c * m + k0;
+#pragma unroll
+                    for (int t = 0; t < NB; ++t)
+                        if (t < kb) __stcg(colp + t, Uc[t * ldu + idx]);
+                }
+            }
+            // (e) trailing update of the own columns, 4x4 register tiles
+            const int nrow = m - ctrail;
+            if (nrow > 0 && nown > 0) {
+                // first own chunk that still has trailing columns
+                int q0 = 0;
+                while (q0 < nown && (rank + q0 * C) * CWO + CWO <= ctrail) ++q0;
+                const int rbase = kb & ~3;                   // tile origin aligned to 4 rows (kb < 16 only in a front's last panel)
+                const int tr = (mp - rbase + 3) >> 2, tc = (nown - q0) * (CWO / 4);
+                for (int tile = tid; tile < tr * tc; tile += TW) {
+                    const int ti = tile % tr, tj = tile / tr;
+                    const int i0 = rbase + 4 * ti, idx0 = q0 * CWO + 4 * tj;
+                    const int c0 = (rank + (idx0 / CWO) * C) * CWO + (idx0 % CWO);
+                    double f[4][4], acc[4][4];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const double *colp = F + (size_t)(c0 + b) * m + k0;
+                        const bool cv = c0 + b >= ctrail && c0 + b < m;
+#pragma unroll
+                        for (int aa = 0; aa < 4; ++aa) {
+                            f[aa][b] = (cv && i0 + aa >= kb && i0 + aa < mp) ? __ldcg(colp + i0 + aa) : 0.0;
+                            acc[aa][b] = 0.0;
+                        }
+                    }
+                    for (int t = 0; t < kb; ++t) {
+                        // i0 and ldp are multiples of 4: two conflict-free 16-byte shared loads per operand (rows
+                        // beyond mp hold stale data whose results are never stored)
+                        const double2 la = *reinterpret_cast<const double2 *>(P + i0 + t * ldp);
+                        const double2 lb = *reinterpret_cast<const double2 *>(P + i0 + t * ldp + 2);
+                        const double2 ua = *reinterpret_cast<const double2 *>(Uc + t * ldu + idx0);
+                        const double2 ub = *reinterpret_cast<const double2 *>(Uc + t * ldu + idx0 + 2);
+                        const double l[4] = {la.x, la.y, lb.x, lb.y}, uu[4] = {ua.x, ua.y, ub.x, ub.y};
+#pragma unroll
+                        for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) acc[aa][b] = fma(l[aa], uu[b], acc[aa][b]);
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        if (c0 + b >= ctrail && c0 + b < m) {
+                            double *colp = F + (size_t)(c0 + b) * m + k0;
+#pragma unroll
+                            for (int aa = 0; aa < 4; ++aa)
+                                if (i0 + aa >= kb && i0 + aa < mp) __stcg(colp + i0 + aa, f[aa][b] - acc[aa][b]);
                         }
                     }
                 }
-#pragma unroll
-                for (int jj = 0; jj < NB; ++jj) {
-                    if (jj < kb) {
-                        P[i + jj * ldp] = a[q][jj];
-                        if (rank == 0) __stcg(F + (k0 + i) + (size_t)(k0 + jj) * m, a[q][jj]);
-                    }
-                }
             }
+            MF_TICK(acc_trail);
         }
-        __syncthreads();
-        MF_TICK(acc_panel);
-        // (e) trailing update of the own columns, 4x4 register tiles
-        const int nrow = m - ctrail;
-        if (nrow > 0 && nown > 0) {
-            // first own chunk that still has trailing columns
-            int q0 = 0;
-            while (q0 < nown && (rank + q0 * C) * CWO + CWO <= ctrail) ++q0;
-            const int rbase = kb & ~3;                       // tile origin aligned to 4 rows (kb < 16 only in a front's last panel)
-            const int tr = (mp - rbase + 3) >> 2, tc = (nown - q0) * (CWO / 4);
-            for (int tile = tid; tile < tr * tc; tile += TF) {
-                const int ti = tile % tr, tj = tile / tr;
-                const int i0 = rbase + 4 * ti, idx0 = q0 * CWO + 4 * tj;
-                const int c0 = (rank + (idx0 / CWO) * C) * CWO + (idx0 % CWO);
-                double f[4][4], acc[4][4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const double *colp = F + (size_t)(c0 + b) * m + k0;
-                    const bool cv = c0 + b >= ctrail && c0 + b < m;
-#pragma unroll
-                    for (int aa = 0; aa < 4; ++aa) {
-                        f[aa][b] = (cv && i0 + aa >= kb && i0 + aa < mp) ? __ldcg(colp + i0 + aa) : 0.0;
-                        acc[aa][b] = 0.0;
-                    }
-                }
-                for (int t = 0; t < kb; ++t) {
-                    // i0 and ldp are multiples of 4: two conflict-free 16-byte shared loads per operand (rows beyond
-                    // mp hold stale data whose results are never stored)
-                    const double2 la = *reinterpret_cast<const double2 *>(P + i0 + t * ldp);
-                    const double2 lb = *reinterpret_cast<const double2 *>(P + i0 + t * ldp + 2);
-                    const double2 ua = *reinterpret_cast<const double2 *>(Uc + t * ldu + idx0);
-                    const double2 ub = *reinterpret_cast<const double2 *>(Uc + t * ldu + idx0 + 2);
-                    const double l[4] = {la.x, la.y, lb.x, lb.y}, uu[4] = {ua.x, ua.y, ub.x, ub.y};
-#pragma unroll
-                    for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[aa][b] = fma(l[aa], uu[b], acc[aa][b]);
-                }
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    if (c0 + b >= ctrail && c0 + b < m) {
-                        double *colp = F + (size_t)(c0 + b) * m + k0;
-#pragma unroll
-                        for (int aa = 0; aa < 4; ++aa)
-                            if (i0 + aa >= kb && i0 + aa < mp) __stcg(colp + i0 + aa, f[aa][b] - acc[aa][b]);
-                    }
-                }
-            }
-        }
-        MF_TICK(acc_trail);
-        cl.sync();
+        cl.sync();      // publishes the updated trailing matrix (cluster) and the next diagonal block (this CTA)
         MF_TICK(acc_sync);
     }
     if (prof && tid == 0) {
@@ -1028,12 +1114,16 @@ mf_backward_big_kernel(MFDev d, const int *__restrict__ nodes, double *__restric
 }
 
 // kernel variants: <threads, panel rows per thread>
-enum { kVarSmall = 0, kVarMid = 1, kVarBig = 2 };
-inline int factor_variant(int max_m) { return max_m <= 256 ? kVarSmall : (max_m <= 512 ? kVarMid : kVarBig); }
-inline int variant_threads(int v) { return v == kVarSmall ? 256 : 512; }
+// kernel variants: <threads, panel rows per thread>; one warp of every CTA is the look-ahead warp, the others take one
+// or two panel rows each.  The thread counts keep the register budget per thread above what the kernel needs
+// (65536 / 288 = 227, / 416 = 157) - at 512 threads (128 registers) it spills.
+enum { kVar288 = 0, kVar416 = 1, kVar512 = 2, kVar512x2 = 3, kNumVariants = 4 };
+inline int factor_variant(int max_m) { return max_m <= 256 ? kVar288 : (max_m <= 384 ? kVar416 : (max_m <= 480 ? kVar512 : kVar512x2)); }
+inline int variant_threads(int v) { return v == kVar288 ? 288 : (v == kVar416 ? 416 : 512); }
 typedef void (*FactorKernel)(MFDev, const int *, int, int *, long long *);
 inline FactorKernel factor_kernel(int v) {
-    return v == kVarSmall ? mf_factor_kernel<256, 1> : (v == kVarMid ? mf_factor_kernel<512, 1> : mf_factor_kernel<512, 2>);
+    return v == kVar288 ? mf_factor_kernel<288, 1>
+                        : (v == kVar416 ? mf_factor_kernel<416, 1> : (v == kVar512 ? mf_factor_kernel<512, 1> : mf_factor_kernel<512, 2>));
 }
 
 template <class T>
@@ -1190,7 +1280,7 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_kernel<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_kernel<1, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_kernel<2, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    for (int v = 0; v < 3 && e == cudaSuccess; ++v) {
+    for (int v = 0; v < kNumVariants && e == cudaSuccess; ++v) {
         e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     }
