@@ -450,9 +450,27 @@ constexpr int TS = 512;    // threads per CTA in the solve kernels
 
 // element (i, c) of the triangular factor a sweep works with: the stored factor, or its transpose (TR) for solves
 // with A^T = U^T L^T (the adjoint system reuses the factors of the last Newton matrix that way)
-#define MF_E(i, c) (TR ? __ldcg(F + (c) + (size_t)(i) * m) : __ldcg(F + (i) + (size_t)(c) * m))
+#define MF_E(i, c) (TR ? __ldg(F + (c) + (size_t)(i) * m) : __ldg(F + (i) + (size_t)(c) * m))
 #define MF_DI(row, col) (TR ? (col) * NB + (row) : (row) * NB + (col))
 
+
+
+// The factors are read-only during a solve, so they may live in L1: the whole panel a sweep will walk in dependent
+// 16-column steps is requested up front (one prefetch per 128-byte line), and the per-block loads then hit L1 instead
+// of paying an L2 round trip on the serial path.  cols: the first np columns (L panel), else the first np rows (U panel).
+__device__ __forceinline__ void mf_prefetch_l1(const double *F, int m, int np, bool cols, int tid, int nthreads) {
+    if (cols) {
+        const size_t n = (size_t)np * m;
+        for (size_t off = (size_t)tid * 16; off < n; off += (size_t)nthreads * 16)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(F + off));
+    } else {
+        const int nch = (np + 15) >> 4;
+        for (int e = tid; e < m * nch; e += nthreads) {
+            const int j = e / nch, r = (e - j * nch) << 4;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(F + (size_t)j * m + r));
+        }
+    }
+}
 
 // forward: y_P = L11^{-1} b_P,  b_U -= L21 y_P      (RS = rows per thread: 1 for fronts <= 512, 2 up to 1024)
 // TR: the same sweep with U^T in place of L:  y_P = U11^{-T} b_P,  b_U -= U12^T y_P
@@ -468,6 +486,9 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
     const double *F = d.F + d.front_ptr[s];
     const int *I = d.idx + d.idx_ptr[s];
     const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + (TR ? NB * NB : 0);
+    mf_prefetch_l1(F, m, np, !TR, tid, TS);
+    for (int off = tid * 16; off < ((np + NB - 1) / NB) * 2 * NB * NB; off += TS * 16)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + off));
     for (int r = 0; r < NR; ++r)
         for (int k = tid; k < m; k += TS) y[r * m + k] = k < np ? x[(size_t)r * ldx + I[k]] : 0.0;
     double lc[RS][NB], ln[RS][NB];
@@ -479,7 +500,7 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
     }
     double dl[NB];
 #pragma unroll
-    for (int t = 0; t < NB; ++t) dl[t] = (tid < NB) ? __ldcg(Dinv + MF_DI(tid, t)) : 0.0;
+    for (int t = 0; t < NB; ++t) dl[t] = (tid < NB) ? __ldg(Dinv + MF_DI(tid, t)) : 0.0;
     __syncthreads();
     const int nblk = (np + NB - 1) / NB;
     for (int b = 0; b < nblk; ++b) {
@@ -513,7 +534,7 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
             }
             if (b + 1 < nblk) {
 #pragma unroll
-                for (int t = 0; t < NB; ++t) dl[t] = __ldcg(Dinv + (size_t)(b + 1) * (2 * NB * NB) + MF_DI(tid, t));
+                for (int t = 0; t < NB; ++t) dl[t] = __ldg(Dinv + (size_t)(b + 1) * (2 * NB * NB) + MF_DI(tid, t));
             }
         }
         __syncthreads();
@@ -554,6 +575,9 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
     const double *F = d.F + d.front_ptr[s];
     const int *I = d.idx + d.idx_ptr[s];
     const double *Dinv = d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + (TR ? 0 : NB * NB);
+    mf_prefetch_l1(F, m, np, TR, tid, TS);
+    for (int off = tid * 16; off < ((np + NB - 1) / NB) * 2 * NB * NB; off += TS * 16)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + off));
     for (int r = 0; r < NR; ++r)
         for (int k = tid; k < m; k += TS) y[r * m + k] = x[(size_t)r * ldx + I[k]];
     const int nblk = (np + NB - 1) / NB;
@@ -569,7 +593,7 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
     }
     double du[NB];
 #pragma unroll
-    for (int t = 0; t < NB; ++t) du[t] = (tid < NB) ? __ldcg(Dinv + (size_t)(nblk - 1) * (2 * NB * NB) + MF_DI(tid, t)) : 0.0;
+    for (int t = 0; t < NB; ++t) du[t] = (tid < NB) ? __ldg(Dinv + (size_t)(nblk - 1) * (2 * NB * NB) + MF_DI(tid, t)) : 0.0;
     __syncthreads();
     // y_P -= U12 x_U (TR: L21^T x_U): all 16 warps share the (np x nu) mat-vec so that no thread walks a long
     // dependent chain of L2 loads.  Plain: warp w takes the columns j = np + w, np + w + 16, ... with its lanes over
@@ -586,7 +610,7 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
                 for (int r = 0; r < NR; ++r) a[r] = 0.0;
                 if (k < np) {
                     for (int j = np + wid; j < m; j += NW) {
-                        const double e = __ldcg(F + k + (size_t)j * m);
+                        const double e = __ldg(F + k + (size_t)j * m);
 #pragma unroll
                         for (int r = 0; r < NR; ++r) a[r] = fma(e, y[r * m + j], a[r]);
                     }
@@ -608,7 +632,7 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
 #pragma unroll
                 for (int r = 0; r < NR; ++r) a[r] = 0.0;
                 for (int j = np + lane; j < m; j += 32) {
-                    const double e = __ldcg(F + j + (size_t)k * m);
+                    const double e = __ldg(F + j + (size_t)k * m);
 #pragma unroll
                     for (int r = 0; r < NR; ++r) a[r] = fma(e, y[r * m + j], a[r]);
                 }
@@ -651,7 +675,7 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
             }
             if (b > 0) {
 #pragma unroll
-                for (int t = 0; t < NB; ++t) du[t] = __ldcg(Dinv + (size_t)(b - 1) * (2 * NB * NB) + MF_DI(tid, t));
+                for (int t = 0; t < NB; ++t) du[t] = __ldg(Dinv + (size_t)(b - 1) * (2 * NB * NB) + MF_DI(tid, t));
             }
         }
         __syncthreads();
