@@ -705,15 +705,16 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Large fronts (m > kBigM: the top of the tree on refined meshes, cfg5).  A front no longer fits a cluster's shared
-// memory, so a GROUP of G co-resident CTAs (cooperative launch, G = #SMs / #large fronts of the level) works on it
+// memory, so a GROUP of G co-resident CTAs (cooperative launch; the SMs are shared out among the level's large fronts in
+// proportion to their flops) works on it
 // out of L2 / HBM with a right-looking blocked LU, panel width 32, static pivoting as above:
-//   phase A  every CTA factors the 32 x 32 diagonal block redundantly (warp 0, shuffles) and turns its share of the
+//   phase A  every CTA factors the 32 x 32 diagonal block redundantly (warp 0, pivot row via shared memory) and turns its share of the
 //            rows below it into L = A U11^{-1} (one row per thread, in registers)
 //   -- group barrier --
 //   phase B  the CTA owning a column (4-column blocks, cyclic over the group) solves U12 for it and applies the
 //            rank-32 update to it: U12 of the own columns sits in shared memory, every thread keeps the L rows of
-//            two matrix rows in registers (2 x 32) and streams along them through the own columns, four at a time -
-//            C in, 256 DFMAs, C out - with the next four columns' C values already in flight.  Lanes are
+//            two matrix rows in registers (2 x 32) and streams along them through the own columns, eight at a time -
+//            C in, 512 DFMAs in 16 independent chains, C out - with the next eight columns' C values in flight.  Lanes are
 //            consecutive rows, so every global access of a warp is 256 contiguous bytes and U is a broadcast.
 //   -- group barrier --
 // Column ownership is static, so a column is only ever read and written by its owner between barriers.
