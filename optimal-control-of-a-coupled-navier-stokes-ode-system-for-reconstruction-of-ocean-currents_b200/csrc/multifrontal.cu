@@ -179,8 +179,9 @@ __device__ __forceinline__ void diag16_factor(double (&r)[NB], int lane, int kb,
 // L21' = A21 U11^{-1} and A22 - L21' U12' with exactly the arithmetic of phases (d), (c), (e) below (so the result is
 // bit-identical to what the trailing update stores) and factors it.  The serial 16-step elimination - the longest
 // single-warp section of a panel - is thereby off the critical path.  All global stores of a panel are issued after
-// a split-phase cluster barrier whose arrival the look-ahead warps signal once they hold their corner in registers,
-// so no CTA can overwrite an entry another CTA's look-ahead warp still has to read.
+// the wait (acquire) of a split-phase cluster barrier; the look-ahead warps arrive (release) once they hold their
+// corner in registers and the workers once their panel loads are issued, so no CTA can overwrite an entry another
+// CTA still has to read.
 template <int TF, int RMAX>
 __global__ void __launch_bounds__(TF, 1)
 mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, long long *prof) {
@@ -300,7 +301,6 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
             cluster_wait();
         } else {
             // ================= workers: panel k =================
-            cluster_arrive();
             // (a) panel rows into registers
             double a[RMAX][NB];
 #pragma unroll
@@ -310,6 +310,9 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
                 for (int jj = 0; jj < NB; ++jj)
                     a[q][jj] = (i < mp && jj < kb) ? __ldcg(F + (k0 + i) + (size_t)(k0 + jj) * m) : 0.0;
             }
+            // arrive with release semantics AFTER the panel loads: CTA 0's store of the L panel into these very entries
+            // comes after its wait (acquire) below, hence after every worker's loads above
+            cluster_arrive();
             if (prof) { worker_sync<TW>(); MF_TICK(acc_load); }
             // (d) U12 = L11^{-1} F12 for the own trailing columns.  Runs on the highest worker ids, whose panel rows
             // (phase c) mostly do not exist (m < TW), so this serial 16-step substitution overlaps phase (c).
