@@ -494,12 +494,16 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
         asm volatile("prefetch.global.L1 [%0];" ::"l"(d.dinv + (size_t)d.dinv_ptr[s] * (2 * NB * NB) + off));
     for (int r = 0; r < NR; ++r)
         for (int k = tid; k < m; k += TS) y[r * m + k] = k < np ? x[(size_t)r * ldx + I[k]] : 0.0;
+    // warps whose rows all lie beyond the front skip the per-block row work (they still meet the barriers): with 512
+    // threads and fronts of order ~100-380 that is most warps, and their predicated address arithmetic was a fifth
+    // of the issue slots of a block step
+    const bool live = (tid & ~31) < m;
     double lc[RS][NB], ln[RS][NB];
 #pragma unroll
     for (int q = 0; q < RS; ++q) {
         const int i = tid + q * TS;
 #pragma unroll
-        for (int t = 0; t < NB; ++t) lc[q][t] = (i < m && i >= min(NB, np) && t < np) ? MF_E(i, t) : 0.0;
+        for (int t = 0; t < NB; ++t) lc[q][t] = (live && i < m && i >= min(NB, np) && t < np) ? MF_E(i, t) : 0.0;
     }
     double dl[NB];
 #pragma unroll
@@ -509,7 +513,7 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
     for (int b = 0; b < nblk; ++b) {
         const int k0 = b * NB, kb = min(NB, np - k0), k1 = k0 + NB;
         // prefetch the next block's columns / inverse (rows below the next block; its last block may be partial)
-        if (b + 1 < nblk) {
+        if (live && b + 1 < nblk) {
             const int rnext = k1 + min(NB, np - k1);
 #pragma unroll
             for (int q = 0; q < RS; ++q) {
@@ -541,24 +545,28 @@ mf_forward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x
             }
         }
         __syncthreads();
+        if (live) {
 #pragma unroll
-        for (int q = 0; q < RS; ++q) {
-            const int i = tid + q * TS;
-            if (i < m && i >= k0 + kb) {
+            for (int q = 0; q < RS; ++q) {
+                const int i = tid + q * TS;
+                if (i < m && i >= k0 + kb) {
 #pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    double acc = 0.0;
+                    for (int r = 0; r < NR; ++r) {
+                        double acc = 0.0;
 #pragma unroll
-                    for (int t = 0; t < NB; ++t) acc = fma(lc[q][t], (t < kb) ? yb[r][t] : 0.0, acc);
-                    y[r * m + i] -= acc;
+                        for (int t = 0; t < NB; ++t) acc = fma(lc[q][t], (t < kb) ? yb[r][t] : 0.0, acc);
+                        y[r * m + i] -= acc;
+                    }
                 }
             }
         }
         __syncthreads();
+        if (live) {
 #pragma unroll
-        for (int q = 0; q < RS; ++q)
+            for (int q = 0; q < RS; ++q)
 #pragma unroll
-            for (int t = 0; t < NB; ++t) lc[q][t] = ln[q][t];
+                for (int t = 0; t < NB; ++t) lc[q][t] = ln[q][t];
+        }
     }
     for (int r = 0; r < NR; ++r) {
         for (int k = tid; k < np; k += TS) x[(size_t)r * ldx + I[k]] = y[r * m + k];
@@ -651,7 +659,8 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
     __syncthreads();
     for (int b = nblk - 1; b >= 0; --b) {
         const int k0 = b * NB, kb = min(NB, np - k0);
-        if (b > 0) {
+        const bool live = (tid & ~31) < k0;       // rows above the block only: dead warps just meet the barriers
+        if (live && b > 0) {
             const int kp = k0 - NB;
 #pragma unroll
             for (int q = 0; q < RS; ++q) {
@@ -682,24 +691,28 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
             }
         }
         __syncthreads();
+        if (live) {
 #pragma unroll
-        for (int q = 0; q < RS; ++q) {
-            const int i = tid + q * TS;
-            if (i < k0) {
+            for (int q = 0; q < RS; ++q) {
+                const int i = tid + q * TS;
+                if (i < k0) {
 #pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    double acc = 0.0;
+                    for (int r = 0; r < NR; ++r) {
+                        double acc = 0.0;
 #pragma unroll
-                    for (int t = 0; t < NB; ++t) acc = fma(uc[q][t], (t < kb) ? yb[r][t] : 0.0, acc);
-                    y[r * m + i] -= acc;
+                        for (int t = 0; t < NB; ++t) acc = fma(uc[q][t], (t < kb) ? yb[r][t] : 0.0, acc);
+                        y[r * m + i] -= acc;
+                    }
                 }
             }
         }
         __syncthreads();
+        if (live) {
 #pragma unroll
-        for (int q = 0; q < RS; ++q)
+            for (int q = 0; q < RS; ++q)
 #pragma unroll
-            for (int t = 0; t < NB; ++t) uc[q][t] = un[q][t];
+                for (int t = 0; t < NB; ++t) uc[q][t] = un[q][t];
+        }
     }
     for (int r = 0; r < NR; ++r)
         for (int k = tid; k < np; k += TS) x[(size_t)r * ldx + I[k]] = y[r * m + k];
