@@ -125,3 +125,14 @@ def test_multifrontal_analysis_solves_forward_and_adjoint_matrices(lib, which):
             x, st = capi.host_mf_probe(V.csr_rowptr, V.csr_col, vals, xy, kind, b, pivot_window=window)
             assert np.abs(A @ x - b).max() / np.abs(b).max() < 1e-11
             assert st["min_pivot"] > 1e-6 and st["levels"] <= 16
+
+
+def test_scripts_parse():
+    """bench.py, the graft entry and every tool compile (they only run on the GPU box)."""
+    import ast
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + glob.glob(os.path.join(root, "tools", "*.py"))
+    assert len(files) >= 6
+    for f in files:
+        ast.parse(open(f).read(), filename=f)
