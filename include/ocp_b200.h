@@ -39,6 +39,7 @@ extern "C" {
 #define OCP_ERR_SOLVER (-3)
 #define OCP_ERR_NOT_CONVERGED (-4)
 #define OCP_ERR_NO_DEVICE (-5)
+#define OCP_ERR_COMM (-6)
 
 typedef struct ocp_ctx ocp_ctx;
 
@@ -181,6 +182,24 @@ int ocp_set_observations_host(ocp_ctx *ctx, const double *h_x0, const double *h_
  * h_z (ndofs), h_mask (K), h_scalars[0..3] = misfit, int_G1 |f|^2, n_masked, newton iterations. */
 int ocp_gradient_host(ocp_ctx *ctx, const double *h_f, double *h_w, double *h_z, double *h_mask,
                       double *h_scalars);
+
+/* ---- multi-GPU: buoys sharded over the GPUs of one box -------------------------------------------
+ * The reference is serial; its sum over buoys (the PointSource loop OCP_dolfin.py:353-366 and partA of J,
+ * OCP_dolfin.py:259) is what gets partitioned: every rank holds a shard of the buoys and a replica of mesh, state and
+ * factorisation, and the accumulator [b | misfit | n_masked] is summed across ranks by ONE NCCL all-reduce (fp64)
+ * per gradient evaluation, on the context's stream.  Set-up: rank 0 calls ocp_comm_get_unique_id, the host ships the
+ * OCP_COMM_ID_BYTES bytes to the other ranks (MPI, a file, torch.distributed ...), every rank calls ocp_comm_init
+ * (collective, blocks until all ranks joined).  libnccl.so.2 is resolved with dlopen at the first call
+ * (environment OCP_NCCL_LIB overrides the name); without it these calls return OCP_ERR_COMM.
+ * With a communicator, ocp_gradient_host all-reduces the accumulator between the backward sweep and the adjoint
+ * solve, so every rank returns the gradient of the WHOLE buoy set; h_scalars[0,2] are then global sums. */
+#define OCP_COMM_ID_BYTES 128
+int ocp_comm_get_unique_id(void *id128);
+int ocp_comm_init(ocp_ctx *ctx, int nranks, int rank, const void *id128);
+int ocp_comm_size(const ocp_ctx *ctx);          /* 1 without a communicator */
+int ocp_comm_nccl_version(void);                /* e.g. 22809; 0 when NCCL cannot be loaded */
+/* in-place sum over the ranks of d_buf[0..n) (device, fp64) on the context's stream; no-op for a single rank */
+int ocp_allreduce(ocp_ctx *ctx, double *d_buf, size_t n);
 
 /* Number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 long long ocp_launch_count(void);

@@ -16,9 +16,9 @@ LIB_PATH = os.path.join(_HERE, "libocp_b200.so")
 
 OCP_OK = 0
 ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "sparse solver error", -4: "Newton did not converge",
-          -5: "no CUDA device"}
+          -5: "no CUDA device", -6: "NCCL communicator error"}
 
-# every symbol include/ocp_b200.h declares (tests/test_capi_symbols.py checks the header against this list)
+# every symbol include/ocp_b200.h declares (tests/test_capi_cpu.py checks the header against this list)
 SYMBOLS = [
     "ocp_version", "ocp_device_available", "ocp_create", "ocp_destroy", "ocp_last_error",
     "ocp_get_solver_stats", "ocp_reset_solver_stats", "ocp_set_viscosity", "ocp_set_profiling", "ocp_set_dirichlet",
@@ -27,6 +27,7 @@ SYMBOLS = [
     "ocp_adjoint_solve", "ocp_boundary_inner", "ocp_nodal_axpby", "ocp_field_norms", "ocp_traj_transpose",
     "ocp_solve_primal_ode_host", "ocp_solve_adjoint_ode_host", "ocp_set_observations_host", "ocp_gradient_host",
     "ocp_launch_count",
+    "ocp_comm_get_unique_id", "ocp_comm_init", "ocp_comm_size", "ocp_comm_nccl_version", "ocp_allreduce",
     "ocp_host_lu_probe", "ocp_host_mf_probe", "ocp_host_mf_set_pivot_window", "ocp_selftest_cell_matrix", "ocp_selftest_facet_matrix",
 ]
 
@@ -81,6 +82,9 @@ def load_library() -> C.CDLL:
         lib.ocp_set_profiling.restype = None
         lib.ocp_selftest_cell_matrix.restype = None
         lib.ocp_selftest_facet_matrix.restype = None
+        lib.ocp_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.ocp_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.ocp_comm_size.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 
@@ -183,6 +187,20 @@ class Context:
     def set_viscosity(self, nu: float):
         self.lib.ocp_set_viscosity(self._h, float(nu))
 
+    # -- multi-GPU exchange (NCCL inside the library) -------------------------------------
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        """Collective: every rank calls it with the 128-byte id rank 0 obtained from ``comm_unique_id()``."""
+        if len(unique_id) != COMM_ID_BYTES:
+            raise OcpError("unique id must be 128 bytes")
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._check(self.lib.ocp_comm_init(self._h, int(nranks), int(rank), buf), "ocp_comm_init")
+
+    def comm_size(self) -> int:
+        return int(self.lib.ocp_comm_size(self._h))
+
+    def allreduce(self, d_buf):
+        self._check(self.lib.ocp_allreduce(self._h, _dp(d_buf), C.c_size_t(d_buf.numel())), "ocp_allreduce")
+
     # -- device entry points ----------------------------------------------------------
     def forward_solve(self, d_f, d_w, zero_init: bool = True):
         its = C.c_int(0)
@@ -268,6 +286,22 @@ class Context:
         self._check(self.lib.ocp_gradient_host(self._h, _hp(f), _hp(w), _hp(z), _hp(mask), _hp(sc)),
                     "ocp_gradient_host")
         return w, z, mask, dict(misfit=sc[0], f_norm2=sc[1], n_masked=int(sc[2]), newton_its=int(sc[3]))
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0); ship the bytes to the other ranks and call Context.comm_init."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = load_library().ocp_comm_get_unique_id(buf)
+    if rc != OCP_OK:
+        raise OcpError(f"ocp_comm_get_unique_id failed ({ERRORS.get(rc, rc)}): is libnccl.so.2 loadable?")
+    return buf.raw
+
+
+def nccl_version() -> int:
+    return int(load_library().ocp_comm_nccl_version())
 
 
 def launch_count() -> int:

@@ -21,16 +21,22 @@ def _collapsed_p2_dofs(V: TaylorHood):
     return np.hstack([2 * cn, 2 * cn + 1]).astype(np.int32)           # (nc, 12) [u_x(6), u_y(6)]
 
 
-def write_control(path_h5: str, V: TaylorHood, f_nodal: np.ndarray, mtime: int = 0) -> str:
-    """``q.xdmf`` / ``q.h5`` with the function named ``f`` (OCP_dolfin.py:440-441, 485-486)."""
+def write_control(path_h5: str, V: TaylorHood, f_nodal: np.ndarray, mtime: int = 0, append: bool = False) -> str:
+    """``q.xdmf`` / ``q.h5`` with the function named ``f`` (OCP_dolfin.py:440-441, 485-486).  ``append=True`` adds a
+    group ``f_k`` per call like the reference's per-iteration ``checkpoints/q.xdmf``; a non-finite control is
+    refused so that a diverged iteration cannot replace the last good resume point."""
     vec = np.ascontiguousarray(f_nodal, np.float64).reshape(-1)         # (nn,2) row-major = interleaved numbering
-    return h5lite.write_checkpoint(path_h5, "f", V.mesh.cells, V.mesh.coords, _collapsed_p2_dofs(V), vec, 12, mtime)
+    if not np.all(np.isfinite(vec)):
+        raise ValueError("write_control: the control holds non-finite values; checkpoint left untouched")
+    return h5lite.write_checkpoint(path_h5, "f", V.mesh.cells, V.mesh.coords, _collapsed_p2_dofs(V), vec, 12, mtime,
+                                   append=append)
 
 
-def read_control(path_h5: str, V: TaylorHood) -> np.ndarray:
+def read_control(path_h5: str, V: TaylorHood, counter: int = -1) -> np.ndarray:
     """Control checkpoint -> P2 nodal field (nn,2), for any dof numbering of the collapsed space (the file carries its
-    own ``cell_dofs``), e.g. reference_runs/u_bar_chapter_6.3.3/q_backup/q.h5."""
-    d = h5lite.read_checkpoint(path_h5, "f")
+    own ``cell_dofs``), e.g. reference_runs/u_bar_chapter_6.3.3/q_backup/q.h5.  ``counter`` = -1 reads the LAST
+    appended group, which is what dolfin's ``read_checkpoint(f, "f")`` returns (OCP_dolfin.py:151-160)."""
+    d = h5lite.read_checkpoint(path_h5, "f", counter)
     if not np.array_equal(d["topology"], V.mesh.cells) or not np.allclose(d["geometry"], V.mesh.coords, atol=1e-14):
         raise ValueError("checkpoint mesh differs from the space's mesh")
     cd = d["cell_dofs"].reshape(-1, 12)

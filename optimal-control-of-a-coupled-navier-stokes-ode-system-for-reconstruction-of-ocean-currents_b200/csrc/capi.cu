@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/ocp_b200.h"
+#include "comm.cuh"
 #include "element_math.cuh"
 #include "host_lu.hpp"
 #include "kernels.cuh"
@@ -110,6 +111,7 @@ struct ocp_ctx {
     int n_adj_reused = 0, n_adj_fallback = 0;
     bool mass_factored = false;
     int adj_refine = 0;   // iterative-refinement steps of the adjoint solve (OCP_ADJ_REFINE); 0 is already ~1e-11
+    Communicator comm;    // NCCL communicator when the buoys are sharded over ranks (ocp_comm_init); 1 rank otherwise
     ocp_solver_stats stats{};
     bool profile = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -443,6 +445,8 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
 
 void ocp_destroy(ocp_ctx *c) {
     if (!c) return;
+    cudaStreamSynchronize(c->stream);
+    c->comm.destroy();
     void *ptrs[] = {c->d_geom, c->d_g1_len, c->d_g1_normal, c->d_cell_nodes, c->d_cell_dofs, c->d_cell_slots,
                     c->d_dof_ux, c->d_dof_uy, c->d_dof_p, c->d_rowptr, c->d_col, c->d_dir, c->d_g1_nodes,
                     c->d_g1_dofs, c->d_g1_slots, c->d_bin_ptr, c->d_bin_cells, c->d_m_rowptr, c->d_m_col,
@@ -648,17 +652,34 @@ int ocp_adjoint_solve(ocp_ctx *c, const double *d_w, const double *d_bnode, doub
         c->stats.n_factor++;
     }
     {
+        // Regular path (nu != 1, warm-started states, OCP_ADJ_REUSE=0, or the fast path was rejected): own
+        // factorisation, one refinement step, and the same residual gate as the fast path - a static-pivot
+        // breakdown or a merely small pivot must not return a silently wrong z (hence gradient and control update).
         PhaseTimer t(c, &c->stats.solve_ms);
         CUDA_OK(c, cudaMemcpyAsync(d_z, c->d_rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
         if (!c->lu_adj.solve(d_z, s, c->err)) return OCP_ERR_SOLVER;
         c->stats.n_solve++;
-        for (int k = 0; k < c->adj_refine; ++k) {   // one step of iterative refinement on the same factors
+        for (int k = 0; k < 1 + c->adj_refine; ++k) {
             launch_spmv_residual(n, c->d_rowptr, c->d_col, c->d_vals, d_z, c->d_rhs, c->d_tmp, s);
             if (!c->lu_adj.solve(c->d_tmp, s, c->err)) return OCP_ERR_SOLVER;
             launch_axpy(n, 1.0, c->d_tmp, d_z, s);
             c->stats.n_solve++;
         }
+        launch_spmv_residual(n, c->d_rowptr, c->d_col, c->d_vals, d_z, c->d_rhs, c->d_tmp, s);
+        launch_sumsq(n, c->d_tmp, c->d_scalar, c->d_scratch, c->d_counter, s);
+        launch_sumsq(n, c->d_rhs, c->d_scalar + 1, c->d_scratch, c->d_counter, s);
         CUDA_OK(c, cudaGetLastError());
+        double ss[2];
+        int rc = read_scalar(c, c->d_scalar, 2, ss);
+        if (rc != OCP_OK) return rc;
+        if (!c->lu_adj.check(c->err)) return OCP_ERR_SOLVER;          // stream is idle: the pivot flag has landed
+        if (!(ss[0] == ss[0]) || ss[0] > 1e-20 * ss[1]) {             // ||b - A z|| > 1e-10 ||b|| (or NaN)
+            char msg[160];
+            snprintf(msg, sizeof msg, "adjoint solve: relative residual %.3e after refinement (static pivoting "
+                     "unreliable for this matrix; run with OCP_SOLVER=rf)", std::sqrt(ss[0] / (ss[1] > 0 ? ss[1] : 1.0)));
+            c->err = msg;
+            return OCP_ERR_SOLVER;
+        }
     }
     return OCP_OK;
 }
@@ -815,6 +836,8 @@ int ocp_gradient_host(ocp_ctx *c, const double *h_f, double *h_w, double *h_z, d
                         c->d_parked, s);
     if ((rc = ocp_buoy_adjoint_scatter(c, d_vel, d_g, K, d_x, d_u, c->d_obs_ud, d_mask, c->d_parked, nullptr, d_acc)))
         return rc;
+    // buoys sharded over ranks: the sum over buoys (OCP_dolfin.py:353-366) is completed across GPUs here
+    if (!c->comm.allreduce_sum(d_acc, nacc, s, c->err)) return OCP_ERR_COMM;
     if ((rc = ocp_adjoint_solve(c, d_w, d_acc, d_z))) return rc;
     launch_boundary_inner(c->n_g1, c->d_g1_nodes, c->d_g1_len, d_f, d_f, c->d_scalar, s);
     CUDA_OK(c, cudaMemcpyAsync(h_w, d_w, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
@@ -829,6 +852,29 @@ int ocp_gradient_host(ocp_ctx *c, const double *h_f, double *h_w, double *h_z, d
     h_scalars[3] = (double)its;
     CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
+}
+
+// ---- multi-GPU exchange -----------------------------------------------------------------------------------------
+
+int ocp_comm_get_unique_id(void *id128) {
+    if (!id128) return OCP_ERR_INVALID;
+    std::string err;
+    return comm_unique_id(id128, err) ? OCP_OK : OCP_ERR_COMM;
+}
+
+int ocp_comm_init(ocp_ctx *c, int nranks, int rank, const void *id128) {
+    if (!c) return OCP_ERR_INVALID;
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return c->comm.init(nranks, rank, id128, c->err) ? OCP_OK : OCP_ERR_COMM;
+}
+
+int ocp_comm_size(const ocp_ctx *c) { return c ? c->comm.size() : 0; }
+
+int ocp_comm_nccl_version(void) { return comm_nccl_version(); }
+
+int ocp_allreduce(ocp_ctx *c, double *d_buf, size_t n) {
+    if (!c || (!d_buf && n)) return OCP_ERR_INVALID;
+    return c->comm.allreduce_sum(d_buf, n, c->stream, c->err) ? OCP_OK : OCP_ERR_COMM;
 }
 
 long long ocp_launch_count(void) { return ocp::g_launch_count.load(); }

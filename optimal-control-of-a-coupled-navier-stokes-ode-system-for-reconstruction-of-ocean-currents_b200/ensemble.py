@@ -48,12 +48,14 @@ class Ensemble:
             self.out.append((pin(V.ndofs), pin(V.ndofs), pin(c.x0.shape[0]), pin(4)))
         self.pool = ThreadPoolExecutor(max_workers=len(cases))
 
-    def _one(self, i: int, f: np.ndarray):
+    def _one(self, i: int, f: np.ndarray, copy: bool = True):
         torch.cuda.set_device(self.device)            # the CUDA context is per host thread
         c = self.cases[i]
         w, z, mask, sc = self.ctx[i].gradient_host(f, self.out[i])
         alpha = c.alpha * c.x0.shape[0]
         grad = alpha * f - self.V.velocity_nodal(z)
+        if copy:      # the pinned staging buffers are overwritten by the next call: hand out copies
+            w, z = w.copy(), z.copy()
         return dict(J=sc["misfit"] + 0.5 * alpha * sc["f_norm2"], grad=grad, newton_its=sc["newton_its"],
                     n_masked=sc["n_masked"], w=w, z=z)
 
@@ -74,7 +76,7 @@ class Ensemble:
         def run(i):
             torch.cuda.set_device(self.device)
             for _ in range(steps):
-                r = self._one(i, fs[i])
+                r = self._one(i, fs[i], copy=False)
                 hist[i].append(r["J"])
                 fs[i] = fs[i] - lr * r["grad"]
 

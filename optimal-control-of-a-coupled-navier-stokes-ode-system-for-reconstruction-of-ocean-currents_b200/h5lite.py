@@ -163,12 +163,26 @@ class H5File:
         return self._cache
 
 
-def read_checkpoint(path: str, name: str | None = None) -> Dict[str, np.ndarray]:
+def checkpoint_counters(path: str, name: str) -> list:
+    """Counters k of the groups ``/<name>/<name>_k`` present in the file, ascending.  The reference appends one group
+    per gradient-descent iteration (``write_checkpoint(..., append=True)``, OCP_dolfin.py:440-441)."""
+    ds = H5File(path).datasets()
+    ks = set()
+    for key in ds:
+        parts = key.split("/")
+        if len(parts) > 2 and parts[1] == name and parts[2].startswith(name + "_") and parts[2][len(name) + 1:].isdigit():
+            ks.add(int(parts[2][len(name) + 1:]))
+    return sorted(ks)
+
+
+def read_checkpoint(path: str, name: str | None = None, counter: int = -1) -> Dict[str, np.ndarray]:
     """Return the datasets of a dolfin checkpoint as a flat dict.
 
     Keys: ``topology, geometry, cell_dofs, x_cell_dofs, cells, vector``.
     ``name`` selects the function group (``u``, ``p``, ``f``); if omitted the
-    file must hold exactly one function.
+    file must hold exactly one function.  ``counter`` selects the group ``<name>_<counter>``; the default -1 is
+    dolfin's ``read_checkpoint(f, name)`` (counter = -1): the LAST group written, i.e. the latest iteration of an
+    appended ``checkpoints/q.h5`` (OCP_dolfin.py:151-160, 440-441).
     """
     ds = H5File(path).datasets()
     groups = sorted({k.split("/")[1] for k in ds})
@@ -176,7 +190,20 @@ def read_checkpoint(path: str, name: str | None = None) -> Dict[str, np.ndarray]
         if len(groups) != 1:
             raise H5FormatError(f"{path}: several functions {groups}, pass name=")
         name = groups[0]
-    pre = f"/{name}/{name}_0/"
+    ks = sorted({int(k.split("/")[2][len(name) + 1:]) for k in ds
+                 if k.split("/")[1] == name and k.split("/")[2].startswith(name + "_")
+                 and k.split("/")[2][len(name) + 1:].isdigit()})
+    if not ks:
+        raise H5FormatError(f"{path}: no group /{name}/{name}_<k>")
+    if counter < 0:
+        if -counter > len(ks):
+            raise H5FormatError(f"{path}: counter {counter} but only {len(ks)} groups of {name}")
+        k = ks[counter]
+    elif counter in ks:
+        k = counter
+    else:
+        raise H5FormatError(f"{path}: no group /{name}/{name}_{counter} (present: {ks})")
+    pre = f"/{name}/{name}_{k}/"
     out = {}
     for key in ("mesh/topology", "mesh/geometry", "cell_dofs", "x_cell_dofs", "cells", "vector"):
         if pre + key not in ds:
@@ -185,6 +212,7 @@ def read_checkpoint(path: str, name: str | None = None) -> Dict[str, np.ndarray]
     out["vector"] = out["vector"].reshape(-1)
     out["cell_dofs"] = out["cell_dofs"].reshape(-1).astype(np.int64)
     out["topology"] = out["topology"].astype(np.int64)
+    out["counter"] = k
     return out
 
 
@@ -256,17 +284,21 @@ class _Writer:
         return self.alloc(_object_header(msgs))
 
     def group(self, children: dict) -> tuple:
-        """children: name -> (object header address, (btree, heap) for groups or None). Returns (hdr, btree, heap)."""
-        names = sorted(children)
-        if len(names) > 2 * _LEAF_K:
-            raise H5FormatError("more than 8 links per group are not needed for checkpoints")
+        """children: name -> (object header address, (btree, heap) for groups or None). Returns (hdr, btree, heap).
+        Links are spread over symbol-table nodes of at most 2 * _LEAF_K entries under ONE level-0 B-tree node, which
+        holds up to 2 * _INTERNAL_K of them: 256 links per group (a gradient-descent run appends one group per
+        iteration; the reference's default is 50 iterations)."""
+        names = sorted(children, key=lambda n: n.encode())      # libhdf5 orders links by strcmp
+        per = 2 * _LEAF_K
+        if len(names) > per * 2 * _INTERNAL_K:
+            raise H5FormatError(f"more than {per * 2 * _INTERNAL_K} links per group are not supported")
         heap_data = bytearray(8)                       # offset 0: the empty name
         offs = {}
         for n in names:
             offs[n] = len(heap_data)
             heap_data += _pad8(n.encode() + b"\0")
-        if len(heap_data) < 88:                        # libhdf5's default data segment, rest is one free block
-            free_off = len(heap_data)
+        if len(heap_data) <= 88 - 16:                  # libhdf5's default data segment, rest is one free block
+            free_off = len(heap_data)                  # (a free block needs 16 bytes: next offset + size)
             free = bytearray(88 - free_off)
             struct.pack_into("<QQ", free, 0, 1, len(free))
             heap_data += free
@@ -274,20 +306,26 @@ class _Writer:
             free_off = 1                               # H5HL_FREE_NULL
         data_addr = self.alloc(bytes(heap_data))
         heap = self.alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), free_off, data_addr))
-        snod = bytearray(8 + 2 * _LEAF_K * 40)
-        snod[:4] = b"SNOD"
-        struct.pack_into("<BBH", snod, 4, 1, 0, len(names))
-        for k, n in enumerate(names):
-            hdr, sub = children[n]
-            if sub is None:
-                struct.pack_into("<QQII16x", snod, 8 + 40 * k, offs[n], hdr, 0, 0)
-            else:
-                struct.pack_into("<QQIIQQ", snod, 8 + 40 * k, offs[n], hdr, 1, 0, sub[0], sub[1])
-        snod_addr = self.alloc(bytes(snod))
+        chunks = [names[i:i + per] for i in range(0, len(names), per)] or [[]]
+        snod_addrs = []
+        for chunk in chunks:
+            snod = bytearray(8 + per * 40)
+            snod[:4] = b"SNOD"
+            struct.pack_into("<BBH", snod, 4, 1, 0, len(chunk))
+            for k, n in enumerate(chunk):
+                hdr, sub = children[n]
+                if sub is None:
+                    struct.pack_into("<QQII16x", snod, 8 + 40 * k, offs[n], hdr, 0, 0)
+                else:
+                    struct.pack_into("<QQIIQQ", snod, 8 + 40 * k, offs[n], hdr, 1, 0, sub[0], sub[1])
+            snod_addrs.append(self.alloc(bytes(snod)))
         tree = bytearray(24 + (2 * _INTERNAL_K + 1) * 8 + 2 * _INTERNAL_K * 8)
         tree[:4] = b"TREE"
-        struct.pack_into("<BBHQQ", tree, 4, 0, 0, 1, _UNDEF, _UNDEF)
-        struct.pack_into("<QQQ", tree, 24, 0, snod_addr, offs[names[-1]] if names else 0)
+        struct.pack_into("<BBHQQ", tree, 4, 0, 0, len(chunks), _UNDEF, _UNDEF)
+        # key[0] | child[0] | key[1] | child[1] | ... : key[i+1] = heap offset of the largest name below child i
+        struct.pack_into("<Q", tree, 24, 0)
+        for i, chunk in enumerate(chunks):
+            struct.pack_into("<QQ", tree, 32 + 16 * i, snod_addrs[i], offs[chunk[-1]] if chunk else 0)
         btree = self.alloc(bytes(tree))
         hdr = self.alloc(_object_header([_message(0x11, struct.pack("<QQ", btree, heap))]))
         return hdr, btree, heap
@@ -304,55 +342,75 @@ class _Writer:
 
 
 def write_checkpoint(path_h5: str, name: str, topology, geometry, cell_dofs, vector, dofs_per_cell: int,
-                     mtime: int = 0, element_degree: int = 2, value_rank: int = 1) -> str:
-    """Write ``<name>/<name>_0/{mesh/{topology,geometry},cell_dofs,x_cell_dofs,cells,vector}`` like dolfin's
-    ``write_checkpoint(fn, name, 0)`` and the companion ``.xdmf``; returns the xdmf path."""
-    topology = np.asarray(topology, np.int32)
-    geometry = np.asarray(geometry, np.float64)
-    cell_dofs = np.asarray(cell_dofs, np.int32).reshape(-1)
-    vector = np.asarray(vector, np.float64).reshape(-1)
-    nc = topology.shape[0]
+                     mtime: int = 0, element_degree: int = 2, value_rank: int = 1, append: bool = False) -> str:
+    """Write ``<name>/<name>_k/{mesh/{topology,geometry},cell_dofs,x_cell_dofs,cells,vector}`` like dolfin's
+    ``write_checkpoint(fn, name, 0, append=...)`` and the companion ``.xdmf``; returns the xdmf path.
+
+    ``append=False`` writes a single group ``<name>_0`` (dolfin truncates the file); ``append=True`` keeps the groups
+    already in the file and adds ``<name>_{k+1}`` - the reference appends the control of every gradient-descent
+    iteration to ``checkpoints/q.xdmf`` (OCP_dolfin.py:440-441).  The file is rebuilt and replaced atomically
+    (temporary file + ``os.replace``), so a crash in mid-write never destroys the previous checkpoint."""
+    new = dict(topology=np.asarray(topology, np.int32), geometry=np.asarray(geometry, np.float64),
+               cell_dofs=np.asarray(cell_dofs, np.int32).reshape(-1), vector=np.asarray(vector, np.float64).reshape(-1))
+    steps = []
+    if append and os.path.exists(path_h5):
+        for k in checkpoint_counters(path_h5, name):
+            d = read_checkpoint(path_h5, name, k)
+            steps.append(dict(topology=d["topology"].astype(np.int32), geometry=d["geometry"],
+                              cell_dofs=d["cell_dofs"].astype(np.int32), vector=d["vector"]))
+    steps.append(new)
     w = _Writer()
     ds = lambda a: (w.dataset(a, mtime), None)
-    mesh = w.group({"topology": ds(topology), "geometry": ds(geometry)})
-    inner = w.group({
-        "mesh": (mesh[0], mesh[1:]),
-        "cell_dofs": ds(cell_dofs),
-        "x_cell_dofs": ds(np.arange(nc + 1, dtype=np.uint64) * np.uint64(dofs_per_cell)),
-        "cells": ds(np.arange(nc, dtype=np.uint64)),
-        "vector": ds(vector),
-    })
-    outer = w.group({f"{name}_0": (inner[0], inner[1:])})
+    groups = {}
+    for k, st in enumerate(steps):
+        nck = st["topology"].shape[0]
+        mesh = w.group({"topology": ds(st["topology"]), "geometry": ds(st["geometry"])})
+        inner = w.group({
+            "mesh": (mesh[0], mesh[1:]),
+            "cell_dofs": ds(st["cell_dofs"]),
+            "x_cell_dofs": ds(np.arange(nck + 1, dtype=np.uint64) * np.uint64(dofs_per_cell)),
+            "cells": ds(np.arange(nck, dtype=np.uint64)),
+            "vector": ds(st["vector"]),
+        })
+        groups[f"{name}_{k}"] = (inner[0], inner[1:])
+    outer = w.group(groups)
     root = w.group({name: (outer[0], outer[1:])})
-    with open(path_h5, "wb") as fh:
+    tmp = path_h5 + ".tmp"
+    with open(tmp, "wb") as fh:
         fh.write(w.finish(root))
+    os.replace(tmp, path_h5)
     base = os.path.basename(path_h5)
-    grp = f"{base}:{name}/{name}_0"
     atype = "Vector" if value_rank == 1 else "Scalar"
-    xdmf = f"""<?xml version="1.0"?>
-<Xdmf Version="3.0">
-  <Domain>
-    <Grid GridType="Collection" CollectionType="Temporal" Name="{name}">
-      <Grid Name="{name}_0" GridType="Uniform">
+    grids = []
+    for k, st in enumerate(steps):
+        grp = f"{base}:{name}/{name}_{k}"
+        nc, nvert = st["topology"].shape[0], st["geometry"].shape[0]
+        grids.append(f"""      <Grid Name="{name}_{k}" GridType="Uniform">
         <Topology NumberOfElements="{nc}" TopologyType="Triangle" NodesPerElement="3">
           <DataItem Dimensions="{nc} 3" NumberType="UInt" Format="HDF">{grp}/mesh/topology</DataItem>
         </Topology>
         <Geometry GeometryType="XY">
-          <DataItem Dimensions="{geometry.shape[0]} 2" Format="HDF">{grp}/mesh/geometry</DataItem>
+          <DataItem Dimensions="{nvert} 2" Format="HDF">{grp}/mesh/geometry</DataItem>
         </Geometry>
         <Time Value="0.000000000000000e+00" />
         <Attribute ItemType="FiniteElementFunction" ElementFamily="CG" ElementDegree="{element_degree}" ElementCell="triangle" Name="{name}" Center="Other" AttributeType="{atype}">
-          <DataItem Dimensions="{cell_dofs.size} 1" NumberType="UInt" Format="HDF">{grp}/cell_dofs</DataItem>
-          <DataItem Dimensions="{vector.size} 1" NumberType="Float" Format="HDF">{grp}/vector</DataItem>
+          <DataItem Dimensions="{st['cell_dofs'].size} 1" NumberType="UInt" Format="HDF">{grp}/cell_dofs</DataItem>
+          <DataItem Dimensions="{st['vector'].size} 1" NumberType="Float" Format="HDF">{grp}/vector</DataItem>
           <DataItem Dimensions="{nc + 1} 1" NumberType="UInt" Format="HDF">{grp}/x_cell_dofs</DataItem>
           <DataItem Dimensions="{nc} 1" NumberType="UInt" Format="HDF">{grp}/cells</DataItem>
         </Attribute>
       </Grid>
-    </Grid>
+""")
+    xdmf = f"""<?xml version="1.0"?>
+<Xdmf Version="3.0">
+  <Domain>
+    <Grid GridType="Collection" CollectionType="Temporal" Name="{name}">
+{''.join(grids)}    </Grid>
   </Domain>
 </Xdmf>
 """
     path_x = os.path.splitext(path_h5)[0] + ".xdmf"
-    with open(path_x, "w") as fh:
+    with open(path_x + ".tmp", "w") as fh:
         fh.write(xdmf)
+    os.replace(path_x + ".tmp", path_x)
     return path_x

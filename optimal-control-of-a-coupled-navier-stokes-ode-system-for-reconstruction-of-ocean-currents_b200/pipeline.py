@@ -110,6 +110,9 @@ class OCP:
         self.h, self.nt = float(params.dt), params.nt
         self.center_of_domain = np.array([1.0, 0.5]) if V.mesh.l_shape else np.array([1.0, 1.0])
         self.ctx = capi.Context(V, params.viscosity, params.dt, self.nt, self.center_of_domain)
+        if group is not None:
+            from .sharding import attach_communicator
+            attach_communicator(self.ctx, group)      # NCCL groups: the all-reduce runs inside the library
         x0 = np.ascontiguousarray(x0, np.float64).reshape(-1, 2)
         self.K = x0.shape[0]
         if u_d is not None and u_d.shape != (self.K, self.nt, 2):
@@ -205,7 +208,7 @@ class OCP:
 
     def _allreduce(self, t: torch.Tensor):
         from .sharding import allreduce_accumulator
-        allreduce_accumulator(t, self.group)
+        allreduce_accumulator(t, self.group, self.ctx)
 
     def set_control(self, f_nodal: np.ndarray):
         self.d_f.copy_(self._dev(f_nodal))
@@ -235,6 +238,10 @@ class OCP:
         buoy_mask[:] = self._buoy_vector_to_host(self.d_mask)
         return self._to_reference_layout(self.d_x), self._to_reference_layout(self.d_u)
 
+    def last_parked(self) -> np.ndarray:
+        """Per-buoy flags of the last solve_primal_ode: 1 where only the final sample left the domain."""
+        return self._buoy_vector_to_host(self.d_parked)
+
     def solve_adjoint_ode(self, wSol: State, grad_u: torch.Tensor, x, buoy_mask, u_values_array) -> np.ndarray:
         """OCP_dolfin.py:234-252 -> numpy mu (K,nt,2).  (The fused sweep also deposits point sources and the
         misfit into a scratch accumulator, which this reference-shaped call discards.)"""
@@ -247,15 +254,22 @@ class OCP:
         self.ctx.buoy_adjoint_scatter(self.d_vel, grad_u, x.shape[0], d_x, d_u, self.d_ud, d_mask, parked, d_mu, acc)
         return self._to_reference_layout(d_mu)
 
-    def adjoint_solve(self, w: State, x, u_values, buoy_mask, grad_u: Optional[torch.Tensor] = None) -> State:
+    def adjoint_solve(self, w: State, x, u_values, buoy_mask, grad_u: Optional[torch.Tensor] = None,
+                      parked=None) -> State:
         """The adjoint PDE block OCP_dolfin.py:336-371 for host arrays x, u_values (K,nt,2): recomputes mu,
-        deposits the point sources, all-reduces, assembles aAdj, applies the BC and solves."""
+        deposits the point sources, all-reduces, assembles aAdj, applies the BC and solves.  ``parked`` (K) flags
+        the buoys whose LAST sample alone left the domain (OCP_dolfin.py:226-229; ``last_parked()`` after
+        solve_primal_ode); without it the flags are inferred from the stored arrays (last sample at the centre with
+        zero velocity), which is what the reference's scatter loop sees."""
         d_x, d_u = self._to_time_major(x), self._to_time_major(u_values)
         d_mask = self._buoy_vector_to_dev(buoy_mask)
         g = grad_u if grad_u is not None else self.project_grad(w)
         self.ctx.velocity_nodal(w.d_w, self.d_vel)
-        parked = ((d_x[-1, :, 0] == self.center_of_domain[0]) & (d_x[-1, :, 1] == self.center_of_domain[1])
-                  & (d_u[-1, :, 0] == 0) & (d_u[-1, :, 1] == 0) & (d_mask == 0)).to(torch.uint8)
+        if parked is not None:
+            parked = self._buoy_vector_to_dev(np.asarray(parked, np.float64)).to(torch.uint8)
+        else:
+            parked = ((d_x[-1, :, 0] == self.center_of_domain[0]) & (d_x[-1, :, 1] == self.center_of_domain[1])
+                      & (d_u[-1, :, 0] == 0) & (d_u[-1, :, 1] == 0) & (d_mask == 0)).to(torch.uint8)
         self.d_acc.zero_()
         self.ctx.buoy_adjoint_scatter(self.d_vel, g, x.shape[0], d_x, d_u, self.d_ud, d_mask, parked, None, self.d_acc)
         self._allreduce(self.d_acc)
@@ -420,10 +434,17 @@ class OCP:
             self.ctx.field_norms(self.d_w, self.d_sc)
             res.divs_u.append(float(np.sqrt(self.d_sc[0].item())))
             if out_dir is not None:
-                # control checkpoint of this iteration (OCP_dolfin.py:440-441); resume with checkpoint.read_control
+                # control checkpoint of this iteration, appended as group f_i like the reference's
+                # write_checkpoint(..., append=True) (OCP_dolfin.py:440-441); resume with checkpoint.read_control,
+                # which returns the last group.  A non-finite cost/control never replaces the last good checkpoint.
                 from . import checkpoint
                 os.makedirs(os.path.join(out_dir, "checkpoints"), exist_ok=True)
-                checkpoint.write_control(os.path.join(out_dir, "checkpoints", "q.h5"), self.V, d_f.cpu().numpy())
+                f_host = d_f.cpu().numpy()
+                if np.isfinite(res.J_array[-1]) and np.all(np.isfinite(f_host)):
+                    checkpoint.write_control(os.path.join(out_dir, "checkpoints", "q.h5"), self.V, f_host, append=i > 0)
+                else:
+                    res.exit_reason = "non-finite cost or control"
+                    break
             if callback is not None:
                 callback(i, self, res)
             if res.exit_reason == "line_search_stalled":
@@ -492,6 +513,23 @@ class OCP:
 
     def close(self):
         self.ctx.close()
+
+
+# -- the reference's own L-shape experiment --------------------------------------------------------------------
+def lshape_reference_observations(params: Parameters = Parameters()):
+    """``ud_type == "L-shape"`` of OCP_dolfin.py:163-196: K = 3 buoys started at (0.5, 0.5), (1.0, 0.5), (1.5, 1.0)
+    with the analytic target velocities u_d(t) sampled on ``time_interval = np.linspace(t0, T, int(T / h))`` - whose
+    spacing is 1/199, not h (kept).  Returns ``x0`` (3,2) and ``u_d`` (3,nt,2)."""
+    nt = params.nt
+    time_interval = np.linspace(params.t0, params.T, nt)
+    ud1 = 0.5 * (np.cos(np.pi * (time_interval - 0.5)) - 1 - np.cos(np.pi))
+    ud2 = ud1.copy()
+    x0 = np.array([[0.5, 0.5], [1.0, 0.5], [1.5, 1.0]])
+    u_d = np.zeros((3, nt, 2))
+    u_d[0, :, 0] = ud1
+    u_d[1, :, 0], u_d[1, :, 1] = ud1, ud2
+    u_d[2, :, 1] = ud2
+    return x0, u_d
 
 
 # -- initial controls of the three pipelines -------------------------------------------------------------------

@@ -3,7 +3,12 @@
 Buoys are independent given the velocity field, so they are partitioned contiguously over ranks; every rank
 holds a replica of the mesh, the state ``w`` and the factorisation.  The only exchange step of a gradient
 evaluation is one all-reduce(sum, fp64) of the accumulator ``[b (nn,2) | misfit | n_masked]`` that the backward
-sweep deposits into (OCP_dolfin.py:353-366 is a sum over buoys) - NCCL over NVLink on GPUs, gloo in CPU tests.
+sweep deposits into (OCP_dolfin.py:353-366 is a sum over buoys).
+
+The collective itself lives INSIDE the C-ABI library (``ocp_comm_init`` / ``ocp_allreduce``: ``ncclAllReduce`` on the
+context's stream, csrc/comm.cu), so that a C / C++ host can run sharded without Python.  This module only hands the
+NCCL unique id from rank 0 to the other ranks (``attach_communicator``) through whatever process group the launcher
+set up; ``torch.distributed`` is the fallback exchange for process groups that are not NCCL (gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -45,11 +50,34 @@ def spatial_order(V, x0: np.ndarray) -> np.ndarray:
     return np.argsort(key, kind="stable")
 
 
-def allreduce_accumulator(acc: torch.Tensor, group=None) -> torch.Tensor:
-    """In-place sum of the per-rank accumulators; a no-op for a single rank."""
-    if group is not None and dist.get_world_size(group) > 1:
+def allreduce_accumulator(acc: torch.Tensor, group=None, ctx=None) -> torch.Tensor:
+    """In-place sum of the per-rank accumulators; a no-op for a single rank.  With a context that owns an NCCL
+    communicator (``attach_communicator``) the exchange is the library's ``ocp_allreduce``."""
+    if ctx is not None and ctx.comm_size() > 1:
+        ctx.allreduce(acc)
+    elif group is not None and dist.get_world_size(group) > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
     return acc
+
+
+def attach_communicator(ctx, group) -> bool:
+    """Give ``ctx`` its own NCCL communicator over the ranks of ``group``: rank 0 asks the library for a unique id,
+    the 128 bytes travel through the process group, every rank calls ``ocp_comm_init``.  Returns False (and leaves
+    the torch.distributed fallback in place) when the group is not an NCCL group, e.g. gloo ranks sharing one GPU."""
+    from . import capi
+    if group is None or dist.get_world_size(group) <= 1:
+        return False
+    if dist.get_backend(group) != "nccl":
+        return False
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if rank == 0:
+        t = torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8).to(dev)
+    else:
+        t = torch.empty(capi.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0), group=group)
+    ctx.comm_init(world, rank, bytes(t.cpu().numpy().tobytes()))
+    return True
 
 
 def init_from_env(backend: str = "nccl"):

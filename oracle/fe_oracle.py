@@ -223,11 +223,12 @@ class FEOracle:
     @staticmethod
     def apply_dirichlet_rows(J, dofs):
         """``bc.apply(A)``: zero the rows, unit diagonal, columns untouched."""
-        J = J.tolil(copy=True)
-        for d in dofs:
-            J.rows[d] = [int(d)]
-            J.data[d] = [1.0]
-        return J.tocsr()
+        n = J.shape[0]
+        mask = np.zeros(n)
+        mask[np.asarray(dofs, dtype=np.int64)] = 1.0
+        out = (sp.diags(1.0 - mask) @ J.tocsr() + sp.diags(mask)).tocsr()
+        out.eliminate_zeros()
+        return out
 
     def forward_jacobian(self, w):
         return self.apply_dirichlet_rows(self.jacobian_unconstrained(w), self.V.dirichlet_dofs)

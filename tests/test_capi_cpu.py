@@ -136,3 +136,38 @@ def test_scripts_parse():
     assert len(files) >= 6
     for f in files:
         ast.parse(open(f).read(), filename=f)
+
+
+def _header_struct_fields():
+    """(name, kind) of every member of ocp_problem_desc in include/ocp_b200.h, in declaration order."""
+    txt = open(HEADER).read()
+    body = txt[txt.index("typedef struct {"):txt.index("} ocp_problem_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for stmt in body.split(";"):
+        stmt = " ".join(stmt.replace("typedef struct {", "").split())
+        if not stmt:
+            continue
+        m = re.match(r"(const )?(int32_t|double) (.*)", stmt)
+        assert m, stmt
+        for name in m.group(3).split(","):
+            name = name.strip()
+            kind = "ptr" if name.startswith("*") else m.group(2)
+            out.append((name.lstrip("*"), kind))
+    return out
+
+
+def test_problem_desc_bindings_match_the_header():
+    """The ctypes struct shipped in capi.py AND the one printed in INTEGRATION.md (what a maintainer would paste into
+    the reference repo) mirror ocp_problem_desc field for field - a missing member silently mis-binds every pointer
+    after it."""
+    import ctypes as C
+    kinds = {C.c_int32: "int32_t", C.c_double: "double", C.c_void_p: "ptr"}
+    hdr = _header_struct_fields()
+    assert [(n, kinds[t]) for n, t in capi.ProblemDesc._fields_] == hdr
+    md = open(os.path.join(H.ROOT, "INTEGRATION.md")).read()
+    code = md[md.index("class ProblemDesc(C.Structure):"):md.index("def p(a): return")]
+    ns = {"C": C}
+    exec(code, ns)
+    assert [(n, kinds[t]) for n, t in ns["ProblemDesc"]._fields_] == hdr
+    assert C.sizeof(ns["ProblemDesc"]) == C.sizeof(capi.ProblemDesc)

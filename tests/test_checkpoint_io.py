@@ -57,3 +57,32 @@ def test_written_files_have_the_structure_of_dolfins(tmp_path):
     # the reference's control checkpoint reads into the nodal field used by the K4/K5 tests
     V = H.square32()
     assert np.array_equal(checkpoint.read_control(os.path.join(REF, "q_backup/q.h5"), V), H.q_nodal(V))
+
+
+def test_appended_checkpoints_read_back_the_last_group(tmp_path):
+    """The reference appends one group f_k per GD iteration (OCP_dolfin.py:440-441) and dolfin's
+    read_checkpoint(f, "f") returns the LAST one: multi-step files, counter semantics, more than 8 links per group."""
+    V = H.square32()
+    q = H.q_nodal(V)
+    path = str(tmp_path / "q.h5")
+    n = 21                                                    # > 2 symbol-table nodes (8 links each)
+    for k in range(n):
+        checkpoint.write_control(path, V, q * (k + 1), append=k > 0)
+    assert h5lite.checkpoint_counters(path, "f") == list(range(n))
+    assert np.array_equal(checkpoint.read_control(path, V), q * n)             # default: the latest iteration
+    assert np.array_equal(checkpoint.read_control(path, V, counter=0), q)
+    assert np.array_equal(checkpoint.read_control(path, V, counter=9), q * 10)
+    assert np.array_equal(checkpoint.read_control(path, V, counter=-2), q * (n - 1))
+    with pytest.raises(h5lite.H5FormatError):
+        checkpoint.read_control(path, V, counter=n)
+    assert open(str(tmp_path / "q.xdmf")).read().count("<Grid Name=\"f_") == n
+    # append=False truncates like dolfin
+    checkpoint.write_control(path, V, q)
+    assert h5lite.checkpoint_counters(path, "f") == [0]
+    # a non-finite control never replaces the last good checkpoint, and no temporary file is left behind
+    bad = q.copy()
+    bad[3, 1] = np.nan
+    with pytest.raises(ValueError):
+        checkpoint.write_control(path, V, bad, append=True)
+    assert np.array_equal(checkpoint.read_control(path, V), q)
+    assert sorted(os.listdir(tmp_path)) == ["q.h5", "q.xdmf"]

@@ -1,0 +1,201 @@
+"""Parity at the BENCHMARKED sizes and on the paths the small cases do not reach (round-2 gate):
+
+  * cfg3, K = 10 000 (the headline bench workload): w, b, z, gradient and J of one full gradient evaluation;
+  * K = 20 000 >= 8 cells' worth per cell: the per-SM private-copy scatter, element-wise against the oracle;
+  * 128 x 128 mesh with the DEFAULT large-front threshold (fronts up to 1559, many-CTA groups), against the
+    committed oracle fixture tests/golden/mesh128_gradient.npz (tools/make_golden_mesh128.py);
+  * the reference's own L-shape experiment (K = 3, analytic u_d, OCP_dolfin.py:163-196);
+  * the reference-shaped host entry point solve_adjoint_ode.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from ocp_b200.pipeline import OCP, Knobs, Parameters, State, initial_control, lshape_reference_observations
+from oracle.buoy_oracle import BuoyOracle
+from oracle.fe_oracle import FEOracle
+
+pytestmark = pytest.mark.gpu
+COST_TOL = 1e-8
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+def cfg3_problem():
+    """BASELINE.json config 3: 100 x 100 start grid, u_d advected through the stored 10000_buoys field."""
+    V = H.square32()
+    gx, gy = np.meshgrid(np.linspace(0.1, 0.4, 100), np.linspace(0.25, 1.75, 100))
+    x0 = np.stack([gx.ravel(), gy.ravel()], 1)
+    _, ud, _, mask, _ = BuoyOracle(V).forward(V.velocity_nodal(H.field_for(10000)), x0, 200, H.H, H.CENTER)
+    assert mask.sum() == 0
+    return V, x0, ud
+
+
+def test_cfg3_10000_buoys_full_gradient_vs_oracle():
+    V, x0, ud = cfg3_problem()
+    K = x0.shape[0]
+    f = initial_control(V, "PL")
+    P = H.OraclePipeline(V, 1.0, x0, ud, 1e-6 * K)
+    s = P.gradient_step(f)
+    ocp = OCP(V, Parameters(), x0, ud, device=dev())
+    ocp.set_control(f)
+    ocp.gradient_step(ocp.d_f)
+    nn = V.num_nodes
+    w = ocp.d_w.cpu().numpy()
+    assert ocp.last_newton_its == s["its"] == 3
+    assert H.rel(w, s["w"]) < 1e-11
+    x, u = ocp._to_reference_layout(ocp.d_x), ocp._to_reference_layout(ocp.d_u)
+    assert np.abs(x - s["x"]).max() < 1e-10 and np.abs(u - s["u"]).max() < 1e-10
+    acc = ocp.d_acc.cpu().numpy()
+    b = acc[:2 * nn].reshape(-1, 2)
+    assert H.rel(b, s["bnode"]) < 1e-11                       # end to end (two different LU solvers upstream)
+    # the same chain evaluated by the oracle on the GPU's own state: isolates the buoy kernels -> 1e-12
+    B, O = P.B, P.O
+    g_o = O.project_gradient(w)
+    xo, uo, co, mo, po = B.forward(V.velocity_nodal(w), x0, 200, H.H, H.CENTER)
+    assert np.array_equal(x, xo) and np.array_equal(u, uo)    # bit-exact on an identical field
+    muo = B.adjoint(g_o, xo, uo, ud, mo, H.H)
+    bo = B.point_sources(V.velocity_nodal(w), xo, ud, muo, mo, H.H, H.CENTER)
+    assert H.rel(ocp.d_g.cpu().numpy(), g_o) < 1e-12
+    assert H.rel(b, bo) < 1e-12
+    assert abs(acc[2 * nn] - B.misfit(uo, ud, H.H)) <= 1e-12 * B.misfit(uo, ud, H.H) and acc[2 * nn + 1] == 0
+    z = ocp.d_z.cpu().numpy()
+    assert H.rel(z, s["z"]) < 1e-9
+    g1 = np.unique(V.g1_nodes)
+    assert H.rel(ocp.d_grad.cpu().numpy()[g1], s["grad"][g1]) < COST_TOL
+    J, Jo = ocp._cost_from_acc(ocp.d_f), P.cost(s["u"], f)
+    assert abs(J - Jo) <= COST_TOL * abs(Jo)
+    # and through the C-ABI host-buffer call the bench times
+    ocp.ctx.set_observations_host(x0, ud)
+    w2, z2, mask2, sc = ocp.ctx.gradient_host(f)
+    assert sc["newton_its"] == 3 and sc["n_masked"] == 0
+    assert H.rel(w2, s["w"]) < 1e-11 and H.rel(z2, s["z"]) < 1e-9
+    assert abs(sc["misfit"] + 0.5 * 1e-6 * K * sc["f_norm2"] - Jo) <= COST_TOL * abs(Jo)
+    ocp.close()
+
+
+@pytest.mark.parametrize("K", [20_000, 40_001])
+def test_private_copy_scatter_elementwise_vs_oracle(K):
+    """K >= 8 * #cells switches the point-source deposit to per-SM private copies of b (buoy_private_copies);
+    b, mu and the misfit element-wise against the oracle, trajectories bit-exact."""
+    V = H.square32()
+    assert K >= 8 * V.mesh.num_cells
+    rng = np.random.default_rng(11)
+    x0 = np.stack([rng.uniform(0.05, 1.95, K), rng.uniform(0.05, 1.95, K)], 1)
+    w = H.field_for(100)
+    vel = V.velocity_nodal(w)
+    B, O = BuoyOracle(V), FEOracle(V, 1.0)
+    xo, uo, co, mo, po = B.forward(vel, x0, 200, H.H, H.CENTER)
+    ud = 1.1 * uo + 0.01 * rng.standard_normal(uo.shape)
+    g = O.project_gradient(w)
+    muo = B.adjoint(g, xo, uo, ud, mo, H.H)
+    bo = B.point_sources(vel, xo, ud, muo, mo, H.H, H.CENTER)
+    ocp = OCP(V, Parameters(), x0, ud, device=dev())
+    ocp._primal(T(w), ocp.d_x, ocp.d_u, ocp.d_mask)
+    x, u = ocp._to_reference_layout(ocp.d_x), ocp._to_reference_layout(ocp.d_u)
+    assert np.array_equal(x, xo) and np.array_equal(u, uo)
+    assert np.array_equal(ocp._buoy_vector_to_host(ocp.d_mask), mo)
+    nn = V.num_nodes
+    acc = torch.zeros(2 * nn + 2, device=dev(), dtype=torch.float64)
+    mu = torch.empty_like(ocp.d_x)
+    ocp.ctx.buoy_adjoint_scatter(ocp.d_vel, T(g), K, ocp.d_x, ocp.d_u, ocp.d_ud, ocp.d_mask, ocp.d_parked, mu, acc)
+    a = acc.cpu().numpy()
+    assert H.rel(ocp._to_reference_layout(mu), muo) < 1e-12
+    assert H.rel(a[:2 * nn].reshape(-1, 2), bo) < 1e-12
+    assert abs(a[2 * nn] - B.misfit(uo, ud, H.H)) <= 1e-12 * B.misfit(uo, ud, H.H)
+    assert a[2 * nn + 1] == mo.sum()
+    ocp.close()
+
+
+def test_mesh128_default_large_front_solver_vs_oracle_fixture():
+    """cfg5 mesh (148 739 dofs): Newton, projection, buoy sweeps and the transposed adjoint solve with the large
+    fronts on the many-CTA group kernels at their DEFAULT threshold, against the oracle's stored results."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk128", os.path.join(H.ROOT, "tools", "make_golden_mesh128.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    G = np.load(os.path.join(H.GOLD, "mesh128_gradient.npz"))
+    V, x0, f = mk.problem()
+    K, st = x0.shape[0], int(G["stride"])
+    assert "OCP_MF_BIG" not in os.environ
+    ocp = OCP(V, Parameters(), x0, G["ud"], device=dev())
+    ocp.set_control(f)
+    ocp.gradient_step(ocp.d_f)
+    assert ocp.last_newton_its == int(G["its"])
+    assert np.allclose(ocp.last_res_hist[:-1], G["hist"][:-1], rtol=1e-6)
+    w, z, g = ocp.d_w.cpu().numpy(), ocp.d_z.cpu().numpy(), ocp.d_g.cpu().numpy()
+    assert H.rel(w[::st], G["w_sample"]) < 1e-10 and abs(np.linalg.norm(w) - G["w_norm"]) < 1e-11 * G["w_norm"]
+    assert H.rel(g[::st], G["g_sample"]) < 1e-9 and abs(np.linalg.norm(g) - G["g_norm"]) < 1e-10 * G["g_norm"]
+    assert H.rel(z[::st], G["z_sample"]) < 1e-8 and abs(np.linalg.norm(z) - G["z_norm"]) < 1e-9 * G["z_norm"]
+    g1 = np.unique(V.g1_nodes)
+    assert H.rel(V.velocity_nodal(z)[g1], G["z_g1"]) < 1e-8
+    assert H.rel(ocp.d_grad.cpu().numpy()[g1], G["grad_g1"]) < COST_TOL
+    nn = V.num_nodes
+    b = ocp.d_acc.cpu().numpy()[:2 * nn].reshape(-1, 2)
+    assert np.array_equal(np.flatnonzero(np.abs(b).sum(1) > 0), G["b_nodes"])
+    assert H.rel(b[G["b_nodes"]], G["b_vals"]) < 1e-9
+    assert np.abs(ocp._to_reference_layout(ocp.d_x)[:, -1, :] - G["x_last"]).max() < 1e-10
+    J = ocp._cost_from_acc(ocp.d_f)
+    assert abs(J - float(G["J"])) <= COST_TOL * abs(float(G["J"]))
+    ocp.close()
+
+
+def test_reference_lshape_experiment_K3_analytic_ud():
+    """OCP_dolfin.py with L_shape = True: K = 3, analytic u_d(t) on linspace(t0, T, 200) (quirk A.7(1)), sinusoidal
+    q0, Armijo line search, alpha = 3e-6, exit rule K/2.  The mshr mesh is not reproducible; same domain, jittered
+    structured triangulation, CUDA path against the oracle pipeline on that mesh."""
+    V = H.lshape(16, 0.15)
+    P = Parameters()
+    x0, ud = lshape_reference_observations(P)
+    assert ud.shape == (3, 200, 2) and abs(ud[0, 1, 0] - 0.5 * (np.cos(np.pi * (1 / 199 - 0.5)))) < 1e-15
+    ocp = OCP(V, P, x0, ud, device=dev())
+    assert np.array_equal(ocp.center_of_domain, [1.0, 0.5]) and abs(ocp.alpha - 3e-6) < 1e-20
+    f0 = initial_control(V, "OCP")
+    r = ocp.run(f0, Knobs(num_steps=3, use_line_search=True))
+    ref = H.OraclePipeline(V, 1.0, x0, ud, 3e-6, center=[1.0, 0.5]).run(f0, 3, True)
+    assert r.inner_iterations == ref["inner"]
+    assert np.allclose(r.J_array, ref["J_array"], rtol=COST_TOL, atol=0)
+    g1 = np.unique(V.g1_nodes)
+    assert H.rel(r.f[g1], ref["f"][g1]) < 1e-7
+    assert abs(r.LR - ref["LR"]) == 0
+    # first gradient evaluation in detail
+    s = H.OraclePipeline(V, 1.0, x0, ud, 3e-6, center=[1.0, 0.5]).gradient_step(f0)
+    ocp.set_control(f0)
+    ocp.gradient_step(ocp.d_f)
+    assert ocp.last_newton_its == s["its"]
+    assert np.array_equal(ocp._buoy_vector_to_host(ocp.d_mask), s["mask"])
+    assert np.abs(ocp._to_reference_layout(ocp.d_x) - s["x"]).max() < 1e-10
+    assert H.rel(ocp.d_z.cpu().numpy(), s["z"]) < 1e-9
+    ocp.close()
+
+
+def test_solve_adjoint_ode_host_entry_point_matches_oracle():
+    """ocp_solve_adjoint_ode_host = the reference's solve_adjoint_ode(wSol, grad_u, x, buoy_mask, u_values_array)
+    with host (K,nt,2) arrays (OCP_dolfin.py:234-252), masked buoys skipped."""
+    V = H.lshape()
+    O, B = FEOracle(V, 1.0), BuoyOracle(V)
+    w = O.newton_solve(initial_control(V, "PL"))
+    g = O.project_gradient(w)
+    rng = np.random.default_rng(5)
+    K = 300
+    x0 = np.stack([rng.uniform(-0.05, 2.05, K), rng.uniform(-0.05, 2.05, K)], 1)
+    ud = 0.05 * rng.standard_normal((K, 200, 2))
+    center = np.array([1.0, 0.5])
+    xo, uo, co, mo, po = B.forward(V.velocity_nodal(w), x0, 200, H.H, center)
+    assert 0 < mo.sum() < K
+    muo = B.adjoint(g, xo, uo, ud, mo, H.H)
+    ocp = OCP(V, Parameters(), x0, ud, device=dev())
+    mu = ocp.ctx.solve_adjoint_ode_host(g, xo, uo, ud, mo)
+    assert mu.shape == (K, 200, 2)
+    assert H.rel(mu, muo) < 1e-12
+    assert np.all(mu[mo != 0] == 0)
+    ocp.close()
