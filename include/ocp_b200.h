@@ -201,6 +201,14 @@ int ocp_comm_nccl_version(void);                /* e.g. 22809; 0 when NCCL canno
 /* in-place sum over the ranks of d_buf[0..n) (device, fp64) on the context's stream; no-op for a single rank */
 int ocp_allreduce(ocp_ctx *ctx, double *d_buf, size_t n);
 
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------------------------------
+ * out8 = [flops of one numeric factorisation of the W x W matrix (from the symbolic analysis), non-zeros of L+U,
+ * tree levels, largest front, front workspace in doubles, flops and non-zeros of the P1 mass factorisation, fronts]. */
+void ocp_get_solver_info(const ocp_ctx *ctx, double *out8);
+/* fp64 FMA-pipe peak of the device, TFlop/s: register-resident DFMA loop on every SM, best of 5 launches (CUDA
+ * events).  The denominator of the sparse-LU roofline; MEASURED_PEAKS.json holds no fp64 figure. */
+int ocp_selftest_fp64_peak(ocp_ctx *ctx, double *tflops);
+
 /* Number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 long long ocp_launch_count(void);
 

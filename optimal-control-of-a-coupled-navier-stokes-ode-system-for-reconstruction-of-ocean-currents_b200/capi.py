@@ -26,7 +26,7 @@ SYMBOLS = [
     "ocp_velocity_nodal", "ocp_buoy_forward", "ocp_buoy_adjoint_scatter", "ocp_misfit",
     "ocp_adjoint_solve", "ocp_boundary_inner", "ocp_nodal_axpby", "ocp_field_norms", "ocp_traj_transpose",
     "ocp_solve_primal_ode_host", "ocp_solve_adjoint_ode_host", "ocp_set_observations_host", "ocp_gradient_host",
-    "ocp_launch_count",
+    "ocp_launch_count", "ocp_get_solver_info", "ocp_selftest_fp64_peak",
     "ocp_comm_get_unique_id", "ocp_comm_init", "ocp_comm_size", "ocp_comm_nccl_version", "ocp_allreduce",
     "ocp_host_lu_probe", "ocp_host_mf_probe", "ocp_host_mf_set_pivot_window", "ocp_selftest_cell_matrix", "ocp_selftest_facet_matrix",
 ]
@@ -82,6 +82,8 @@ def load_library() -> C.CDLL:
         lib.ocp_set_profiling.restype = None
         lib.ocp_selftest_cell_matrix.restype = None
         lib.ocp_selftest_facet_matrix.restype = None
+        lib.ocp_get_solver_info.restype = None
+        lib.ocp_get_solver_info.argtypes = [C.c_void_p, C.c_void_p]
         lib.ocp_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         lib.ocp_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.ocp_comm_size.argtypes = [C.c_void_p]
@@ -173,6 +175,18 @@ class Context:
 
     def reset_solver_stats(self):
         self.lib.ocp_reset_solver_stats(self._h)
+
+    def solver_info(self) -> dict:
+        out = np.zeros(8)
+        self.lib.ocp_get_solver_info(self._h, _hp(out))
+        keys = ["factor_flops", "factor_nnz", "levels", "max_front", "workspace_doubles", "mass_flops", "mass_nnz",
+                "fronts"]
+        return dict(zip(keys, out.tolist()))
+
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double(0.0)
+        self._check(self.lib.ocp_selftest_fp64_peak(self._h, C.byref(v)), "ocp_selftest_fp64_peak")
+        return float(v.value)
 
     def set_profiling(self, on: bool):
         """Line-item timing synchronises after every phase: keep it off outside profiling runs."""

@@ -725,21 +725,22 @@ int ocp_solve_primal_ode_host(ocp_ctx *c, const double *h_w, const double *h_x0,
     if ((rc = ensure_stage(c, 0, c->ndofs)) || (rc = ensure_stage(c, 1, 2 * (size_t)c->nn)) ||
         (rc = ensure_stage(c, 2, 2 * (size_t)K + 2)) || (rc = ensure_stage(c, 3, tr)) ||
         (rc = ensure_stage(c, 4, tr)) || (rc = ensure_stage(c, 5, tr)) || (rc = ensure_stage(c, 6, (size_t)K + 1)) ||
-        (rc = ensure_parked(c, (size_t)K + 1)))
+        (rc = ensure_stage(c, 7, tr)) || (rc = ensure_parked(c, (size_t)K + 1)))
         return rc;
     double *d_w = c->d_stage[0], *d_vel = c->d_stage[1], *d_x0 = c->d_stage[2], *d_x = c->d_stage[3],
-           *d_u = c->d_stage[4], *d_t = c->d_stage[5], *d_mask = c->d_stage[6];
+           *d_u = c->d_stage[4], *d_t = c->d_stage[5], *d_mask = c->d_stage[6], *d_t2 = c->d_stage[7];
     CUDA_OK(c, cudaMemcpyAsync(d_w, h_w, sizeof(double) * c->ndofs, cudaMemcpyHostToDevice, s));
     CUDA_OK(c, cudaMemcpyAsync(d_x0, h_x0, sizeof(double) * 2 * K, cudaMemcpyHostToDevice, s));
     CUDA_OK(c, cudaMemcpyAsync(d_mask, h_mask, sizeof(double) * K, cudaMemcpyHostToDevice, s));
     launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, d_w, d_vel, s);
     launch_cell_records(c->tab, d_vel, c->d_cellvel, nullptr, nullptr, s);
     launch_buoy_forward(c->tab, c->d_cellvel, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, nullptr, d_mask, c->d_parked, s);
+    // both result arrays go back in the reference's (K,nt,2) layout; each has its own staging buffer, so the
+    // two transposes and the two device-to-host copies are queued back to back without a host round trip in between
     launch_traj_transpose(d_x, d_t, K, c->nt, 0, s);
+    launch_traj_transpose(d_u, d_t2, K, c->nt, 0, s);
     CUDA_OK(c, cudaMemcpyAsync(h_x, d_t, sizeof(double) * tr, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(c, cudaStreamSynchronize(s));   // d_t is reused for u
-    launch_traj_transpose(d_u, d_t, K, c->nt, 0, s);
-    CUDA_OK(c, cudaMemcpyAsync(h_u, d_t, sizeof(double) * tr, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(c, cudaMemcpyAsync(h_u, d_t2, sizeof(double) * tr, cudaMemcpyDeviceToHost, s));
     CUDA_OK(c, cudaMemcpyAsync(h_mask, d_mask, sizeof(double) * K, cudaMemcpyDeviceToHost, s));
     CUDA_OK(c, cudaStreamSynchronize(s));
     CUDA_OK(c, cudaGetLastError());
@@ -875,6 +876,42 @@ int ocp_comm_nccl_version(void) { return comm_nccl_version(); }
 int ocp_allreduce(ocp_ctx *c, double *d_buf, size_t n) {
     if (!c || (!d_buf && n)) return OCP_ERR_INVALID;
     return c->comm.allreduce_sum(d_buf, n, c->stream, c->err) ? OCP_OK : OCP_ERR_COMM;
+}
+
+// ---- measurement helpers ------------------------------------------------------------------------------------------
+
+void ocp_get_solver_info(const ocp_ctx *c, double *out8) {
+    if (!c || !out8) return;
+    for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+    if (!c->lu_fwd.use_mf) return;
+    const MultifrontalLU &m = c->lu_fwd.mf;
+    out8[0] = m.flops();
+    out8[1] = (double)m.factor_nnz();
+    out8[2] = m.levels();
+    out8[3] = m.max_front();
+    out8[4] = (double)m.workspace_doubles();
+    out8[5] = c->lu_mass.use_mf ? c->lu_mass.mf.flops() : 0.0;
+    out8[6] = c->lu_mass.use_mf ? (double)c->lu_mass.mf.factor_nnz() : 0.0;
+    out8[7] = m.fronts();
+}
+
+int ocp_selftest_fp64_peak(ocp_ctx *c, double *tflops) {
+    if (!c || !tflops) return OCP_ERR_INVALID;
+    int rc = ensure_scratch(c, 148 * 8 * 256);
+    if (rc != OCP_OK) return rc;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(c->ev0, c->stream);
+        const double flop = launch_fp64_peak(c->d_scratch, 148 * 8, 256, 16384, c->stream);
+        cudaEventRecord(c->ev1, c->stream);
+        CUDA_OK(c, cudaEventSynchronize(c->ev1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        if (rep > 0 && ms > 0.f) best = std::max(best, flop / (ms * 1e-3) * 1e-12);
+    }
+    *tflops = best;
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
 }
 
 long long ocp_launch_count(void) { return ocp::g_launch_count.load(); }

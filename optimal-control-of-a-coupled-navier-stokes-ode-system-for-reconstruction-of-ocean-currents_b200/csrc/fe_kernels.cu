@@ -305,6 +305,18 @@ spmv_residual_kernel(int n, const int *__restrict__ rowptr, const int *__restric
     if (lane == 0) r[row] = b[row] - s;
 }
 
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(double *out, int iters) {
+    const double y = 0.99999999, x = 1e-9 * (threadIdx.x + 1);
+    double a0 = x, a1 = 2 * x, a2 = 3 * x, a3 = 4 * x, a4 = 5 * x, a5 = 6 * x, a6 = 7 * x, a7 = 8 * x;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, y, x); a1 = fma(a1, y, x); a2 = fma(a2, y, x); a3 = fma(a3, y, x);
+        a4 = fma(a4, y, x); a5 = fma(a5, y, x); a6 = fma(a6, y, x); a7 = fma(a7, y, x);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
@@ -393,6 +405,12 @@ void launch_field_norms(int nc, const double *geom, const int *cell_dofs, const 
                         double *scratch, unsigned *counter, cudaStream_t s) {
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     field_norms_kernel<<<cdiv(nc, 128), 128, 0, s>>>(nc, geom, cell_dofs, w, out3, scratch, counter);
+}
+
+double launch_fp64_peak(double *out, int blocks, int threads, int iters, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    fp64_peak_kernel<<<blocks, threads, 0, s>>>(out, iters);
+    return 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
 }
 
 void launch_spmv_residual(int n, const int *rowptr, const int *col, const double *vals, const double *x,

@@ -66,4 +66,8 @@ void launch_field_norms(int nc, const double *geom, const int *cell_dofs, const 
 void launch_spmv_residual(int n, const int *rowptr, const int *col, const double *vals, const double *x,
                           const double *b, double *r, cudaStream_t s);                   // r = b - A x
 
+// register-resident DFMA loop (8 independent chains per thread): the fp64 FMA-pipe peak the LU roofline is quoted
+// against; returns the flop count of the launch
+double launch_fp64_peak(double *out, int blocks, int threads, int iters, cudaStream_t s);
+
 }  // namespace ocp

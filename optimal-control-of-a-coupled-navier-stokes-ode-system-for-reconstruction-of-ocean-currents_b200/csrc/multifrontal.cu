@@ -1454,6 +1454,8 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     for (int s = 0; s < S.nnodes; ++s)
         factor_nnz_ += (long long)S.m[s] * S.m[s] - (long long)(S.m[s] - S.np[s]) * (S.m[s] - S.np[s]);
     flops_ = S.flops;
+    fsize_ = S.fsize;
+    nfronts_ = S.nnodes;
     nlevels_ = S.nlevels;
     max_front_ = S.max_front;
     analyse_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -31,13 +31,16 @@ class MultifrontalLU {
     double flops() const { return flops_; }
     int levels() const { return nlevels_; }
     int max_front() const { return max_front_; }
+    int fronts() const { return nfronts_; }
+    long long workspace_doubles() const { return fsize_; }
     double analyse_ms = 0.0;
 
   private:
     struct Impl;
     Impl *impl_ = nullptr;
     int n_ = 0, nnz_ = 0, nlevels_ = 0, max_front_ = 0;
-    long long factor_nnz_ = 0;
+    long long factor_nnz_ = 0, fsize_ = 0;
+    int nfronts_ = 0;
     double flops_ = 0.0;
 };
 
