@@ -199,3 +199,72 @@ def test_solve_adjoint_ode_host_entry_point_matches_oracle():
     assert H.rel(mu, muo) < 1e-12
     assert np.all(mu[mo != 0] == 0)
     ocp.close()
+
+
+def _nccl_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, H.ROOT)
+    sys.path.insert(0, os.path.join(H.ROOT, "tests"))
+    import torch.distributed as dist
+    from ocp_b200.sharding import shard_buoys
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        V = H.square32()
+        xr, ud = H.traj(400)
+        x0, ud_loc = shard_buoys(xr[:, 0, :].copy(), ud, rank, world)
+        ocp = OCP(V, Parameters(), x0, ud_loc, device=torch.device("cuda", rank), group=dist.group.WORLD)
+        assert ocp.ctx.comm_size() == world                      # the library owns an NCCL communicator
+        f = initial_control(V, "PL")
+        ocp.set_control(f)
+        ocp.gradient_step(ocp.d_f)
+        acc = ocp.d_acc.cpu().numpy()
+        z = ocp.d_z.cpu().numpy()
+        # the C-ABI host call with the collective inside
+        ocp.ctx.set_observations_host(x0, ud_loc)
+        w2, z2, mask2, sc = ocp.ctx.gradient_host(f)
+        q.put((rank, acc, z, z2, sc["misfit"], sc["n_masked"]))
+        ocp.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL refuses two ranks on one device)")
+def test_nccl_allreduce_inside_the_library_two_gpus():
+    """SURVEY 8(e) on hardware: 400 buoys sharded over two GPUs, the accumulator summed by ncclAllReduce INSIDE
+    libocp_b200 (ocp_comm_init / ocp_allreduce), against the single-GPU run and the oracle."""
+    import torch.multiprocessing as mp
+    V = H.square32()
+    xr, ud = H.traj(400)
+    x0 = xr[:, 0, :].copy()
+    f = initial_control(V, "PL")
+    ocp = OCP(V, Parameters(), x0, ud, device=dev())
+    ocp.set_control(f)
+    ocp.gradient_step(ocp.d_f)
+    acc1, z1 = ocp.d_acc.cpu().numpy(), ocp.d_z.cpu().numpy()
+    ocp.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        r = q.get(timeout=600)
+        got[r[0]] = r[1:]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    nn2 = 2 * V.num_nodes
+    for rank in (0, 1):
+        acc, z, z2, misfit, nmask = got[rank]
+        assert H.rel(acc[:nn2], acc1[:nn2]) < 1e-12
+        assert abs(acc[nn2] - acc1[nn2]) <= 1e-12 * abs(acc1[nn2]) and acc[nn2 + 1] == acc1[nn2 + 1]
+        assert H.rel(z, z1) < 1e-10 and H.rel(z2, z1) < 1e-10
+        assert abs(misfit - acc1[nn2]) <= 1e-12 * abs(acc1[nn2]) and nmask == int(acc1[nn2 + 1])
+    assert np.array_equal(got[0][0], got[1][0])                 # identical on both ranks after the all-reduce
+    s = H.OraclePipeline(V, 1.0, x0, ud, 1e-6 * 400).gradient_step(f)
+    assert H.rel(got[0][0][:nn2].reshape(-1, 2), s["bnode"]) < 1e-11 and H.rel(got[0][1], s["z"]) < 1e-9
