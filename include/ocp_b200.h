@@ -101,6 +101,15 @@ void ocp_set_viscosity(ocp_ctx *ctx, double viscosity);
  * the reference's u_d data constrains the whole boundary and one pressure line with non-zero data
  * (plotting/ud_construction_pipeline.py:95-106). */
 int ocp_set_dirichlet(ocp_ctx *ctx, const int32_t *h_dofs, const double *h_vals, int n);
+/* Reproducible point-source deposit (also: environment OCP_DETERMINISTIC=1).  Off (default): the deposits of
+ * OCP_dolfin.py:353-366 are summed with fp64 atomics, so the last bits of b change from run to run with the arrival
+ * order of the threads.  On: every deposit is split exactly into fixed-point digits that are accumulated with 64-bit
+ * INTEGER atomics (associative), which makes b - hence z, the gradient and the control update - bit-identical from
+ * run to run, independent of launch geometry; it agrees with the atomic variant to round-off (1e-12 tested). */
+int ocp_set_deterministic(ocp_ctx *ctx, int on);
+/* Current value of an option: "deterministic", "buoy_staged" (mesh tables staged in shared memory by TMA bulk
+ * copies: chosen automatically when they fit an SM, environment OCP_BUOY_STAGED=0 disables), "adj_reuse"; -1 unknown. */
+int ocp_get_option(const ocp_ctx *ctx, const char *name);
 /* Per-phase line-item timing (ocp_get_solver_stats) synchronises the stream after every phase; it is therefore off
  * by default and switched on only for profiling runs (also: environment OCP_PROFILE=1). */
 void ocp_set_profiling(ocp_ctx *ctx, int on);

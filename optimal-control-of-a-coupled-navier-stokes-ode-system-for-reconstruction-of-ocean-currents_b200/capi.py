@@ -22,6 +22,7 @@ ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "sparse solver error", -
 SYMBOLS = [
     "ocp_version", "ocp_device_available", "ocp_create", "ocp_destroy", "ocp_last_error",
     "ocp_get_solver_stats", "ocp_reset_solver_stats", "ocp_set_viscosity", "ocp_set_profiling", "ocp_set_dirichlet",
+    "ocp_set_deterministic", "ocp_get_option",
     "ocp_forward_solve", "ocp_assemble_forward", "ocp_assemble_adjoint", "ocp_project_grad",
     "ocp_velocity_nodal", "ocp_buoy_forward", "ocp_buoy_adjoint_scatter", "ocp_misfit",
     "ocp_adjoint_solve", "ocp_boundary_inner", "ocp_nodal_axpby", "ocp_field_norms", "ocp_traj_transpose",
@@ -82,6 +83,8 @@ def load_library() -> C.CDLL:
         lib.ocp_set_profiling.restype = None
         lib.ocp_selftest_cell_matrix.restype = None
         lib.ocp_selftest_facet_matrix.restype = None
+        lib.ocp_get_option.argtypes = [C.c_void_p, C.c_char_p]
+        lib.ocp_set_deterministic.argtypes = [C.c_void_p, C.c_int]
         lib.ocp_get_solver_info.restype = None
         lib.ocp_get_solver_info.argtypes = [C.c_void_p, C.c_void_p]
         lib.ocp_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -197,6 +200,13 @@ class Context:
         v = None if vals is None else np.ascontiguousarray(vals, np.float64)
         self._check(self.lib.ocp_set_dirichlet(self._h, _hp(dofs), _hp(v) if v is not None else C.c_void_p(0),
                                                int(dofs.size)), "ocp_set_dirichlet")
+
+    def set_deterministic(self, on: bool):
+        """Reproducible (integer fixed-point) point-source deposit instead of fp64 atomics."""
+        self._check(self.lib.ocp_set_deterministic(self._h, int(bool(on))), "ocp_set_deterministic")
+
+    def option(self, name: str) -> int:
+        return int(self.lib.ocp_get_option(self._h, name.encode()))
 
     def set_viscosity(self, nu: float):
         self.lib.ocp_set_viscosity(self._h, float(nu))

@@ -1,11 +1,20 @@
 // Buoy sweeps: one thread per buoy, trajectories time-major so that a warp's loads/stores are
-// 512-byte contiguous runs.  The FE tables (cell geometry 48 B, cell nodes 24 B, nodal velocity
-// 16 B, nodal gradient 32 B) are read through the read-only path and live in L1/L2.
+// 512-byte contiguous runs.
 //
 //   buoy_forward_kernel          solve_primal_ode            OCP_dolfin.py:201-230
 //   buoy_adjoint_scatter_kernel  solve_adjoint_ode           OCP_dolfin.py:234-252
 //                                + PointSource loop          OCP_dolfin.py:353-366
 //                                + partA of J                OCP_dolfin.py:259
+//
+// Two table paths, same arithmetic (bit-identical results):
+//   * STAGED (kStaged = true): the mesh tables a sweep reads per sample - cell geometry (48 B / cell), cell -> node
+//     map (24 B / cell), nodal velocity (16 B / node) or nodal projected gradient (32 B / vertex) - are copied ONCE per
+//     CTA into shared memory with TMA bulk copies (cp.async.bulk + mbarrier transaction count) by a persistent
+//     grid of one CTA per SM; every per-sample table access is then a shared-memory load (~25 cycles) instead of an
+//     L1/L2 round trip on the dependent chain locate -> evaluate -> advance.  Used whenever the tables fit the
+//     227 KB of an SM (the reference's 32 x 32 mesh: 215 KB forward, 182 KB backward).
+//   * GLOBAL (kStaged = false): per-cell coefficient records (cellvel / cellg, rebuilt whenever the state changes) read
+//     through the read-only path; refined meshes (cfg5) whose tables exceed shared memory.
 #include <algorithm>
 
 #include "element_math.cuh"
@@ -16,92 +25,184 @@ namespace ocp {
 namespace {
 
 constexpr int kBuoyThreads = 128;
+constexpr int kStagedMaxThreads = 512;      // 16 warps x 128 registers fill one SM's register file (no spills)
+constexpr int kDepthLarge = 2;              // samples of the input streams in flight per thread in large launches
+constexpr int kDepthSmall = 4;              // ... in small launches (one warp per scheduler)
+constexpr size_t kSmemBudget = 227 * 1024 - 1024;   // dynamic shared memory we allow ourselves per CTA
 
-__device__ __forceinline__ void load_geom(const DeviceTables &t, int c, double g[6]) {
-    const double2 *p = reinterpret_cast<const double2 *>(t.geom) + 3 * (size_t)c;
-    const double2 a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);
+// ---- TMA bulk copy (global -> shared) completing on an mbarrier ------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// bytes: multiple of 16, src / dst 16-byte aligned.  Issued in pieces of 32 KiB so that several are in flight.
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    for (unsigned off = 0; off < bytes; off += 32768u) {
+        const unsigned n = min(32768u, bytes - off);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(static_cast<char *>(dst) + off)),
+                     "l"(static_cast<const char *>(src) + off), "r"(n), "r"(smem_addr(bar))
+                     : "memory");
+    }
+}
+
+// ---- table access: shared memory (staged) or the read-only global path ------------------------------------------
+template <bool S>
+__device__ __forceinline__ double2 ld2(const double2 *p) {
+    if (S) return *p;
+    return __ldg(p);
+}
+template <bool S>
+__device__ __forceinline__ int2 ldi2(const int2 *p) {
+    if (S) return *p;
+    return __ldg(p);
+}
+
+template <bool S>
+__device__ __forceinline__ void load_geom(const double *geom, int c, double g[6]) {
+    const double2 *p = reinterpret_cast<const double2 *>(geom) + 3 * (size_t)c;
+    const double2 a = ld2<S>(p), b = ld2<S>(p + 1), d = ld2<S>(p + 2);
     g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y; g[4] = d.x; g[5] = d.y;
 }
 
-__device__ __forceinline__ void load_nodes(const DeviceTables &t, int c, int n[6]) {
-    const int2 *p = reinterpret_cast<const int2 *>(t.cell_nodes) + 3 * (size_t)c;
-    const int2 a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);
+template <bool S>
+__device__ __forceinline__ void load_nodes(const int *cell_nodes, int c, int n[6]) {
+    const int2 *p = reinterpret_cast<const int2 *>(cell_nodes) + 3 * (size_t)c;
+    const int2 a = ldi2<S>(p), b = ldi2<S>(p + 1), d = ldi2<S>(p + 2);
     n[0] = a.x; n[1] = a.y; n[2] = b.x; n[3] = b.y; n[4] = d.x; n[5] = d.y;
 }
 
-// Lowest-index cell whose barycentrics are all >= -tol (the oracle's definition of dolfin's "first colliding cell").
+// Definition of the point location (the oracle's restatement of dolfin's "first colliding cell"): the lowest-index
+// cell of the point's bin whose barycentrics are all >= -tol; -1 = dolfin's "point outside" error.
+// WARP-COOPERATIVE: the lanes of a warp that need this slow path are served one after the other, and for each of them
+// all 32 lanes test 32 candidate cells of its bin at once (ballot + find-first-set keeps "lowest index"); the lane that
+// asked then recomputes its barycentrics for the winning cell, so the result is bit-identical to a serial scan.
+// `need` must be warp-uniform-convergent: every lane of the (converged) warp calls this, lanes with need == false
+// only help.
+template <bool S>
+__device__ __forceinline__ int locate_bins_warp(const DeviceTables &t, const double *geom, bool need, double x, double y,
+                                                double &l0, double &l1, double &l2) {
+    const unsigned active = 0xffffffffu;        // call sites keep the warp converged (uniform trip counts)
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(active, need);
+    int result = -1;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const double sx = __shfl_sync(active, x, src), sy = __shfl_sync(active, y, src);
+        const double fx = floor(OCP_MUL(OCP_SUB(sx, t.ox), t.ihx));
+        const double fy = floor(OCP_MUL(OCP_SUB(sy, t.oy), t.ihy));
+        const int ix = fx < 0.0 ? 0 : (fx > (double)(t.nbx - 1) ? t.nbx - 1 : (int)fx);
+        const int iy = fy < 0.0 ? 0 : (fy > (double)(t.nby - 1) ? t.nby - 1 : (int)fy);
+        const int bin = iy * t.nbx + ix;
+        const int j0 = __ldg(t.bin_ptr + bin), j1 = __ldg(t.bin_ptr + bin + 1);
+        int found = -1;
+        const int rank = lane, width = 32;
+        for (int jb = j0; jb < j1 && found < 0; jb += width) {
+            const int j = jb + rank;
+            bool hit = false;
+            int c = -1;
+            if (j < j1) {
+                c = __ldg(t.bin_cells + j);
+                double g[6], a0, a1, a2;
+                load_geom<S>(geom, c, g);
+                bary(g, sx, sy, a0, a1, a2);
+                hit = a0 >= -kLocateTol && a1 >= -kLocateTol && a2 >= -kLocateTol;
+            }
+            const unsigned hits = __ballot_sync(active, hit);
+            if (hits) found = __shfl_sync(active, c, __ffs(hits) - 1);     // candidates ascend with the lane rank
+        }
+        if (lane == src) result = found;
+    }
+    if (need && result >= 0) {
+        double g[6];
+        load_geom<S>(geom, result, g);
+        bary(g, x, y, l0, l1, l2);
+    }
+    return result;
+}
+
+// Lowest-index cell whose barycentrics are all >= -tol.
 //   1. `hint` (previous cell): accepted when the point is strictly inside (margin 1e-9) - then no other cell can
 //      contain it, so the answer equals the definition.
 //   2. neighbour walk: leave through the edge with the most negative barycentric, at most 4 hops, again accepting
 //      only strictly-inside hits.  This is what a buoy crossing into the next cell costs (one or two hops).
 //   3. anything ambiguous (on an edge/vertex within the margin, outside the mesh, far jump): the definition itself,
-//      ascending scan of the bin's candidate list.
-// -1 = dolfin's "point outside" error.
-__device__ __forceinline__ int locate(const DeviceTables &t, double x, double y, int hint, double &l0, double &l1,
-                                      double &l2) {
-    if (!(x == x) || !(y == y)) return -1;
-    double g[6];
-    if (hint >= 0) {
-        int c = hint;
+//      searched warp-cooperatively (locate_bins_warp).
+// `alive`: lanes whose buoy has already finished pass false and only help their warp in step 3.
+template <bool S>
+__device__ __forceinline__ int locate(const DeviceTables &t, const double *geom, bool alive, double x, double y, int hint,
+                                      double &l0, double &l1, double &l2) {
+    bool need = alive;
+    int c = -1;
+    if (alive && (!(x == x) || !(y == y))) need = false;      // NaN position: "outside"
+    if (need && hint >= 0) {
+        double g[6];
+        c = hint;
 #pragma unroll 1
         for (int hop = 0; hop < 5; ++hop) {
-            load_geom(t, c, g);
+            load_geom<S>(geom, c, g);
             bary(g, x, y, l0, l1, l2);
-            if (l0 > kLocateMargin && l1 > kLocateMargin && l2 > kLocateMargin) return c;
+            if (l0 > kLocateMargin && l1 > kLocateMargin && l2 > kLocateMargin) {
+                need = false;
+                break;
+            }
             const double lm = fmin(l0, fmin(l1, l2));
             if (lm >= -kLocateTol) break;                       // within the tie zone of an edge: use the definition
             const int e = (l0 == lm) ? 0 : ((l1 == lm) ? 1 : 2);
             c = __ldg(t.cell_nbr + 3 * (size_t)c + e);
             if (c < 0) break;
         }
+        if (need) c = -1;
     }
-    const double fx = floor(OCP_MUL(OCP_SUB(x, t.ox), t.ihx));
-    const double fy = floor(OCP_MUL(OCP_SUB(y, t.oy), t.ihy));
-    const int ix = fx < 0.0 ? 0 : (fx > (double)(t.nbx - 1) ? t.nbx - 1 : (int)fx);
-    const int iy = fy < 0.0 ? 0 : (fy > (double)(t.nby - 1) ? t.nby - 1 : (int)fy);
-    const int b = iy * t.nbx + ix;
-    const int j1 = __ldg(t.bin_ptr + b + 1);
-    for (int j = __ldg(t.bin_ptr + b); j < j1; ++j) {
-        const int c = __ldg(t.bin_cells + j);
-        load_geom(t, c, g);
-        bary(g, x, y, l0, l1, l2);
-        if (l0 >= -kLocateTol && l1 >= -kLocateTol && l2 >= -kLocateTol) return c;
+    if (__any_sync(0xffffffffu, need)) {
+        const int r = locate_bins_warp<S>(t, geom, need, x, y, l0, l1, l2);
+        if (need) c = r;
     }
-    return -1;
+    return c;
 }
 
-__device__ __forceinline__ void eval_p2(const DeviceTables &t, const double2 *__restrict__ vel, int c, double l0,
+// P2 velocity at barycentrics (l0,l1,l2) of cell c.  Staged: nodal field + cell -> node map in shared memory; global:
+// the per-cell coefficient record (12 doubles, contiguous).  Same operation order either way.
+template <bool S>
+__device__ __forceinline__ void eval_p2(const double2 *__restrict__ vel, const int *cell_nodes, int c, double l0,
                                         double l1, double l2, double &ux, double &uy) {
     double phi[6];
-    int n[6];
     p2_basis(l0, l1, l2, phi);
-    load_nodes(t, c, n);
-    double2 v = __ldg(vel + n[0]);
-    double sx = OCP_MUL(phi[0], v.x), sy = OCP_MUL(phi[0], v.y);
+    double2 v[6];
+    if (S) {
+        int n[6];
+        load_nodes<true>(cell_nodes, c, n);
 #pragma unroll
-    for (int i = 1; i < 6; ++i) {
-        v = __ldg(vel + n[i]);
-        sx = OCP_FMA(phi[i], v.x, sx);
-        sy = OCP_FMA(phi[i], v.y, sy);
+        for (int i = 0; i < 6; ++i) v[i] = vel[n[i]];
+    } else {
+        const double2 *r = vel + 6 * (size_t)c;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[i] = __ldg(r + i);
     }
-    ux = sx;
-    uy = sy;
-}
-
-// P2 velocity from the per-cell coefficient record (12 doubles: (u_x, u_y) of the cell's six nodes, contiguous), same
-// operation order as eval_p2 - the record only replaces the node-index indirection by one contiguous 96-byte read.
-__device__ __forceinline__ void eval_p2_cell(const double2 *__restrict__ cellvel, int c, double l0, double l1,
-                                             double l2, double &ux, double &uy) {
-    double phi[6];
-    p2_basis(l0, l1, l2, phi);
-    const double2 *r = cellvel + 6 * (size_t)c;
-    double2 v = __ldg(r);
-    double sx = OCP_MUL(phi[0], v.x), sy = OCP_MUL(phi[0], v.y);
+    double sx = OCP_MUL(phi[0], v[0].x), sy = OCP_MUL(phi[0], v[0].y);
 #pragma unroll
     for (int i = 1; i < 6; ++i) {
-        v = __ldg(r + i);
-        sx = OCP_FMA(phi[i], v.x, sx);
-        sy = OCP_FMA(phi[i], v.y, sy);
+        sx = OCP_FMA(phi[i], v[i].x, sx);
+        sy = OCP_FMA(phi[i], v[i].y, sy);
     }
     ux = sx;
     uy = sy;
@@ -122,66 +223,136 @@ __global__ void cell_records_kernel(int nc, const int *__restrict__ cell_nodes, 
     }
 }
 
-__global__ void __launch_bounds__(kBuoyThreads)
-buoy_forward_kernel(DeviceTables t, const double2 *__restrict__ vel /* per-cell records */, const double2 *__restrict__ x0, int K, int nt,
-                    double h, double cx, double cy, double2 *__restrict__ x, double2 *__restrict__ u,
-                    int *__restrict__ cell, double *__restrict__ mask, uint8_t *__restrict__ parked) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= K) return;
-    double2 p = x0[b];
-    int hint = -1, kfail = -1;
-    double l0, l1, l2;
-    for (int k = 0; k < nt - 1; ++k) {
-        const int c = locate(t, p.x, p.y, hint, l0, l1, l2);
-        if (c < 0) {
-            kfail = k;
-            break;
-        }
-        double ux, uy;
-        eval_p2_cell(vel, c, l0, l1, l2, ux, uy);
-        const size_t o = (size_t)k * K + b;
-        x[o] = p;
-        u[o] = make_double2(ux, uy);
-        if (cell) cell[o] = c;
-        p.x = OCP_ADD(p.x, OCP_MUL(h, ux));      // two roundings, as numpy at OCP_dolfin.py:212
-        p.y = OCP_ADD(p.y, OCP_MUL(h, uy));
-        hint = c;
+// Shared-memory image of the mesh tables of a staged sweep.  Every region starts 16-byte aligned; the bulk of each
+// table arrives through TMA bulk copies, a tail shorter than 16 bytes through plain loads.
+struct StagedTables {
+    const double *geom;
+    const int *nodes;
+    const double2 *field;      // nodal velocity (forward) or nodal projected gradient, 2 x double2 per vertex (backward)
+};
+
+__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+__host__ __device__ inline size_t staged_bytes(int nc, size_t field_bytes) {
+    return align16(48 * (size_t)nc) + align16(field_bytes) + align16(24 * (size_t)nc);
+}
+
+__device__ __forceinline__ void stage_one(void *dst, const void *src, size_t bytes, unsigned long long *bar) {
+    const unsigned bulk = (unsigned)(bytes & ~(size_t)15);
+    if (bulk) bulk_copy_g2s(dst, src, bulk, bar);
+    for (size_t i = bulk; i < bytes; i += 4)      // tail (tables are arrays of 4- or 8-byte items)
+        *reinterpret_cast<int *>(static_cast<char *>(dst) + i) = *reinterpret_cast<const int *>(static_cast<const char *>(src) + i);
+}
+
+// One elected thread arms the mbarrier with the byte count and issues the bulk copies; everybody waits on the barrier.
+__device__ __forceinline__ StagedTables stage_tables(unsigned char *smem, unsigned long long *bar, const DeviceTables &t,
+                                                    const void *field, size_t field_bytes) {
+    const size_t gb = 48 * (size_t)t.nc, nb = 24 * (size_t)t.nc;
+    unsigned char *s_geom = smem, *s_field = s_geom + align16(gb), *s_nodes = s_field + align16(field_bytes);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, (unsigned)((gb & ~(size_t)15) + (field_bytes & ~(size_t)15) + (nb & ~(size_t)15)));
+        stage_one(s_geom, t.geom, gb, bar);
+        stage_one(s_field, field, field_bytes, bar);
+        stage_one(s_nodes, t.cell_nodes, nb, bar);
     }
-    if (kfail < 0) {
-        // trailing evaluation at the last sample, OCP_dolfin.py:223-229
-        const size_t o = (size_t)(nt - 1) * K + b;
-        const int c = locate(t, p.x, p.y, hint, l0, l1, l2);
-        if (c >= 0) {
-            double ux, uy;
-            eval_p2_cell(vel, c, l0, l1, l2, ux, uy);
-            x[o] = p;
-            u[o] = make_double2(ux, uy);
-            if (cell) cell[o] = c;
+    __syncthreads();
+    mbar_wait(bar, 0);
+    StagedTables st;
+    st.geom = reinterpret_cast<const double *>(s_geom);
+    st.field = reinterpret_cast<const double2 *>(s_field);
+    st.nodes = reinterpret_cast<const int *>(s_nodes);
+    return st;
+}
+
+// solve_primal_ode.  S = staged tables (`field` = NODAL velocity (nn), persistent grid, `per_block` buoys per CTA pass)
+// or global tables (`field` = per-cell records).  All lanes of a warp run the same trip counts (finished or padding
+// lanes idle) so that the warp-cooperative slow path of the point location always sees a converged warp.
+template <bool S>
+__global__ void __launch_bounds__(S ? kStagedMaxThreads : kBuoyThreads, 1)
+buoy_forward_kernel(DeviceTables t, const double2 *__restrict__ field, const double2 *__restrict__ x0, int K,
+                    int per_block, int nt, double h, double cx, double cy, double2 *__restrict__ x,
+                    double2 *__restrict__ u, int *__restrict__ cell, double *__restrict__ mask,
+                    uint8_t *__restrict__ parked) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ unsigned long long bar;
+    const double *geom = t.geom;
+    const int *nodes = t.cell_nodes;
+    const double2 *vel = field;
+    if (S) {
+        const StagedTables st = stage_tables(smem_raw, &bar, t, field, 16 * (size_t)t.nn);
+        geom = st.geom;
+        nodes = st.nodes;
+        vel = st.field;
+    }
+    for (long long base = (long long)blockIdx.x * per_block; base < K; base += (long long)gridDim.x * per_block) {
+        const long long bl = base + threadIdx.x;
+        const bool alive = (int)threadIdx.x < per_block && bl < K;
+        const int b = alive ? (int)bl : 0;
+        double2 p = alive ? x0[b] : make_double2(cx, cy);
+        int hint = -1, kfail = -1;
+        double l0, l1, l2;
+        for (int k = 0; k < nt - 1; ++k) {
+            const bool run = alive && kfail < 0;
+            const int c = locate<S>(t, geom, run, p.x, p.y, hint, l0, l1, l2);
+            if (run) {
+                if (c < 0) {
+                    kfail = k;
+                } else {
+                    double ux, uy;
+                    eval_p2<S>(vel, nodes, c, l0, l1, l2, ux, uy);
+                    const size_t o = (size_t)k * K + b;
+                    x[o] = p;
+                    u[o] = make_double2(ux, uy);
+                    if (cell) cell[o] = c;
+                    p.x = OCP_ADD(p.x, OCP_MUL(h, ux));      // two roundings, as numpy at OCP_dolfin.py:212
+                    p.y = OCP_ADD(p.y, OCP_MUL(h, uy));
+                    hint = c;
+                }
+            }
+        }
+        {
+            // trailing evaluation at the last sample, OCP_dolfin.py:223-229
+            const bool run = alive && kfail < 0;
+            const int c = locate<S>(t, geom, run, p.x, p.y, hint, l0, l1, l2);
+            if (run) {
+                const size_t o = (size_t)(nt - 1) * K + b;
+                if (c >= 0) {
+                    double ux, uy;
+                    eval_p2<S>(vel, nodes, c, l0, l1, l2, ux, uy);
+                    x[o] = p;
+                    u[o] = make_double2(ux, uy);
+                    if (cell) cell[o] = c;
+                    parked[b] = 0;
+                } else {
+                    x[o] = make_double2(cx, cy);
+                    u[o] = make_double2(0.0, 0.0);
+                    if (cell) cell[o] = -1;
+                    parked[b] = 1;
+                }
+            }
+        }
+        // the `except` branch, OCP_dolfin.py:213-221: park the whole trajectory at the centre, mask the buoy;
+        // samples 0..kfail-1 keep their velocities, sample kfail stays 0, sample kfail+1 gets u(centre)
+        const bool failed = alive && kfail >= 0;
+        const int cc = locate<S>(t, geom, failed, cx, cy, -1, l0, l1, l2);
+        if (failed) {
+            mask[b] = 1.0;
             parked[b] = 0;
-        } else {
-            x[o] = make_double2(cx, cy);
-            u[o] = make_double2(0.0, 0.0);
-            if (cell) cell[o] = -1;
-            parked[b] = 1;
-        }
-        return;
-    }
-    // the `except` branch, OCP_dolfin.py:213-221: park the whole trajectory at the centre, mask the buoy;
-    // samples 0..kfail-1 keep their velocities, sample kfail stays 0, sample kfail+1 gets u(centre)
-    mask[b] = 1.0;
-    parked[b] = 0;
-    const int cc = locate(t, cx, cy, -1, l0, l1, l2);
-    double ucx = 0.0, ucy = 0.0;
-    if (cc >= 0) eval_p2_cell(vel, cc, l0, l1, l2, ucx, ucy);
-    for (int k = 0; k < nt; ++k) {
-        const size_t o = (size_t)k * K + b;
-        x[o] = make_double2(cx, cy);
-        if (k == kfail + 1) {
-            u[o] = make_double2(ucx, ucy);
-            if (cell) cell[o] = cc;
-        } else if (k >= kfail) {
-            u[o] = make_double2(0.0, 0.0);
-            if (cell) cell[o] = -1;
+            double ucx = 0.0, ucy = 0.0;
+            if (cc >= 0) eval_p2<S>(vel, nodes, cc, l0, l1, l2, ucx, ucy);
+            for (int k = 0; k < nt; ++k) {
+                const size_t o = (size_t)k * K + b;
+                x[o] = make_double2(cx, cy);
+                if (k == kfail + 1) {
+                    u[o] = make_double2(ucx, ucy);
+                    if (cell) cell[o] = cc;
+                } else if (k >= kfail) {
+                    u[o] = make_double2(0.0, 0.0);
+                    if (cell) cell[o] = -1;
+                }
+            }
         }
     }
 }
@@ -235,10 +406,10 @@ __device__ __forceinline__ void block_finish2(double a, double b, double *scratc
     }
 }
 
-__device__ __forceinline__ void flush_sources(double *__restrict__ bnode, const DeviceTables &t, int c,
-                                              double acc[12]) {
+template <bool S>
+__device__ __forceinline__ void flush_sources(double *__restrict__ bnode, const int *cell_nodes, int c, double acc[12]) {
     int n[6];
-    load_nodes(t, c, n);
+    load_nodes<S>(cell_nodes, c, n);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         atomicAdd(bnode + 2 * (size_t)n[i], acc[i]);
@@ -248,75 +419,168 @@ __device__ __forceinline__ void flush_sources(double *__restrict__ bnode, const 
     }
 }
 
+// ---- reproducible deposit (deterministic mode) ---------------------------------------------------------------------
+// A double is split EXACTLY into four signed digits of weights 2^-4, 2^-36, 2^-68, 2^-100 (values below 2^-100 ~ 8e-31
+// are dropped, magnitudes must stay below 2^27); the digits are accumulated with 64-bit INTEGER atomics, which are
+// associative and commutative - the sum does not depend on the order in which threads, CTAs, SMs or GPUs arrive, so
+// two runs (and sharded vs unsharded runs) give bit-identical point-source vectors.  finalize_exact_kernel turns the
+// digit sums back into doubles with one rounding.
+constexpr double kW3 = 16.0, kW2 = 68719476736.0 /* 2^36 */, kW1 = 295147905179352825856.0 /* 2^68 */,
+                 kW0 = 1267650600228229401496703205376.0 /* 2^100 */;
+
+__device__ __forceinline__ void exact_add(long long *slot /* 4 digits */, double v, long long *overflow) {
+    if (!(fabs(v) < 134217728.0)) {                  // NaN, Inf or beyond the fixed-point range (2^27)
+        atomicAdd(reinterpret_cast<unsigned long long *>(overflow), 1ull);
+        return;
+    }
+    const double d3 = rint(v * kW3);
+    double r = v - d3 * (1.0 / kW3);                 // exact: d3 / 16 is v rounded to a multiple of 2^-4
+    const double d2 = rint(r * kW2);
+    r -= d2 * (1.0 / kW2);
+    const double d1 = rint(r * kW1);
+    r -= d1 * (1.0 / kW1);
+    const double d0 = rint(r * kW0);
+    unsigned long long *u = reinterpret_cast<unsigned long long *>(slot);
+    if (d0 != 0.0) atomicAdd(u + 0, (unsigned long long)(long long)d0);
+    if (d1 != 0.0) atomicAdd(u + 1, (unsigned long long)(long long)d1);
+    if (d2 != 0.0) atomicAdd(u + 2, (unsigned long long)(long long)d2);
+    if (d3 != 0.0) atomicAdd(u + 3, (unsigned long long)(long long)d3);
+}
+
+template <bool S>
+__device__ __forceinline__ void flush_sources_exact(long long *__restrict__ digits, long long *overflow,
+                                                    const int *cell_nodes, int c, double acc[12]) {
+    int n[6];
+    load_nodes<S>(cell_nodes, c, n);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        exact_add(digits + 4 * (2 * (size_t)n[i]), acc[i], overflow);
+        exact_add(digits + 4 * (2 * (size_t)n[i] + 1), acc[6 + i], overflow);
+        acc[i] = 0.0;
+        acc[6 + i] = 0.0;
+    }
+}
+
+// out[i] += value of the digit sums of entry i.  The carries are propagated in integers first, so that the four
+// digits are non-overlapping 32-bit fields and the conversion rounds exactly once.
+__global__ void finalize_exact_kernel(int n, const long long *__restrict__ digits, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (digits[4 * (size_t)n] != 0) {       // a deposit was NaN / Inf / >= 2^27: do not hide it
+        out[i] = nan("");
+        return;
+    }
+    long long d0 = digits[4 * (size_t)i], d1 = digits[4 * (size_t)i + 1], d2 = digits[4 * (size_t)i + 2],
+              d3 = digits[4 * (size_t)i + 3];
+    // floor-division carries (arithmetic shift), digit in [0, 2^32)
+    long long c = d0 >> 32; d0 -= c << 32; d1 += c;
+    c = d1 >> 32; d1 -= c << 32; d2 += c;
+    c = d2 >> 32; d2 -= c << 32; d3 += c;
+    // value = d3 2^-4 + d2 2^-36 + d1 2^-68 + d0 2^-100 with non-overlapping digits: `hi` is exact for sums below
+    // 2^17, `lo` and the final addition round - a fixed function of the integer sums, error <= 1 ulp
+    const double hi = (double)d3 * (1.0 / kW3) + (double)d2 * (1.0 / kW2);
+    const double lo = (double)d1 * (1.0 / kW1) + (double)d0 * (1.0 / kW0);
+    out[i] += hi + lo;
+}
+
 // Backward sweep k = nt-1 .. 0.  Per sample: gamma_k = h((u_d - u(x_k)) + mu_k) is deposited as
 // gamma_c phi_i(x_k); deposits are accumulated in registers while the buoy stays in one cell and
 // flushed with 12 fp64 atomics when it changes cell (a buoy crosses a handful of cells per trajectory),
 // then mu_{k-1} = mu_k - h G(x_k)^T ((u_k - u_d,k) - mu_k).
-__global__ void __launch_bounds__(kBuoyThreads, 5)
-buoy_adjoint_scatter_kernel(DeviceTables t, const double2 *__restrict__ vel /* per-cell records */,
-                            const double2 *__restrict__ g /* per-cell vertex gradients */, int K,
-                            int nt, double h, double cx, double cy, const double2 *__restrict__ x,
-                            const double2 *__restrict__ u, const double2 *__restrict__ ud,
-                            const double *__restrict__ mask, const uint8_t *__restrict__ parked,
-                            double2 *__restrict__ mu, double *__restrict__ acc_out, double *scratch,
-                            unsigned *counter, double *__restrict__ bpriv, int nrep) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+//   S: staged tables (fieldv = NODAL velocity, fieldg = NODAL projected gradient (nv,4); persistent grid) or global
+//      tables (per-cell records cellvel / cellg).
+//   D: samples of the three input streams requested ahead (register ring): 2 for bandwidth-bound launches (16 warps
+//      per SM hide the rest), 4 for small launches where one warp per scheduler has to cover the HBM latency itself.
+//   X: reproducible integer deposit (deterministic mode) instead of fp64 atomics.
+template <bool S, int D, bool X>
+__global__ void __launch_bounds__(S ? (D == kDepthSmall ? 128 : kStagedMaxThreads) : kBuoyThreads, S ? 1 : 4)
+buoy_adjoint_scatter_kernel(DeviceTables t, const double2 *__restrict__ fieldv, const double2 *__restrict__ fieldg,
+                            int K, int per_block, int nt, double h, double cx, double cy,
+                            const double2 *__restrict__ x, const double2 *__restrict__ u,
+                            const double2 *__restrict__ ud, const double *__restrict__ mask,
+                            const uint8_t *__restrict__ parked, double2 *__restrict__ mu, double *__restrict__ acc_out,
+                            double *scratch, unsigned *counter, double *__restrict__ bpriv, int nrep,
+                            long long *__restrict__ digits) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ unsigned long long bar;
+    const double *geom = t.geom;
+    const int *nodes = t.cell_nodes;
+    const double2 *gtab = fieldg;
+    if (S) {
+        const StagedTables st = stage_tables(smem_raw, &bar, t, fieldg, 32 * (size_t)t.nv);
+        geom = st.geom;
+        nodes = st.nodes;
+        gtab = st.field;
+    }
     double misfit = 0.0, nmasked = 0.0;
     // point sources go to one of `nrep` private copies of b (selected by SM id) so that fp64 atomics of the
     // thousands of buoys sharing a cell do not serialise on 12 addresses; the copies are summed afterwards
     double *bdst = acc_out;
+    long long *ddst = digits;
     if (nrep > 1) {
         unsigned smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        bdst = bpriv + (size_t)(smid % (unsigned)nrep) * (2 * (size_t)t.nn);
+        const size_t copy = smid % (unsigned)nrep;
+        bdst = bpriv + copy * (2 * (size_t)t.nn);
+        if (X) ddst = digits + copy * (8 * (size_t)t.nn);
     }
-    if (b < K) {
-        const bool masked = mask[b] != 0.0;
-        const bool park = parked[b] != 0;
-        nmasked = masked ? 1.0 : 0.0;
+    for (long long base = (long long)blockIdx.x * per_block; base < K; base += (long long)gridDim.x * per_block) {
+        const long long bl = base + threadIdx.x;
+        const bool alive = (int)threadIdx.x < per_block && bl < K;
+        const int b = alive ? (int)bl : 0;
+        const bool masked = alive && mask[b] != 0.0;
+        const bool park = alive && parked[b] != 0;
+        if (masked) nmasked += 1.0;
+        const bool run = alive && !masked;
         double mux = 0.0, muy = 0.0;
         double acc[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) acc[i] = 0.0;
         int acc_cell = -1, hint = -1;
-        // the three streams are read one sample ahead so that their HBM latency overlaps the arithmetic
-        double2 pn = __ldcs(x + (size_t)(nt - 1) * K + b), Un = __ldcs(u + (size_t)(nt - 1) * K + b),
-                Dn = __ldcs(ud + (size_t)(nt - 1) * K + b);
-        for (int k = nt - 1; k >= 0; --k) {
+        auto flush = [&](int c) {
+            if (X)
+                flush_sources_exact<S>(ddst, digits + 8 * (size_t)t.nn * (nrep > 1 ? nrep : 1), nodes, c, acc);
+            else
+                flush_sources<S>(bdst, nodes, c, acc);
+        };
+        // one sample; every lane of the warp calls it (padding / masked lanes only help the cooperative search)
+        auto sample = [&](int k, double2 p, const double2 U, const double2 Dd) {
             const size_t o = (size_t)k * K + b;
-            double2 p = pn;
-            const double2 U = Un, D = Dn;
-            if (k > 0) {
-                pn = __ldcs(x + o - K);
-                Un = __ldcs(u + o - K);
-                Dn = __ldcs(ud + o - K);
-            }
-            const double ex = U.x - D.x, ey = U.y - D.y;
-            misfit += ex * ex + ey * ey;
-            if (masked) {
-                if (mu) __stcs(mu + o, make_double2(0.0, 0.0));
-                continue;
-            }
+            const double ex = U.x - Dd.x, ey = U.y - Dd.y;
+            if (alive) misfit += ex * ex + ey * ey;
+            if (masked && mu) __stcs(mu + o, make_double2(0.0, 0.0));
             double l0, l1, l2;
             double ukx = U.x, uky = U.y;
-            int c = locate(t, p.x, p.y, hint, l0, l1, l2);
-            if (c < 0) {            // `except` of OCP_dolfin.py:359-361: u_x = 0, point = centre
-                ukx = 0.0;
-                uky = 0.0;
-                p = make_double2(cx, cy);
-                c = locate(t, cx, cy, -1, l0, l1, l2);
-            } else if (park && k == nt - 1) {
+            int c = locate<S>(t, geom, run, p.x, p.y, hint, l0, l1, l2);
+            // `except` of OCP_dolfin.py:359-361: u_x = 0, point = centre
+            const bool lost = run && c < 0;
+            {
+                double m0, m1, m2;
+                const int cc = locate<S>(t, geom, lost, cx, cy, -1, m0, m1, m2);
+                if (lost) {
+                    ukx = 0.0;
+                    uky = 0.0;
+                    p = make_double2(cx, cy);
+                    c = cc;
+                    l0 = m0; l1 = m1; l2 = m2;
+                }
+            }
+            if (!run) return;
+            if (!lost && park && k == nt - 1 && c >= 0) {
                 // the stored velocity of a parked last sample is 0, the scatter loop re-evaluates u(centre)
-                eval_p2_cell(vel, c, l0, l1, l2, ukx, uky);
+                if (S)
+                    eval_p2<true>(fieldv, nodes, c, l0, l1, l2, ukx, uky);      // nodal field (global memory), rare
+                else
+                    eval_p2<false>(fieldv, nodes, c, l0, l1, l2, ukx, uky);
             }
             if (mu) __stcs(mu + o, make_double2(mux, muy));
             if (c >= 0) {
                 hint = c;
                 if (c != acc_cell) {
-                    if (acc_cell >= 0) flush_sources(bdst, t, acc_cell, acc);
+                    if (acc_cell >= 0) flush(acc_cell);
                     acc_cell = c;
                 }
-                const double gx = h * ((D.x - ukx) + mux), gy = h * ((D.y - uky) + muy);
+                const double gx = h * ((Dd.x - ukx) + mux), gy = h * ((Dd.y - uky) + muy);
                 double phi[6];
                 p2_basis(l0, l1, l2, phi);
 #pragma unroll
@@ -326,9 +590,18 @@ buoy_adjoint_scatter_kernel(DeviceTables t, const double2 *__restrict__ vel /* p
                 }
                 if (k > 0) {
                     // continuous P1 tensor at the cell's three vertices, [g00 g01 | g10 g11] per vertex
-                    const double2 *gr = g + 6 * (size_t)c;
-                    const double2 a0 = __ldg(gr), a1 = __ldg(gr + 1), b0 = __ldg(gr + 2), b1 = __ldg(gr + 3),
-                                  c0 = __ldg(gr + 4), c1 = __ldg(gr + 5);
+                    double2 a0, a1, b0, b1, c0, c1;
+                    if (S) {
+                        int n[6];
+                        load_nodes<true>(nodes, c, n);
+                        a0 = gtab[2 * n[0]]; a1 = gtab[2 * n[0] + 1];
+                        b0 = gtab[2 * n[1]]; b1 = gtab[2 * n[1] + 1];
+                        c0 = gtab[2 * n[2]]; c1 = gtab[2 * n[2] + 1];
+                    } else {
+                        const double2 *gr = gtab + 6 * (size_t)c;
+                        a0 = __ldg(gr); a1 = __ldg(gr + 1); b0 = __ldg(gr + 2); b1 = __ldg(gr + 3);
+                        c0 = __ldg(gr + 4); c1 = __ldg(gr + 5);
+                    }
                     const double G0 = l0 * a0.x + l1 * b0.x + l2 * c0.x;
                     const double G1 = l0 * a0.y + l1 * b0.y + l2 * c0.y;
                     const double G2 = l0 * a1.x + l1 * b1.x + l2 * c1.x;
@@ -338,8 +611,41 @@ buoy_adjoint_scatter_kernel(DeviceTables t, const double2 *__restrict__ vel /* p
                     muy = muy - h * (G1 * rx + G3 * ry);
                 }
             }
+        };
+        // the three streams are read D samples ahead so that their HBM latency overlaps the arithmetic
+        const double2 zero2 = make_double2(0.0, 0.0);
+        double2 P[D], U[D], Q[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const int k = nt - 1 - j;
+            const bool ok = alive && k >= 0;
+            const size_t o = (size_t)(ok ? k : 0) * K + b;
+            P[j] = ok ? __ldcs(x + o) : zero2;
+            U[j] = ok ? __ldcs(u + o) : zero2;
+            Q[j] = ok ? __ldcs(ud + o) : zero2;
         }
-        if (acc_cell >= 0) flush_sources(bdst, t, acc_cell, acc);
+        for (int k0 = nt - 1; k0 >= 0; k0 -= D) {
+            double2 Pn[D], Un[D], Qn[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const int k = k0 - D - j;
+                const bool ok = alive && k >= 0;
+                const size_t o = (size_t)(ok ? k : 0) * K + b;
+                Pn[j] = ok ? __ldcs(x + o) : zero2;
+                Un[j] = ok ? __ldcs(u + o) : zero2;
+                Qn[j] = ok ? __ldcs(ud + o) : zero2;
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (k0 - j >= 0) sample(k0 - j, P[j], U[j], Q[j]);      // (warp-uniform condition)
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                P[j] = Pn[j];
+                U[j] = Un[j];
+                Q[j] = Qn[j];
+            }
+        }
+        if (run && acc_cell >= 0) flush(acc_cell);
     }
     block_finish2(misfit, nmasked, scratch, counter, acc_out + 2 * (size_t)t.nn, acc_out + 2 * (size_t)t.nn + 1,
                   0.5 * h);
@@ -352,6 +658,15 @@ __global__ void reduce_private_kernel(int n, int nrep, const double *__restrict_
     double s = 0.0;
     for (int r = 0; r < nrep; ++r) s += bpriv[(size_t)r * n + i];
     b[i] += s;
+}
+
+// digit sums of the private copies into copy 0 (integer additions: exact, order-free)
+__global__ void reduce_digits_kernel(size_t n, int nrep, long long *__restrict__ digits) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long s = digits[i];
+    for (int r = 1; r < nrep; ++r) s += digits[(size_t)r * n + i];
+    digits[i] = s;
 }
 
 __global__ void __launch_bounds__(256)
@@ -385,12 +700,61 @@ __global__ void transpose_kernel(const double2 *__restrict__ src, double2 *__res
 
 }  // namespace
 
-int buoy_max_blocks(int K) { return (K + kBuoyThreads - 1) / kBuoyThreads; }
+int buoy_max_blocks(int K) { return std::max(160, (K + kBuoyThreads - 1) / kBuoyThreads); }
 
 int buoy_private_copies(int K, int nc, int nn) {
     if ((long long)K < 8LL * nc) return 1;                        // few buoys per cell: no contention to avoid
     const long long cap = (256LL << 20) / (16LL * nn);            // at most 256 MiB of private copies
     return (int)std::max(1LL, std::min(148LL, cap));
+}
+
+size_t buoy_exact_digits(int nn, int nrep) { return 8 * (size_t)nn * (size_t)std::max(nrep, 1) + 1; }
+
+namespace {
+
+int device_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// Persistent launch shape of the staged kernels: one CTA per SM.  Small launches (K <= #SMs x 512) give every CTA
+// ONE contiguous share of ceil(K / #SMs) buoys (threads = that share rounded up to whole warps) so that all SMs hold
+// work - at K = 10^4 that is 148 CTAs of 68 buoys instead of 79 CTAs of 128; large launches loop over 512-buoy blocks.
+struct StagedShape {
+    int grid, threads, per_block;
+};
+
+StagedShape staged_shape(int K) {
+    const int sms = device_sms();
+    StagedShape sh;
+    if ((long long)K <= (long long)sms * kStagedMaxThreads) {
+        int per = std::max(32, (K + sms - 1) / sms);
+        per = (per + 3) & ~3;                                  // 64-byte aligned shares of the (nt, K, 2) arrays
+        sh.per_block = per;
+        sh.threads = (per + 31) & ~31;
+        sh.grid = (K + per - 1) / per;
+    } else {
+        sh.per_block = sh.threads = kStagedMaxThreads;
+        sh.grid = sms;
+    }
+    return sh;
+}
+
+template <class Kern>
+bool allow_smem(Kern k, size_t bytes) {
+    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+}
+
+}  // namespace
+
+bool buoy_tables_fit_shared(int nc, int nn, int nv) {
+    return staged_bytes(nc, 16 * (size_t)nn) <= kSmemBudget && staged_bytes(nc, 32 * (size_t)nv) <= kSmemBudget;
 }
 
 void launch_cell_records(const DeviceTables &t, const double *vel, double *cellvel, const double *g, double *cellg,
@@ -401,29 +765,82 @@ void launch_cell_records(const DeviceTables &t, const double *vel, double *cellv
         reinterpret_cast<const double2 *>(g), reinterpret_cast<double2 *>(cellg));
 }
 
-void launch_buoy_forward(const DeviceTables &t, const double *cellvel, const double *x0, int K, int nt, double h,
-                         double cx, double cy, double *x, double *u, int *cell, double *mask, uint8_t *parked,
-                         cudaStream_t s) {
+void launch_buoy_forward(const DeviceTables &t, bool staged, const double *field, const double *x0, int K, int nt,
+                         double h, double cx, double cy, double *x, double *u, int *cell, double *mask,
+                         uint8_t *parked, cudaStream_t s) {
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (K <= 0) return;
-    buoy_forward_kernel<<<buoy_max_blocks(K), kBuoyThreads, 0, s>>>(
-        t, reinterpret_cast<const double2 *>(cellvel), reinterpret_cast<const double2 *>(x0), K, nt, h, cx, cy,
-        reinterpret_cast<double2 *>(x), reinterpret_cast<double2 *>(u), cell, mask, parked);
+    const double2 *f2 = reinterpret_cast<const double2 *>(field), *x02 = reinterpret_cast<const double2 *>(x0);
+    double2 *x2 = reinterpret_cast<double2 *>(x), *u2 = reinterpret_cast<double2 *>(u);
+    if (staged) {
+        const size_t smem = staged_bytes(t.nc, 16 * (size_t)t.nn);
+        static bool ok = allow_smem(buoy_forward_kernel<true>, kSmemBudget);
+        (void)ok;
+        const StagedShape sh = staged_shape(K);
+        buoy_forward_kernel<true><<<sh.grid, sh.threads, smem, s>>>(t, f2, x02, K, sh.per_block, nt, h, cx, cy, x2, u2,
+                                                                    cell, mask, parked);
+    } else {
+        buoy_forward_kernel<false><<<(K + kBuoyThreads - 1) / kBuoyThreads, kBuoyThreads, 0, s>>>(
+            t, f2, x02, K, kBuoyThreads, nt, h, cx, cy, x2, u2, cell, mask, parked);
+    }
 }
 
-void launch_buoy_adjoint_scatter(const DeviceTables &t, const double *vel, const double *g, int K, int nt, double h,
-                                 double cx, double cy, const double *x, const double *u, const double *ud,
-                                 const double *mask, const uint8_t *parked, double *mu, double *acc,
-                                 double *scratch, unsigned *counter, double *bpriv, int nrep, cudaStream_t s) {
+void launch_buoy_adjoint_scatter(const DeviceTables &t, bool staged, const double *fieldv, const double *fieldg, int K,
+                                 int nt, double h, double cx, double cy, const double *x, const double *u,
+                                 const double *ud, const double *mask, const uint8_t *parked, double *mu, double *acc,
+                                 double *scratch, unsigned *counter, double *bpriv, int nrep, long long *digits,
+                                 cudaStream_t s) {
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (K <= 0) return;
-    if (nrep > 1) cudaMemsetAsync(bpriv, 0, sizeof(double) * 2 * (size_t)t.nn * nrep, s);
-    buoy_adjoint_scatter_kernel<<<buoy_max_blocks(K), kBuoyThreads, 0, s>>>(
-        t, reinterpret_cast<const double2 *>(vel), reinterpret_cast<const double2 *>(g), K, nt, h, cx, cy,
-        reinterpret_cast<const double2 *>(x), reinterpret_cast<const double2 *>(u),
-        reinterpret_cast<const double2 *>(ud), mask, parked, reinterpret_cast<double2 *>(mu), acc, scratch, counter,
-        bpriv, nrep);
-    if (nrep > 1) {
+    const bool exact = digits != nullptr;
+    if (exact)
+        cudaMemsetAsync(digits, 0, sizeof(long long) * buoy_exact_digits(t.nn, nrep), s);
+    else if (nrep > 1)
+        cudaMemsetAsync(bpriv, 0, sizeof(double) * 2 * (size_t)t.nn * nrep, s);
+    const double2 *fv = reinterpret_cast<const double2 *>(fieldv), *fg = reinterpret_cast<const double2 *>(fieldg);
+    const double2 *x2 = reinterpret_cast<const double2 *>(x), *u2 = reinterpret_cast<const double2 *>(u),
+                  *d2 = reinterpret_cast<const double2 *>(ud);
+    double2 *mu2 = reinterpret_cast<double2 *>(mu);
+#define OCP_BWD_ARGS t, fv, fg, K, per, nt, h, cx, cy, x2, u2, d2, mask, parked, mu2, acc, scratch, counter, bpriv, nrep, digits
+    if (staged) {
+        const size_t smem = staged_bytes(t.nc, 32 * (size_t)t.nv);
+        static bool ok = allow_smem(buoy_adjoint_scatter_kernel<true, kDepthLarge, false>, kSmemBudget) &&
+                         allow_smem(buoy_adjoint_scatter_kernel<true, kDepthSmall, false>, kSmemBudget) &&
+                         allow_smem(buoy_adjoint_scatter_kernel<true, kDepthLarge, true>, kSmemBudget) &&
+                         allow_smem(buoy_adjoint_scatter_kernel<true, kDepthSmall, true>, kSmemBudget);
+        (void)ok;
+        const StagedShape sh = staged_shape(K);
+        const int per = sh.per_block;
+        if (sh.threads <= 128) {       // small launch: one warp per scheduler must hide the stream latency itself
+            if (exact)
+                buoy_adjoint_scatter_kernel<true, kDepthSmall, true><<<sh.grid, sh.threads, smem, s>>>(OCP_BWD_ARGS);
+            else
+                buoy_adjoint_scatter_kernel<true, kDepthSmall, false><<<sh.grid, sh.threads, smem, s>>>(OCP_BWD_ARGS);
+        } else {
+            if (exact)
+                buoy_adjoint_scatter_kernel<true, kDepthLarge, true><<<sh.grid, sh.threads, smem, s>>>(OCP_BWD_ARGS);
+            else
+                buoy_adjoint_scatter_kernel<true, kDepthLarge, false><<<sh.grid, sh.threads, smem, s>>>(OCP_BWD_ARGS);
+        }
+    } else {
+        const int per = kBuoyThreads, grid = (K + kBuoyThreads - 1) / kBuoyThreads;
+        if (exact)
+            buoy_adjoint_scatter_kernel<false, kDepthLarge, true><<<grid, kBuoyThreads, 0, s>>>(OCP_BWD_ARGS);
+        else
+            buoy_adjoint_scatter_kernel<false, kDepthLarge, false><<<grid, kBuoyThreads, 0, s>>>(OCP_BWD_ARGS);
+    }
+#undef OCP_BWD_ARGS
+    if (exact) {
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        if (nrep > 1) {
+            const size_t n = 8 * (size_t)t.nn;
+            g_launch_count.fetch_add(1, std::memory_order_relaxed);
+            reduce_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, nrep, digits);
+            // the overflow counter of the copies sits behind the last copy: move it behind copy 0 for the finalize
+            cudaMemcpyAsync(digits + n, digits + n * nrep, sizeof(long long), cudaMemcpyDeviceToDevice, s);
+        }
+        finalize_exact_kernel<<<(2 * t.nn + 255) / 256, 256, 0, s>>>(2 * t.nn, digits, acc);
+    } else if (nrep > 1) {
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
         reduce_private_kernel<<<(2 * t.nn + 255) / 256, 256, 0, s>>>(2 * t.nn, nrep, bpriv, acc);
     }

@@ -93,6 +93,10 @@ struct ocp_ctx {
     double *d_cellvel = nullptr, *d_cellg = nullptr;   // per-cell coefficient records read by the buoy kernels
     double *d_bpriv = nullptr;                         // private copies of the point-source vector (per SM id)
     size_t bpriv_len = 0;
+    long long *d_digits = nullptr;                     // integer digit sums of the reproducible deposit
+    size_t digits_len = 0;
+    bool buoy_staged = false;     // mesh tables fit shared memory: TMA-staged buoy kernels (OCP_BUOY_STAGED=0 disables)
+    bool deterministic = false;   // ocp_set_deterministic / OCP_DETERMINISTIC=1
     size_t scratch_len = 0;
     unsigned *d_counter = nullptr;
     double *h_pinned = nullptr;    // 8 doubles
@@ -165,6 +169,16 @@ int ensure_bpriv(ocp_ctx *c, size_t n) {
     return OCP_OK;
 }
 
+int ensure_digits(ocp_ctx *c, size_t n) {
+    if (n <= c->digits_len) return OCP_OK;
+    cudaFree(c->d_digits);
+    c->d_digits = nullptr;
+    c->digits_len = 0;
+    CUDA_OK(c, cudaMalloc((void **)&c->d_digits, sizeof(long long) * n));
+    c->digits_len = n;
+    return OCP_OK;
+}
+
 int ensure_parked(ocp_ctx *c, size_t n) {
     if (n <= c->parked_len) return OCP_OK;
     cudaFree(c->d_parked);
@@ -221,6 +235,43 @@ int assemble_adjoint(ocp_ctx *c, const double *d_w, double *d_vals, bool bc) {
                            c->d_dof_ux, c->d_dof_uy, d_w, nullptr, true, d_vals, nullptr, s);
     if (bc) launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, d_vals, nullptr, nullptr, nullptr, s);
     CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+// forward sweep on the context's tables: staged (nodal field straight into shared memory) or per-cell records
+void run_buoy_forward(ocp_ctx *c, const double *d_vel, const double *d_x0, int K, double *d_x, double *d_u, int *d_cell,
+                      double *d_mask, uint8_t *d_parked) {
+    const double *field = d_vel;
+    if (!c->buoy_staged) {
+        launch_cell_records(c->tab, d_vel, c->d_cellvel, nullptr, nullptr, c->stream);
+        field = c->d_cellvel;
+    }
+    launch_buoy_forward(c->tab, c->buoy_staged, field, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_cell, d_mask,
+                        d_parked, c->stream);
+}
+
+// backward sweep (adjoint ODE + point sources + misfit); `exact` = reproducible integer deposit
+int run_buoy_backward(ocp_ctx *c, const double *d_vel, const double *d_g, int K, const double *d_x, const double *d_u,
+                      const double *d_ud, const double *d_mask, const uint8_t *d_parked, double *d_mu, double *d_acc,
+                      bool private_copies) {
+    int rc = ensure_scratch(c, 2 * (size_t)buoy_max_blocks(K) + 2);
+    if (rc != OCP_OK) return rc;
+    const int nrep = private_copies ? buoy_private_copies(K, c->nc, c->nn) : 1;
+    long long *digits = nullptr;
+    if (c->deterministic) {
+        if ((rc = ensure_digits(c, buoy_exact_digits(c->nn, nrep))) != OCP_OK) return rc;
+        digits = c->d_digits;
+    } else if (nrep > 1 && (rc = ensure_bpriv(c, 2 * (size_t)c->nn * nrep)) != OCP_OK) {
+        return rc;
+    }
+    const double *fv = d_vel, *fg = d_g;
+    if (!c->buoy_staged) {
+        launch_cell_records(c->tab, d_vel, c->d_cellvel, d_g, c->d_cellg, c->stream);
+        fv = c->d_cellvel;
+        fg = c->d_cellg;
+    }
+    launch_buoy_adjoint_scatter(c->tab, c->buoy_staged, fv, fg, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_ud, d_mask,
+                                d_parked, d_mu, d_acc, c->d_scratch, c->d_counter, c->d_bpriv, nrep, digits, c->stream);
     return OCP_OK;
 }
 
@@ -283,6 +334,21 @@ void ocp_set_profiling(ocp_ctx *ctx, int on) {
     if (ctx) ctx->profile = on != 0;
 }
 
+int ocp_set_deterministic(ocp_ctx *ctx, int on) {
+    if (!ctx) return OCP_ERR_INVALID;
+    ctx->deterministic = on != 0;
+    return OCP_OK;
+}
+
+int ocp_get_option(const ocp_ctx *ctx, const char *name) {
+    if (!ctx || !name) return -1;
+    const std::string n(name);
+    if (n == "deterministic") return ctx->deterministic ? 1 : 0;
+    if (n == "buoy_staged") return ctx->buoy_staged ? 1 : 0;
+    if (n == "adj_reuse") return ctx->adj_reuse ? 1 : 0;
+    return -1;
+}
+
 void ocp_set_viscosity(ocp_ctx *ctx, double viscosity) {
     if (ctx) {
         ctx->nu = viscosity;
@@ -301,6 +367,9 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     if (const char *ep = getenv("OCP_PROFILE")) c->profile = atoi(ep) != 0;
     if (const char *er = getenv("OCP_ADJ_REFINE")) c->adj_refine = std::max(0, atoi(er));
     if (const char *er = getenv("OCP_ADJ_REUSE")) c->adj_reuse = atoi(er) != 0;
+    if (const char *ed = getenv("OCP_DETERMINISTIC")) c->deterministic = atoi(ed) != 0;
+    c->buoy_staged = buoy_tables_fit_shared(d->nc, d->nn, d->nv);
+    if (const char *es = getenv("OCP_BUOY_STAGED")) c->buoy_staged = c->buoy_staged && atoi(es) != 0;
     c->nv = d->nv; c->nn = d->nn; c->nc = d->nc; c->ndofs = d->ndofs; c->nnz = d->nnz;
     c->n_dir = d->n_dirichlet; c->n_g1 = d->n_g1; c->nt = d->nt;
     c->nu = d->viscosity; c->dt = d->dt; c->cx = d->center_x; c->cy = d->center_y;
@@ -451,7 +520,7 @@ void ocp_destroy(ocp_ctx *c) {
                     c->d_dof_ux, c->d_dof_uy, c->d_dof_p, c->d_rowptr, c->d_col, c->d_dir, c->d_g1_nodes,
                     c->d_g1_dofs, c->d_g1_slots, c->d_bin_ptr, c->d_bin_cells, c->d_m_rowptr, c->d_m_col,
                     c->d_m_vals, c->d_vals, c->d_res, c->d_rhs, c->d_tmp, c->d_rhs4, c->d_scalar, c->d_scratch,
-                    c->d_counter, c->d_parked, c->d_obs_x0, c->d_obs_ud, c->d_cell_nbr, c->d_cellvel, c->d_cellg, c->d_bpriv, c->d_dirval};
+                    c->d_counter, c->d_parked, c->d_obs_x0, c->d_obs_ud, c->d_cell_nbr, c->d_cellvel, c->d_cellg, c->d_bpriv, c->d_dirval, c->d_digits};
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < 8; ++i) cudaFree(c->d_stage[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -573,9 +642,7 @@ int ocp_project_grad(ocp_ctx *c, const double *d_w, double *d_g) {
 int ocp_buoy_forward(ocp_ctx *c, const double *d_vel, const double *d_x0, int K, double *d_x, double *d_u,
                      int32_t *d_cell, double *d_mask, uint8_t *d_parked) {
     if (!c || !d_vel || !d_x0 || !d_x || !d_u || !d_mask || !d_parked || K < 0) return OCP_ERR_INVALID;
-    launch_cell_records(c->tab, d_vel, c->d_cellvel, nullptr, nullptr, c->stream);
-    launch_buoy_forward(c->tab, c->d_cellvel, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_cell, d_mask, d_parked,
-                        c->stream);
+    run_buoy_forward(c, d_vel, d_x0, K, d_x, d_u, d_cell, d_mask, d_parked);
     CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
 }
@@ -585,13 +652,8 @@ int ocp_buoy_adjoint_scatter(ocp_ctx *c, const double *d_vel, const double *d_g,
                              double *d_mu, double *d_acc) {
     if (!c || !d_vel || !d_g || !d_x || !d_u || !d_ud || !d_mask || !d_parked || !d_acc || K < 0)
         return OCP_ERR_INVALID;
-    int rc = ensure_scratch(c, 2 * (size_t)buoy_max_blocks(K) + 2);
+    int rc = run_buoy_backward(c, d_vel, d_g, K, d_x, d_u, d_ud, d_mask, d_parked, d_mu, d_acc, true);
     if (rc != OCP_OK) return rc;
-    const int nrep = buoy_private_copies(K, c->nc, c->nn);
-    if (nrep > 1 && (rc = ensure_bpriv(c, 2 * (size_t)c->nn * nrep)) != OCP_OK) return rc;
-    launch_cell_records(c->tab, d_vel, c->d_cellvel, d_g, c->d_cellg, c->stream);
-    launch_buoy_adjoint_scatter(c->tab, c->d_cellvel, c->d_cellg, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_ud, d_mask,
-                                d_parked, d_mu, d_acc, c->d_scratch, c->d_counter, c->d_bpriv, nrep, c->stream);
     CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
 }
@@ -733,8 +795,7 @@ int ocp_solve_primal_ode_host(ocp_ctx *c, const double *h_w, const double *h_x0,
     CUDA_OK(c, cudaMemcpyAsync(d_x0, h_x0, sizeof(double) * 2 * K, cudaMemcpyHostToDevice, s));
     CUDA_OK(c, cudaMemcpyAsync(d_mask, h_mask, sizeof(double) * K, cudaMemcpyHostToDevice, s));
     launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, d_w, d_vel, s);
-    launch_cell_records(c->tab, d_vel, c->d_cellvel, nullptr, nullptr, s);
-    launch_buoy_forward(c->tab, c->d_cellvel, d_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, nullptr, d_mask, c->d_parked, s);
+    run_buoy_forward(c, d_vel, d_x0, K, d_x, d_u, nullptr, d_mask, c->d_parked);
     // both result arrays go back in the reference's (K,nt,2) layout; each has its own staging buffer, so the
     // two transposes and the two device-to-host copies are queued back to back without a host round trip in between
     launch_traj_transpose(d_x, d_t, K, c->nt, 0, s);
@@ -774,9 +835,7 @@ int ocp_solve_adjoint_ode_host(ocp_ctx *c, const double *h_g, const double *h_x,
     CUDA_OK(c, cudaMemsetAsync(d_vel, 0, sizeof(double) * 2 * c->nn, s));
     CUDA_OK(c, cudaMemsetAsync(c->d_parked, 0, (size_t)K + 1, s));
     CUDA_OK(c, cudaMemsetAsync(d_acc, 0, sizeof(double) * nacc, s));
-    launch_cell_records(c->tab, d_vel, c->d_cellvel, d_g, c->d_cellg, s);
-    launch_buoy_adjoint_scatter(c->tab, c->d_cellvel, c->d_cellg, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, d_ud, d_mask,
-                                c->d_parked, d_t, d_acc, c->d_scratch, c->d_counter, nullptr, 1, s);
+    if ((rc = run_buoy_backward(c, d_vel, d_g, K, d_x, d_u, d_ud, d_mask, c->d_parked, d_t, d_acc, false))) return rc;
     launch_traj_transpose(d_t, d_x, K, c->nt, 0, s);
     CUDA_OK(c, cudaMemcpyAsync(h_mu, d_x, sizeof(double) * tr, cudaMemcpyDeviceToHost, s));
     CUDA_OK(c, cudaStreamSynchronize(s));
@@ -832,9 +891,7 @@ int ocp_gradient_host(ocp_ctx *c, const double *h_f, double *h_w, double *h_z, d
     if ((rc = ocp_forward_solve(c, d_f, d_w, 1, &its, nullptr))) return rc;
     if ((rc = ocp_project_grad(c, d_w, d_g))) return rc;
     launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, d_w, d_vel, s);
-    launch_cell_records(c->tab, d_vel, c->d_cellvel, nullptr, nullptr, s);
-    launch_buoy_forward(c->tab, c->d_cellvel, c->d_obs_x0, K, c->nt, c->dt, c->cx, c->cy, d_x, d_u, nullptr, d_mask,
-                        c->d_parked, s);
+    run_buoy_forward(c, d_vel, c->d_obs_x0, K, d_x, d_u, nullptr, d_mask, c->d_parked);
     if ((rc = ocp_buoy_adjoint_scatter(c, d_vel, d_g, K, d_x, d_u, c->d_obs_ud, d_mask, c->d_parked, nullptr, d_acc)))
         return rc;
     // buoys sharded over ranks: the sum over buoys (OCP_dolfin.py:353-366) is completed across GPUs here

@@ -25,16 +25,23 @@ struct DeviceTables {
 // (either output may be null)
 void launch_cell_records(const DeviceTables &t, const double *vel, double *cellvel, const double *g, double *cellg,
                          cudaStream_t s);
-// the buoy kernels read the per-cell records, not the nodal fields
-void launch_buoy_forward(const DeviceTables &t, const double *cellvel, const double *x0, int K, int nt, double h,
-                         double cx, double cy, double *x, double *u, int *cell, double *mask, uint8_t *parked,
-                         cudaStream_t s);
-// scratch: >= 2*max_blocks+2 doubles, counter: 1 unsigned (zero on entry, left zero)
-void launch_buoy_adjoint_scatter(const DeviceTables &t, const double *cellvel, const double *cellg, int K, int nt, double h,
-                                 double cx, double cy, const double *x, const double *u, const double *ud,
-                                 const double *mask, const uint8_t *parked, double *mu, double *acc,
-                                 double *scratch, unsigned *counter, double *bpriv, int nrep, cudaStream_t s);
+// `staged`: the mesh tables fit an SM's shared memory (buoy_tables_fit_shared) and are staged there by TMA bulk copies;
+// `field*` are then the NODAL fields (velocity (nn,2), projected gradient (nv,4)).  Otherwise `field*` are the per-cell
+// records built by launch_cell_records.
+bool buoy_tables_fit_shared(int nc, int nn, int nv);
+void launch_buoy_forward(const DeviceTables &t, bool staged, const double *field, const double *x0, int K, int nt,
+                         double h, double cx, double cy, double *x, double *u, int *cell, double *mask,
+                         uint8_t *parked, cudaStream_t s);
+// scratch: >= 2*buoy_max_blocks(K)+2 doubles, counter: 1 unsigned (zero on entry, left zero).
+// digits != null: reproducible deposit (integer digit sums, buoy_exact_digits(nn, nrep) long longs) instead of fp64
+// atomics; bpriv (nrep > 1): private copies of b.
+void launch_buoy_adjoint_scatter(const DeviceTables &t, bool staged, const double *fieldv, const double *fieldg, int K,
+                                 int nt, double h, double cx, double cy, const double *x, const double *u,
+                                 const double *ud, const double *mask, const uint8_t *parked, double *mu, double *acc,
+                                 double *scratch, unsigned *counter, double *bpriv, int nrep, long long *digits,
+                                 cudaStream_t s);
 int buoy_private_copies(int K, int nc, int nn);   // number of private copies of b worth using (1 = none)
+size_t buoy_exact_digits(int nn, int nrep);       // long longs of the digit accumulator (deterministic mode)
 void launch_misfit(int K, int nt, double h, const double *u, const double *ud, double *out, double *scratch,
                    unsigned *counter, cudaStream_t s);
 void launch_traj_transpose(const double *src, double *dst, int K, int nt, int to_time_major, cudaStream_t s);

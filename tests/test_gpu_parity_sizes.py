@@ -268,3 +268,83 @@ def test_nccl_allreduce_inside_the_library_two_gpus():
     assert np.array_equal(got[0][0], got[1][0])                 # identical on both ranks after the all-reduce
     s = H.OraclePipeline(V, 1.0, x0, ud, 1e-6 * 400).gradient_step(f)
     assert H.rel(got[0][0][:nn2].reshape(-1, 2), s["bnode"]) < 1e-11 and H.rel(got[0][1], s["z"]) < 1e-9
+
+
+def _sweep_both_ways(V, x0, ud, w, g, center, deterministic=False):
+    """forward + backward sweep; returns host copies of everything the sweeps produce"""
+    K = x0.shape[0]
+    ocp = OCP(V, Parameters(), x0, ud, device=dev())
+    if deterministic:
+        ocp.ctx.set_deterministic(True)
+    cell = torch.empty((200, K), device=dev(), dtype=torch.int32)
+    ocp._primal(T(w), ocp.d_x, ocp.d_u, ocp.d_mask, d_cell=cell)
+    nn = V.num_nodes
+    acc = torch.zeros(2 * nn + 2, device=dev(), dtype=torch.float64)
+    mu = torch.empty_like(ocp.d_x)
+    ocp.ctx.buoy_adjoint_scatter(ocp.d_vel, T(g), K, ocp.d_x, ocp.d_u, ocp.d_ud, ocp.d_mask, ocp.d_parked, mu, acc)
+    out = dict(x=ocp._to_reference_layout(ocp.d_x), u=ocp._to_reference_layout(ocp.d_u),
+               cell=ocp._cells_to_host(cell), mask=ocp._buoy_vector_to_host(ocp.d_mask),
+               parked=ocp._buoy_vector_to_host(ocp.d_parked), mu=ocp._to_reference_layout(mu), acc=acc.cpu().numpy(),
+               staged=ocp.ctx.option("buoy_staged"))
+    ocp.close()
+    return out
+
+
+@pytest.mark.parametrize("mesh", ["square32", "lshape"])
+def test_staged_shared_memory_tables_equal_the_global_table_path(mesh, monkeypatch):
+    """The TMA-staged kernels (mesh tables in shared memory, persistent grid) and the global-table kernels (per-cell
+    records through L1/L2) run the same arithmetic: cell indices, trajectories, masks and mu bit-identical, the
+    atomically summed b to round-off.  Buoys that leave the domain and the warp-cooperative bin search included."""
+    V = H.square32() if mesh == "square32" else H.lshape()
+    center = H.CENTER if mesh == "square32" else np.array([1.0, 0.5])
+    O = FEOracle(V, 1.0)
+    w = O.newton_solve(initial_control(V, "PL")) if mesh == "lshape" else H.field_for(100)
+    g = O.project_gradient(w)
+    rng = np.random.default_rng(21)
+    K = 5000
+    x0 = np.stack([rng.uniform(-0.03, 2.03, K), rng.uniform(-0.03, 2.03, K)], 1)
+    x0[:64] = V.mesh.coords[rng.choice(V.mesh.num_vertices, 64)]          # exactly on vertices: the tie rule
+    ud = 0.05 * rng.standard_normal((K, 200, 2))
+    a = _sweep_both_ways(V, x0, ud, w, g, center)
+    monkeypatch.setenv("OCP_BUOY_STAGED", "0")
+    b = _sweep_both_ways(V, x0, ud, w, g, center)
+    assert a["staged"] == 1 and b["staged"] == 0
+    for k in ("x", "u", "cell", "mask", "parked", "mu"):
+        assert np.array_equal(a[k], b[k]), k
+    nn2 = 2 * V.num_nodes
+    assert H.rel(a["acc"][:nn2], b["acc"][:nn2]) < 1e-13 and a["acc"][nn2 + 1] == b["acc"][nn2 + 1]
+    assert abs(a["acc"][nn2] - b["acc"][nn2]) <= 1e-13 * abs(b["acc"][nn2])
+    # and both against the oracle
+    B = BuoyOracle(V, brute=True)
+    xo, uo, co, mo, po = B.forward(V.velocity_nodal(w), x0, 200, H.H, center)
+    assert np.array_equal(a["x"], xo) and np.array_equal(a["u"], uo) and np.array_equal(a["cell"], co)
+    assert np.array_equal(a["mask"], mo) and np.array_equal(a["parked"], po)
+    muo = B.adjoint(g, xo, uo, ud, mo, H.H)
+    bo = B.point_sources(V.velocity_nodal(w), xo, ud, muo, mo, H.H, center)
+    assert H.rel(a["mu"], muo) < 1e-12 and H.rel(a["acc"][:nn2].reshape(-1, 2), bo) < 1e-12
+
+
+@pytest.mark.parametrize("K", [3000, 50_000])
+def test_deterministic_deposit_is_bit_reproducible(K):
+    """SURVEY section 5 (determinism): with ocp_set_deterministic the point sources are accumulated as exact
+    fixed-point digit sums with integer atomics - two runs give bit-identical b (also through the per-SM private
+    copies at K >= 8 cells' worth), and b agrees with the fp64-atomic variant and the oracle to 1e-12."""
+    V = H.square32()
+    O = FEOracle(V, 1.0)
+    w = H.field_for(100)
+    g = O.project_gradient(w)
+    rng = np.random.default_rng(4)
+    x0 = np.stack([rng.uniform(0.05, 1.95, K), rng.uniform(0.05, 1.95, K)], 1)
+    ud = 0.05 * rng.standard_normal((K, 200, 2))
+    r1 = _sweep_both_ways(V, x0, ud, w, g, H.CENTER, deterministic=True)
+    r2 = _sweep_both_ways(V, x0, ud, w, g, H.CENTER, deterministic=True)
+    at = _sweep_both_ways(V, x0, ud, w, g, H.CENTER, deterministic=False)
+    nn2 = 2 * V.num_nodes
+    assert np.array_equal(r1["acc"], r2["acc"])                              # bit-identical, every entry
+    assert H.rel(r1["acc"][:nn2], at["acc"][:nn2]) < 1e-12
+    assert r1["acc"][nn2] == at["acc"][nn2] and r1["acc"][nn2 + 1] == at["acc"][nn2 + 1]
+    B = BuoyOracle(V)
+    xo, uo, co, mo, po = B.forward(V.velocity_nodal(w), x0, 200, H.H, H.CENTER)
+    muo = B.adjoint(g, xo, uo, ud, mo, H.H)
+    bo = B.point_sources(V.velocity_nodal(w), xo, ud, muo, mo, H.H, H.CENTER)
+    assert H.rel(r1["acc"][:nn2].reshape(-1, 2), bo) < 1e-12
