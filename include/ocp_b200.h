@@ -107,8 +107,9 @@ int ocp_set_dirichlet(ocp_ctx *ctx, const int32_t *h_dofs, const double *h_vals,
  * INTEGER atomics (associative), which makes b - hence z, the gradient and the control update - bit-identical from
  * run to run, independent of launch geometry; it agrees with the atomic variant to round-off (1e-12 tested). */
 int ocp_set_deterministic(ocp_ctx *ctx, int on);
-/* Current value of an option: "deterministic", "buoy_staged" (mesh tables staged in shared memory by TMA bulk
- * copies: chosen automatically when they fit an SM, environment OCP_BUOY_STAGED=0 disables), "adj_reuse"; -1 unknown. */
+/* Current value of an option: "deterministic", "buoy_staged" (buoy kernels with the mesh tables staged in shared
+ * memory by TMA bulk copies; opt-in with environment OCP_BUOY_STAGED=1 when the tables fit an SM - measured slower
+ * than the default global-table kernels on B200), "adj_reuse"; -1 unknown. */
 int ocp_get_option(const ocp_ctx *ctx, const char *name);
 /* Per-phase line-item timing (ocp_get_solver_stats) synchronises the stream after every phase; it is therefore off
  * by default and switched on only for profiling runs (also: environment OCP_PROFILE=1). */

@@ -6,16 +6,22 @@
 //                                + PointSource loop          OCP_dolfin.py:353-366
 //                                + partA of J                OCP_dolfin.py:259
 //
-// Two table paths, same arithmetic (bit-identical results):
+// Two table paths, same arithmetic (bit-identical trajectories, cells, masks and mu).  GLOBAL is the default: measured
+// on B200 it is the faster one at every size (profiles/README.md, round 2: 2^20 buoys backward 2.05 ms vs 3.04 ms
+// staged - the staged kernel is limited to one 512-thread CTA per SM by its 182-215 KB of tables, and the tables
+// were L1-resident anyway; at K = 10^4 both take 0.157 ms because the launch is bound by the 200-step dependent
+// chain of a single warp per scheduler, not by table latency).  STAGED stays selectable (OCP_BUOY_STAGED=1).
 //   * STAGED (kStaged = true): the mesh tables a sweep reads per sample - cell geometry (48 B / cell), cell -> node
 //     map (24 B / cell), nodal velocity (16 B / node) or nodal projected gradient (32 B / vertex) - are copied ONCE per
 //     CTA into shared memory with TMA bulk copies (cp.async.bulk + mbarrier transaction count) by a persistent
 //     grid of one CTA per SM; every per-sample table access is then a shared-memory load (~25 cycles) instead of an
-//     L1/L2 round trip on the dependent chain locate -> evaluate -> advance.  Used whenever the tables fit the
-//     227 KB of an SM (the reference's 32 x 32 mesh: 215 KB forward, 182 KB backward).
+//     L1/L2 round trip on the dependent chain locate -> evaluate -> advance.  Possible whenever the tables fit the
+//     227 KB of an SM (the reference's 32 x 32 mesh: 215 KB forward, 182 KB backward).  Its point location falls
+//     back to a WARP-COOPERATIVE bin search (locate_bins_warp).
 //   * GLOBAL (kStaged = false): per-cell coefficient records (cellvel / cellg, rebuilt whenever the state changes) read
 //     through the read-only path; refined meshes (cfg5) whose tables exceed shared memory.
 #include <algorithm>
+#include <cstdlib>
 
 #include "element_math.cuh"
 #include "kernels.cuh"
@@ -220,6 +226,161 @@ __global__ void cell_records_kernel(int nc, const int *__restrict__ cell_nodes, 
     if (cellg && a < 3) {
         cellg[6 * (size_t)c + 2 * a] = __ldg(g + 2 * (size_t)n);
         cellg[6 * (size_t)c + 2 * a + 1] = __ldg(g + 2 * (size_t)n + 1);
+    }
+}
+
+__device__ __forceinline__ void load_geom_g(const DeviceTables &t, int c, double g[6]) {
+    const double2 *p = reinterpret_cast<const double2 *>(t.geom) + 3 * (size_t)c;
+    const double2 a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);
+    g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y; g[4] = d.x; g[5] = d.y;
+}
+
+__device__ __forceinline__ void load_nodes_g(const DeviceTables &t, int c, int n[6]) {
+    const int2 *p = reinterpret_cast<const int2 *>(t.cell_nodes) + 3 * (size_t)c;
+    const int2 a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);
+    n[0] = a.x; n[1] = a.y; n[2] = b.x; n[3] = b.y; n[4] = d.x; n[5] = d.y;
+}
+
+// ---- GLOBAL-table path (per-thread point location, per-cell coefficient records) ---------------------------------
+// Lowest-index cell whose barycentrics are all >= -tol (the oracle's definition of dolfin's "first colliding cell").
+//   1. `hint` (previous cell): accepted when the point is strictly inside (margin 1e-9) - then no other cell can
+//      contain it, so the answer equals the definition.
+//   2. neighbour walk: leave through the edge with the most negative barycentric, at most 4 hops, again accepting
+//      only strictly-inside hits.  This is what a buoy crossing into the next cell costs (one or two hops).
+//   3. anything ambiguous (on an edge/vertex within the margin, outside the mesh, far jump): the definition itself,
+//      ascending scan of the bin's candidate list.
+// -1 = dolfin's "point outside" error.
+__device__ __forceinline__ int locate_g(const DeviceTables &t, double x, double y, int hint, double &l0, double &l1,
+                                      double &l2) {
+    if (!(x == x) || !(y == y)) return -1;
+    double g[6];
+    if (hint >= 0) {
+        int c = hint;
+#pragma unroll 1
+        for (int hop = 0; hop < 5; ++hop) {
+            load_geom_g(t, c, g);
+            bary(g, x, y, l0, l1, l2);
+            if (l0 > kLocateMargin && l1 > kLocateMargin && l2 > kLocateMargin) return c;
+            const double lm = fmin(l0, fmin(l1, l2));
+            if (lm >= -kLocateTol) break;                       // within the tie zone of an edge: use the definition
+            const int e = (l0 == lm) ? 0 : ((l1 == lm) ? 1 : 2);
+            c = __ldg(t.cell_nbr + 3 * (size_t)c + e);
+            if (c < 0) break;
+        }
+    }
+    const double fx = floor(OCP_MUL(OCP_SUB(x, t.ox), t.ihx));
+    const double fy = floor(OCP_MUL(OCP_SUB(y, t.oy), t.ihy));
+    const int ix = fx < 0.0 ? 0 : (fx > (double)(t.nbx - 1) ? t.nbx - 1 : (int)fx);
+    const int iy = fy < 0.0 ? 0 : (fy > (double)(t.nby - 1) ? t.nby - 1 : (int)fy);
+    const int b = iy * t.nbx + ix;
+    const int j1 = __ldg(t.bin_ptr + b + 1);
+    for (int j = __ldg(t.bin_ptr + b); j < j1; ++j) {
+        const int c = __ldg(t.bin_cells + j);
+        load_geom_g(t, c, g);
+        bary(g, x, y, l0, l1, l2);
+        if (l0 >= -kLocateTol && l1 >= -kLocateTol && l2 >= -kLocateTol) return c;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ void eval_p2_nodal_g(const DeviceTables &t, const double2 *__restrict__ vel, int c, double l0,
+                                        double l1, double l2, double &ux, double &uy) {
+    double phi[6];
+    int n[6];
+    p2_basis(l0, l1, l2, phi);
+    load_nodes_g(t, c, n);
+    double2 v = __ldg(vel + n[0]);
+    double sx = OCP_MUL(phi[0], v.x), sy = OCP_MUL(phi[0], v.y);
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        v = __ldg(vel + n[i]);
+        sx = OCP_FMA(phi[i], v.x, sx);
+        sy = OCP_FMA(phi[i], v.y, sy);
+    }
+    ux = sx;
+    uy = sy;
+}
+
+// P2 velocity from the per-cell coefficient record (12 doubles: (u_x, u_y) of the cell's six nodes, contiguous), same
+// operation order as eval_p2 - the record only replaces the node-index indirection by one contiguous 96-byte read.
+__device__ __forceinline__ void eval_p2_cell_g(const double2 *__restrict__ cellvel, int c, double l0, double l1,
+                                             double l2, double &ux, double &uy) {
+    double phi[6];
+    p2_basis(l0, l1, l2, phi);
+    const double2 *r = cellvel + 6 * (size_t)c;
+    double2 v = __ldg(r);
+    double sx = OCP_MUL(phi[0], v.x), sy = OCP_MUL(phi[0], v.y);
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        v = __ldg(r + i);
+        sx = OCP_FMA(phi[i], v.x, sx);
+        sy = OCP_FMA(phi[i], v.y, sy);
+    }
+    ux = sx;
+    uy = sy;
+}
+
+__global__ void __launch_bounds__(kBuoyThreads)
+buoy_forward_global_kernel(DeviceTables t, const double2 *__restrict__ vel /* per-cell records */, const double2 *__restrict__ x0, int K, int nt,
+                    double h, double cx, double cy, double2 *__restrict__ x, double2 *__restrict__ u,
+                    int *__restrict__ cell, double *__restrict__ mask, uint8_t *__restrict__ parked) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= K) return;
+    double2 p = x0[b];
+    int hint = -1, kfail = -1;
+    double l0, l1, l2;
+    for (int k = 0; k < nt - 1; ++k) {
+        const int c = locate_g(t, p.x, p.y, hint, l0, l1, l2);
+        if (c < 0) {
+            kfail = k;
+            break;
+        }
+        double ux, uy;
+        eval_p2_cell_g(vel, c, l0, l1, l2, ux, uy);
+        const size_t o = (size_t)k * K + b;
+        x[o] = p;
+        u[o] = make_double2(ux, uy);
+        if (cell) cell[o] = c;
+        p.x = OCP_ADD(p.x, OCP_MUL(h, ux));      // two roundings, as numpy at OCP_dolfin.py:212
+        p.y = OCP_ADD(p.y, OCP_MUL(h, uy));
+        hint = c;
+    }
+    if (kfail < 0) {
+        // trailing evaluation at the last sample, OCP_dolfin.py:223-229
+        const size_t o = (size_t)(nt - 1) * K + b;
+        const int c = locate_g(t, p.x, p.y, hint, l0, l1, l2);
+        if (c >= 0) {
+            double ux, uy;
+            eval_p2_cell_g(vel, c, l0, l1, l2, ux, uy);
+            x[o] = p;
+            u[o] = make_double2(ux, uy);
+            if (cell) cell[o] = c;
+            parked[b] = 0;
+        } else {
+            x[o] = make_double2(cx, cy);
+            u[o] = make_double2(0.0, 0.0);
+            if (cell) cell[o] = -1;
+            parked[b] = 1;
+        }
+        return;
+    }
+    // the `except` branch, OCP_dolfin.py:213-221: park the whole trajectory at the centre, mask the buoy;
+    // samples 0..kfail-1 keep their velocities, sample kfail stays 0, sample kfail+1 gets u(centre)
+    mask[b] = 1.0;
+    parked[b] = 0;
+    const int cc = locate_g(t, cx, cy, -1, l0, l1, l2);
+    double ucx = 0.0, ucy = 0.0;
+    if (cc >= 0) eval_p2_cell_g(vel, cc, l0, l1, l2, ucx, ucy);
+    for (int k = 0; k < nt; ++k) {
+        const size_t o = (size_t)k * K + b;
+        x[o] = make_double2(cx, cy);
+        if (k == kfail + 1) {
+            u[o] = make_double2(ucx, ucy);
+            if (cell) cell[o] = cc;
+        } else if (k >= kfail) {
+            u[o] = make_double2(0.0, 0.0);
+            if (cell) cell[o] = -1;
+        }
     }
 }
 
@@ -651,6 +812,285 @@ buoy_adjoint_scatter_kernel(DeviceTables t, const double2 *__restrict__ fieldv, 
                   0.5 * h);
 }
 
+__device__ __forceinline__ void flush_sources_g(double *__restrict__ bnode, const DeviceTables &t, int c,
+                                                double acc[12]) {
+    int n[6];
+    load_nodes_g(t, c, n);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        atomicAdd(bnode + 2 * (size_t)n[i], acc[i]);
+        atomicAdd(bnode + 2 * (size_t)n[i] + 1, acc[6 + i]);
+        acc[i] = 0.0;
+        acc[6 + i] = 0.0;
+    }
+}
+
+// Backward sweep k = nt-1 .. 0.  Per sample: gamma_k = h((u_d - u(x_k)) + mu_k) is deposited as
+// gamma_c phi_i(x_k); deposits are accumulated in registers while the buoy stays in one cell and
+// flushed with 12 fp64 atomics when it changes cell (a buoy crosses a handful of cells per trajectory),
+// then mu_{k-1} = mu_k - h G(x_k)^T ((u_k - u_d,k) - mu_k).
+template <bool X>
+__global__ void __launch_bounds__(kBuoyThreads, 5)
+buoy_adjoint_scatter_global_kernel(DeviceTables t, const double2 *__restrict__ vel /* per-cell records */,
+                            const double2 *__restrict__ g /* per-cell vertex gradients */, int K,
+                            int nt, double h, double cx, double cy, const double2 *__restrict__ x,
+                            const double2 *__restrict__ u, const double2 *__restrict__ ud,
+                            const double *__restrict__ mask, const uint8_t *__restrict__ parked,
+                            double2 *__restrict__ mu, double *__restrict__ acc_out, double *scratch,
+                            unsigned *counter, double *__restrict__ bpriv, int nrep, long long *__restrict__ digits) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    double misfit = 0.0, nmasked = 0.0;
+    // point sources go to one of `nrep` private copies of b (selected by SM id) so that fp64 atomics of the
+    // thousands of buoys sharing a cell do not serialise on 12 addresses; the copies are summed afterwards
+    double *bdst = acc_out;
+    long long *ddst = digits;
+    if (nrep > 1) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        bdst = bpriv + (size_t)(smid % (unsigned)nrep) * (2 * (size_t)t.nn);
+        if (X) ddst = digits + (size_t)(smid % (unsigned)nrep) * (8 * (size_t)t.nn);
+    }
+    long long *const dovf = X ? digits + 8 * (size_t)t.nn * (nrep > 1 ? nrep : 1) : nullptr;
+    if (b < K) {
+        const bool masked = mask[b] != 0.0;
+        const bool park = parked[b] != 0;
+        nmasked = masked ? 1.0 : 0.0;
+        double mux = 0.0, muy = 0.0;
+        double acc[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc[i] = 0.0;
+        int acc_cell = -1, hint = -1;
+        // the three streams are read one sample ahead so that their HBM latency overlaps the arithmetic
+        double2 pn = __ldcs(x + (size_t)(nt - 1) * K + b), Un = __ldcs(u + (size_t)(nt - 1) * K + b),
+                Dn = __ldcs(ud + (size_t)(nt - 1) * K + b);
+        for (int k = nt - 1; k >= 0; --k) {
+            const size_t o = (size_t)k * K + b;
+            double2 p = pn;
+            const double2 U = Un, D = Dn;
+            if (k > 0) {
+                pn = __ldcs(x + o - K);
+                Un = __ldcs(u + o - K);
+                Dn = __ldcs(ud + o - K);
+            }
+            const double ex = U.x - D.x, ey = U.y - D.y;
+            misfit += ex * ex + ey * ey;
+            if (masked) {
+                if (mu) __stcs(mu + o, make_double2(0.0, 0.0));
+                continue;
+            }
+            double l0, l1, l2;
+            double ukx = U.x, uky = U.y;
+            int c = locate_g(t, p.x, p.y, hint, l0, l1, l2);
+            if (c < 0) {            // `except` of OCP_dolfin.py:359-361: u_x = 0, point = centre
+                ukx = 0.0;
+                uky = 0.0;
+                p = make_double2(cx, cy);
+                c = locate_g(t, cx, cy, -1, l0, l1, l2);
+            } else if (park && k == nt - 1) {
+                // the stored velocity of a parked last sample is 0, the scatter loop re-evaluates u(centre)
+                eval_p2_cell_g(vel, c, l0, l1, l2, ukx, uky);
+            }
+            if (mu) __stcs(mu + o, make_double2(mux, muy));
+            if (c >= 0) {
+                hint = c;
+                if (c != acc_cell) {
+                    if (acc_cell >= 0) {
+                        if (X)
+                            flush_sources_exact<false>(ddst, dovf, t.cell_nodes, acc_cell, acc);
+                        else
+                            flush_sources_g(bdst, t, acc_cell, acc);
+                    }
+                    acc_cell = c;
+                }
+                const double gx = h * ((D.x - ukx) + mux), gy = h * ((D.y - uky) + muy);
+                double phi[6];
+                p2_basis(l0, l1, l2, phi);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    acc[i] = fma(gx, phi[i], acc[i]);
+                    acc[6 + i] = fma(gy, phi[i], acc[6 + i]);
+                }
+                if (k > 0) {
+                    // continuous P1 tensor at the cell's three vertices, [g00 g01 | g10 g11] per vertex
+                    const double2 *gr = g + 6 * (size_t)c;
+                    const double2 a0 = __ldg(gr), a1 = __ldg(gr + 1), b0 = __ldg(gr + 2), b1 = __ldg(gr + 3),
+                                  c0 = __ldg(gr + 4), c1 = __ldg(gr + 5);
+                    const double G0 = l0 * a0.x + l1 * b0.x + l2 * c0.x;
+                    const double G1 = l0 * a0.y + l1 * b0.y + l2 * c0.y;
+                    const double G2 = l0 * a1.x + l1 * b1.x + l2 * c1.x;
+                    const double G3 = l0 * a1.y + l1 * b1.y + l2 * c1.y;
+                    const double rx = ex - mux, ry = ey - muy;
+                    mux = mux - h * (G0 * rx + G2 * ry);
+                    muy = muy - h * (G1 * rx + G3 * ry);
+                }
+            }
+        }
+        if (acc_cell >= 0) {
+            if (X)
+                flush_sources_exact<false>(ddst, dovf, t.cell_nodes, acc_cell, acc);
+            else
+                flush_sources_g(bdst, t, acc_cell, acc);
+        }
+    }
+    block_finish2(misfit, nmasked, scratch, counter, acc_out + 2 * (size_t)t.nn, acc_out + 2 * (size_t)t.nn + 1,
+                  0.5 * h);
+}
+
+// TIME-PARALLEL backward sweep for small launches.  At K ~ 10^4 one thread per buoy leaves one warp per scheduler
+// walking 200 dependent samples (~0.8 us each): the launch is bound by that chain, not by bandwidth.  The adjoint
+// recursion is AFFINE in mu,
+//     mu_{k-1} = (I + h G_k^T) mu_k - h G_k^T e_k,      G_k = G(x_k), e_k = u_k - u_d,k,
+// so T lanes share one buoy: lane j owns a contiguous chunk of samples and
+//   pass 1  composes the affine map of its chunk (point location + G per sample, no deposits),
+//   scan    the incoming mu of every chunk follows from the chunks after it (T-1 shuffle steps),
+//   pass 2  runs the ordinary per-sample sweep over its chunk from that incoming mu (deposits, misfit, mu output).
+// The dependent chain shrinks from nt to 2 nt / T samples and T times as many warps are in flight.  mu at the chunk
+// boundaries is formed through the composed maps, i.e. with a different (equally valid) rounding sequence than the
+// serial sweep: mu and b agree with it to ~1e-15 relative (tests: 1e-12 against the oracle).
+template <int T, bool X>
+__global__ void __launch_bounds__(kBuoyThreads)
+buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /* per-cell records */,
+                               const double2 *__restrict__ g /* per-cell vertex gradients */, int K, int nt, double h,
+                               double cx, double cy, const double2 *__restrict__ x, const double2 *__restrict__ u,
+                               const double2 *__restrict__ ud, const double *__restrict__ mask,
+                               const uint8_t *__restrict__ parked, double2 *__restrict__ mu,
+                               double *__restrict__ acc_out, double *scratch, unsigned *counter,
+                               long long *__restrict__ digits) {
+    constexpr int G = 32 / T;                                  // buoys per warp
+    const int lane = threadIdx.x & 31, j = lane % T;           // j = chunk index, chunk T-1 holds the last samples
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long bl = warp * G + lane / T;
+    const bool alive = bl < K;
+    const int b = alive ? (int)bl : 0;
+    const int klo = (int)(((long long)j * nt) / T), khi = (int)(((long long)(j + 1) * nt) / T) - 1;
+    const bool masked = alive && mask[b] != 0.0;
+    const bool park = alive && parked[b] != 0;
+    const bool run = alive && !masked;
+    long long *const dovf = X ? digits + 8 * (size_t)t.nn : nullptr;
+    double misfit = 0.0, nmasked = (masked && j == 0) ? 1.0 : 0.0;
+    // G(x_k)^T-step coefficients of one sample: returns false when the sample leaves mu unchanged
+    auto locate_sample = [&](int k, double2 &p, int &hint, double &l0, double &l1, double &l2, bool &lost) -> int {
+        int c = locate_g(t, p.x, p.y, hint, l0, l1, l2);
+        lost = c < 0;
+        if (lost) {                                            // `except` of OCP_dolfin.py:359-361: point = centre
+            p = make_double2(cx, cy);
+            c = locate_g(t, cx, cy, -1, l0, l1, l2);
+        }
+        if (c >= 0) hint = c;
+        return c;
+    };
+    auto grad_at = [&](int c, double l0, double l1, double l2, double &G0, double &G1, double &G2, double &G3) {
+        const double2 *gr = g + 6 * (size_t)c;
+        const double2 a0 = __ldg(gr), a1 = __ldg(gr + 1), b0 = __ldg(gr + 2), b1 = __ldg(gr + 3), c0 = __ldg(gr + 4),
+                      c1 = __ldg(gr + 5);
+        G0 = l0 * a0.x + l1 * b0.x + l2 * c0.x;
+        G1 = l0 * a0.y + l1 * b0.y + l2 * c0.y;
+        G2 = l0 * a1.x + l1 * b1.x + l2 * c1.x;
+        G3 = l0 * a1.y + l1 * b1.y + l2 * c1.y;
+    };
+    // ---- pass 1: affine map of the chunk, mu_{klo-1} = M mu_{khi} + v
+    double m00 = 1.0, m01 = 0.0, m10 = 0.0, m11 = 1.0, v0 = 0.0, v1 = 0.0;
+    if (run && j > 0) {                    // (chunk 0's map is never needed)
+        int hint = -1;
+        for (int k = khi; k >= klo; --k) {
+            const size_t o = (size_t)k * K + b;
+            double2 p = __ldg(x + o);
+            const double2 U = __ldg(u + o), D = __ldg(ud + o);
+            double l0, l1, l2;
+            bool lost;
+            const int c = locate_sample(k, p, hint, l0, l1, l2, lost);
+            if (c >= 0 && k > 0) {
+                double G0, G1, G2, G3;
+                grad_at(c, l0, l1, l2, G0, G1, G2, G3);
+                const double ex = U.x - D.x, ey = U.y - D.y;
+                // A = I + h G^T (row 0: [1 + h G0, h G2], row 1: [h G1, 1 + h G3]),  c = -h G^T e
+                const double a00 = 1.0 + h * G0, a01 = h * G2, a10 = h * G1, a11 = 1.0 + h * G3;
+                const double c0 = -h * (G0 * ex + G2 * ey), c1 = -h * (G1 * ex + G3 * ey);
+                const double n00 = a00 * m00 + a01 * m10, n01 = a00 * m01 + a01 * m11;
+                const double n10 = a10 * m00 + a11 * m10, n11 = a10 * m01 + a11 * m11;
+                const double w0 = a00 * v0 + a01 * v1 + c0, w1 = a10 * v0 + a11 * v1 + c1;
+                m00 = n00; m01 = n01; m10 = n10; m11 = n11; v0 = w0; v1 = w1;
+            }
+        }
+    }
+    // ---- scan over the chunks of a buoy, last chunk first: incoming mu of chunk s-1 = map of chunk s applied to its own
+    double mux = 0.0, muy = 0.0;
+#pragma unroll 1
+    for (int s_ = T - 1; s_ >= 1; --s_) {
+        const double ox = m00 * mux + m01 * muy + v0, oy = m10 * mux + m11 * muy + v1;
+        const int src = (lane / T) * T + s_;
+        const double rx = __shfl_sync(0xffffffffu, ox, src), ry = __shfl_sync(0xffffffffu, oy, src);
+        if (j == s_ - 1) {
+            mux = rx;
+            muy = ry;
+        }
+    }
+    // ---- pass 2: the ordinary sweep over the chunk
+    if (alive) {
+        double acc[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc[i] = 0.0;
+        int acc_cell = -1, hint = -1;
+        for (int k = khi; k >= klo; --k) {
+            const size_t o = (size_t)k * K + b;
+            double2 p = __ldg(x + o);
+            const double2 U = __ldg(u + o), D = __ldg(ud + o);
+            const double ex = U.x - D.x, ey = U.y - D.y;
+            misfit += ex * ex + ey * ey;
+            if (masked) {
+                if (mu) __stcs(mu + o, make_double2(0.0, 0.0));
+                continue;
+            }
+            double l0, l1, l2;
+            double ukx = U.x, uky = U.y;
+            bool lost;
+            const int c = locate_sample(k, p, hint, l0, l1, l2, lost);
+            if (lost) {
+                ukx = 0.0;
+                uky = 0.0;
+            } else if (park && k == nt - 1) {
+                // the stored velocity of a parked last sample is 0, the scatter loop re-evaluates u(centre)
+                eval_p2_cell_g(vel, c, l0, l1, l2, ukx, uky);
+            }
+            if (mu) __stcs(mu + o, make_double2(mux, muy));
+            if (c >= 0) {
+                if (c != acc_cell) {
+                    if (acc_cell >= 0) {
+                        if (X)
+                            flush_sources_exact<false>(digits, dovf, t.cell_nodes, acc_cell, acc);
+                        else
+                            flush_sources_g(acc_out, t, acc_cell, acc);
+                    }
+                    acc_cell = c;
+                }
+                const double gx = h * ((D.x - ukx) + mux), gy = h * ((D.y - uky) + muy);
+                double phi[6];
+                p2_basis(l0, l1, l2, phi);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    acc[i] = fma(gx, phi[i], acc[i]);
+                    acc[6 + i] = fma(gy, phi[i], acc[6 + i]);
+                }
+                if (k > 0) {
+                    double G0, G1, G2, G3;
+                    grad_at(c, l0, l1, l2, G0, G1, G2, G3);
+                    const double rx = ex - mux, ry = ey - muy;
+                    mux = mux - h * (G0 * rx + G2 * ry);
+                    muy = muy - h * (G1 * rx + G3 * ry);
+                }
+            }
+        }
+        if (acc_cell >= 0) {
+            if (X)
+                flush_sources_exact<false>(digits, dovf, t.cell_nodes, acc_cell, acc);
+            else
+                flush_sources_g(acc_out, t, acc_cell, acc);
+        }
+    }
+    block_finish2(misfit, nmasked, scratch, counter, acc_out + 2 * (size_t)t.nn, acc_out + 2 * (size_t)t.nn + 1,
+                  0.5 * h);
+}
+
 // b += sum over the private copies, in copy order (deterministic given the copies)
 __global__ void reduce_private_kernel(int n, int nrep, const double *__restrict__ bpriv, double *__restrict__ b) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -700,7 +1140,9 @@ __global__ void transpose_kernel(const double2 *__restrict__ src, double2 *__res
 
 }  // namespace
 
-int buoy_max_blocks(int K) { return std::max(160, (K + kBuoyThreads - 1) / kBuoyThreads); }
+// upper bound of the CTAs of one sweep launch (sizes the partial-sum scratch): serial sweep K / 128, time-parallel
+// sweep (K <= 12000) at most 32 lanes per buoy
+int buoy_max_blocks(int K) { return std::max(3200, (K + kBuoyThreads - 1) / kBuoyThreads); }
 
 int buoy_private_copies(int K, int nc, int nn) {
     if ((long long)K < 8LL * nc) return 1;                        // few buoys per cell: no contention to avoid
@@ -753,6 +1195,20 @@ bool allow_smem(Kern k, size_t bytes) {
 
 }  // namespace
 
+// Lanes per buoy of the time-parallel backward sweep: 32 for the thesis' buoy counts (<= 2000), 8 up to the 10 000-buoy
+// run, 1 (serial sweep, bandwidth-bound) beyond.  OCP_BUOY_TP=0 forces the serial sweep.
+int time_parallel_lanes(int K, int nt, int nrep) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char *e = getenv("OCP_BUOY_TP");
+        enabled = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (!enabled || nrep > 1 || nt < 64) return 1;
+    if (K <= 2000) return 32;
+    if (K <= 12000) return 8;
+    return 1;
+}
+
 bool buoy_tables_fit_shared(int nc, int nn, int nv) {
     return staged_bytes(nc, 16 * (size_t)nn) <= kSmemBudget && staged_bytes(nc, 32 * (size_t)nv) <= kSmemBudget;
 }
@@ -780,8 +1236,8 @@ void launch_buoy_forward(const DeviceTables &t, bool staged, const double *field
         buoy_forward_kernel<true><<<sh.grid, sh.threads, smem, s>>>(t, f2, x02, K, sh.per_block, nt, h, cx, cy, x2, u2,
                                                                     cell, mask, parked);
     } else {
-        buoy_forward_kernel<false><<<(K + kBuoyThreads - 1) / kBuoyThreads, kBuoyThreads, 0, s>>>(
-            t, f2, x02, K, kBuoyThreads, nt, h, cx, cy, x2, u2, cell, mask, parked);
+        buoy_forward_global_kernel<<<(K + kBuoyThreads - 1) / kBuoyThreads, kBuoyThreads, 0, s>>>(
+            t, f2, x02, K, nt, h, cx, cy, x2, u2, cell, mask, parked);
     }
 }
 
@@ -822,12 +1278,32 @@ void launch_buoy_adjoint_scatter(const DeviceTables &t, bool staged, const doubl
             else
                 buoy_adjoint_scatter_kernel<true, kDepthLarge, false><<<sh.grid, sh.threads, smem, s>>>(OCP_BWD_ARGS);
         }
+    } else if (time_parallel_lanes(K, nt, nrep) > 1) {
+        // small launch: T lanes per buoy (see buoy_adjoint_scatter_tp_kernel); no private copies at these sizes
+        const int T = time_parallel_lanes(K, nt, nrep);
+        const long long threads = (long long)((K + (32 / T) - 1) / (32 / T)) * 32;
+        const int grid = (int)((threads + kBuoyThreads - 1) / kBuoyThreads);
+#define OCP_TP_ARGS t, fv, fg, K, nt, h, cx, cy, x2, u2, d2, mask, parked, mu2, acc, scratch, counter, digits
+        if (T == 32) {
+            if (exact)
+                buoy_adjoint_scatter_tp_kernel<32, true><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
+            else
+                buoy_adjoint_scatter_tp_kernel<32, false><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
+        } else {
+            if (exact)
+                buoy_adjoint_scatter_tp_kernel<8, true><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
+            else
+                buoy_adjoint_scatter_tp_kernel<8, false><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
+        }
+#undef OCP_TP_ARGS
     } else {
-        const int per = kBuoyThreads, grid = (K + kBuoyThreads - 1) / kBuoyThreads;
+        const int grid = (K + kBuoyThreads - 1) / kBuoyThreads;
         if (exact)
-            buoy_adjoint_scatter_kernel<false, kDepthLarge, true><<<grid, kBuoyThreads, 0, s>>>(OCP_BWD_ARGS);
+            buoy_adjoint_scatter_global_kernel<true><<<grid, kBuoyThreads, 0, s>>>(
+                t, fv, fg, K, nt, h, cx, cy, x2, u2, d2, mask, parked, mu2, acc, scratch, counter, bpriv, nrep, digits);
         else
-            buoy_adjoint_scatter_kernel<false, kDepthLarge, false><<<grid, kBuoyThreads, 0, s>>>(OCP_BWD_ARGS);
+            buoy_adjoint_scatter_global_kernel<false><<<grid, kBuoyThreads, 0, s>>>(
+                t, fv, fg, K, nt, h, cx, cy, x2, u2, d2, mask, parked, mu2, acc, scratch, counter, bpriv, nrep, digits);
     }
 #undef OCP_BWD_ARGS
     if (exact) {

@@ -95,7 +95,7 @@ struct ocp_ctx {
     size_t bpriv_len = 0;
     long long *d_digits = nullptr;                     // integer digit sums of the reproducible deposit
     size_t digits_len = 0;
-    bool buoy_staged = false;     // mesh tables fit shared memory: TMA-staged buoy kernels (OCP_BUOY_STAGED=0 disables)
+    bool buoy_staged = false;     // TMA-staged buoy kernels (mesh tables in shared memory), opt-in: OCP_BUOY_STAGED=1
     bool deterministic = false;   // ocp_set_deterministic / OCP_DETERMINISTIC=1
     size_t scratch_len = 0;
     unsigned *d_counter = nullptr;
@@ -368,8 +368,9 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     if (const char *er = getenv("OCP_ADJ_REFINE")) c->adj_refine = std::max(0, atoi(er));
     if (const char *er = getenv("OCP_ADJ_REUSE")) c->adj_reuse = atoi(er) != 0;
     if (const char *ed = getenv("OCP_DETERMINISTIC")) c->deterministic = atoi(ed) != 0;
-    c->buoy_staged = buoy_tables_fit_shared(d->nc, d->nn, d->nv);
-    if (const char *es = getenv("OCP_BUOY_STAGED")) c->buoy_staged = c->buoy_staged && atoi(es) != 0;
+    // staged (shared-memory / TMA) buoy kernels are opt-in: measured slower than the global-table kernels on B200
+    if (const char *es = getenv("OCP_BUOY_STAGED"))
+        c->buoy_staged = atoi(es) != 0 && buoy_tables_fit_shared(d->nc, d->nn, d->nv);
     c->nv = d->nv; c->nn = d->nn; c->nc = d->nc; c->ndofs = d->ndofs; c->nnz = d->nnz;
     c->n_dir = d->n_dirichlet; c->n_g1 = d->n_g1; c->nt = d->nt;
     c->nu = d->viscosity; c->dt = d->dt; c->cx = d->center_x; c->cy = d->center_y;
