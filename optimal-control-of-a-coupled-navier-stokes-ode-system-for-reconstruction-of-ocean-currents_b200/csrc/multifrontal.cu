@@ -36,6 +36,8 @@ struct MFDev {
     int *piv;
     double *dinv;              // per 16-column panel: inverse of the unit-lower and of the upper diagonal block (2 x 256)
     const int *dinv_ptr;       // per front: index of its first panel in dinv
+    double *dinv64;            // per 64-pivot block of a SMALL front: [L11^-1 | U11^-1], each 64 x 64 row-major
+    const int *dinv64_ptr;     // per front: index of its first 64-pivot block in dinv64 (small fronts only)
 };
 
 __global__ void scatter_values_kernel(int nnz, const long long *__restrict__ dest, const double *__restrict__ vals,
@@ -720,6 +722,260 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// Triangular solves of the small fronts in 64-ROW blocks.  The solve of a front is a dependent chain over its pivot
+// blocks (block b needs the update of blocks < b); with 16-row blocks the root front of the 32 x 32 mesh walks 12 such
+// steps, each costing two block barriers and an L2 round trip (~3 k cycles).  Here the explicit inverses of the
+// 64 x 64 diagonal blocks of L and U are formed once per factorisation (mf_dinv64_kernel), so a front has a quarter
+// of the steps, and each step is two fully parallel mat-vecs:
+//   (a) y_blk = D^-1 y_blk        256 threads, four per row (interleaved columns: coalesced), partial sums via smem
+//   (b) y_i  -= E(i, blk) y_blk   one thread per remaining row, its 64 factor entries requested up front - before
+//                                 (a) - so that their L2 latency overlaps the pivot-block product.
+constexpr int SB = 64;
+constexpr int TS6 = 384;     // threads of the 64-row-block solve kernels: 168 registers each keep the 64 entries of a row resident
+
+// One CTA of 64 threads per (64-pivot block, L or U): thread c forms column c of the inverse by substitution with the
+// block in shared memory and all of its 64 unknowns in registers (outer-product form: the 64 dependent steps each
+// update independent registers).  Rows / columns beyond a partial last block are identity padding.
+__global__ void __launch_bounds__(SB)
+mf_dinv64_kernel(MFDev d, const int *__restrict__ block_node, int nblocks) {
+    __shared__ double B[SB][SB + 1];
+    const int p = blockIdx.x >> 1, which = blockIdx.x & 1;      // which = 0: L11^-1, 1: U11^-1
+    if (p >= nblocks) return;
+    const int s = block_node[p];
+    const int m = d.m[s], np = d.np[s];
+    const int k0 = (p - d.dinv64_ptr[s]) * SB, kb = min(SB, np - k0);
+    const double *F = d.F + d.front_ptr[s];
+    const int c = threadIdx.x;
+    for (int j = 0; j < SB; ++j)                                 // column j of the block, rows over the threads
+        B[c][j] = (c < kb && j < kb) ? __ldcg(F + (k0 + c) + (size_t)(k0 + j) * m) : ((c == j) ? 1.0 : 0.0);
+    __syncthreads();
+    double x[SB];
+#pragma unroll
+    for (int i = 0; i < SB; ++i) x[i] = (i == c) ? 1.0 : 0.0;
+    if (which == 0) {
+        // L x = e_c, L unit lower: for k ascending, x_i -= L[i][k] x_k (i > k)
+#pragma unroll
+        for (int k = 0; k < SB; ++k) {
+            const double xk = x[k];
+#pragma unroll
+            for (int i = 0; i < SB; ++i)
+                if (i > k) x[i] = fma(-B[i][k], xk, x[i]);
+        }
+    } else {
+        // U x = e_c, U upper with its diagonal: for k descending, x_k /= U[k][k], x_i -= U[i][k] x_k (i < k)
+#pragma unroll
+        for (int k = SB - 1; k >= 0; --k) {
+            const double xk = x[k] * fast_rcp(B[k][k]);
+            x[k] = xk;
+#pragma unroll
+            for (int i = 0; i < SB; ++i)
+                if (i < k) x[i] = fma(-B[i][k], xk, x[i]);
+        }
+    }
+    double *dst = d.dinv64 + (size_t)p * (2 * SB * SB) + (size_t)which * (SB * SB);
+#pragma unroll
+    for (int i = 0; i < SB; ++i) dst[i * SB + c] = x[i];         // row-major X[i][c]: coalesced over the threads
+}
+
+// (a) of a block step: yb[r][.] = sum_t Dm(., t) y[r][k0 + t] with Dm = the stored inverse (DT = false) or its
+// transpose (DT = true); 256 threads.  Partial sums over four interleaved column classes meet in shared memory.
+template <bool DT, int NR>
+__device__ __forceinline__ void block_inverse_apply(const double *__restrict__ Dblk, const double *y, int m, int k0,
+                                                    int kb, int tid, double (*part)[NR][SB]) {
+    if (tid < 4 * SB) {
+        // DT = false: lanes run over the column class q (four lanes share a row: 32 contiguous bytes per row);
+        // DT = true: lanes run over the rows (the transposed entry X[t][r] is contiguous in r)
+        const int r = DT ? (tid & (SB - 1)) : (tid >> 2), q = DT ? (tid >> 6) : (tid & 3);
+        double a[NR];
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) a[rr] = 0.0;
+#pragma unroll
+        for (int s4 = 0; s4 < SB / 4; ++s4) {
+            const int t = q + 4 * s4;
+            const double e = __ldg(Dblk + (DT ? t * SB + r : r * SB + t));
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) a[rr] = fma(e, (t < kb) ? y[rr * m + k0 + t] : 0.0, a[rr]);
+        }
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) part[q][rr][r] = a[rr];
+    }
+}
+
+// forward: y_P = L11^-1 b_P, b_U -= L21 y_P;  TR: the same sweep with U^T in place of L
+template <bool TR, int NR>
+__global__ void __launch_bounds__(TS6, 1)
+mf_forward64_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x, int ldx) {
+    extern __shared__ double y[];          // NR vectors of length m
+    __shared__ double yb[NR][SB];
+    __shared__ double part[4][NR][SB];
+    const int s = nodes[blockIdx.x];
+    const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
+    if (np == 0) return;
+    const double *F = d.F + d.front_ptr[s];
+    const int *I = d.idx + d.idx_ptr[s];
+    // plain: L11^-1; transposed: (U11^-1)^T
+    const double *Dinv = d.dinv64 + (size_t)d.dinv64_ptr[s] * (2 * SB * SB) + (TR ? SB * SB : 0);
+    const int nblk = (np + SB - 1) / SB;
+    for (int off = tid * 16; off < nblk * 2 * SB * SB; off += TS6 * 16)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(d.dinv64 + (size_t)d.dinv64_ptr[s] * (2 * SB * SB) + off));
+    for (int r = 0; r < NR; ++r)
+        for (int k = tid; k < m; k += TS6) y[r * m + k] = k < np ? x[(size_t)r * ldx + I[k]] : 0.0;
+    __syncthreads();
+    for (int b = 0; b < nblk; ++b) {
+        const int k0 = b * SB, kb = min(SB, np - k0);
+        // factor entries of this thread's first remaining row: requested before the pivot-block product
+        const int i0 = k0 + kb + tid;
+        double e[SB];
+        if (i0 < m) {
+#pragma unroll
+            for (int t = 0; t < SB; ++t) e[t] = (t < kb) ? MF_E(i0, k0 + t) : 0.0;
+        }
+        block_inverse_apply<TR, NR>(Dinv + (size_t)b * (2 * SB * SB), y, m, k0, kb, tid, part);
+        __syncthreads();
+        if (tid < SB * NR) {
+            const int rr = tid / SB, r = tid % SB;
+            const double v = (part[0][rr][r] + part[1][rr][r]) + (part[2][rr][r] + part[3][rr][r]);
+            yb[rr][r] = v;
+            if (r < kb) y[rr * m + k0 + r] = v;
+        }
+        __syncthreads();
+        for (int i = i0; i < m; i += TS6) {
+            if (i != i0) {
+#pragma unroll
+                for (int t = 0; t < SB; ++t) e[t] = (t < kb) ? MF_E(i, k0 + t) : 0.0;
+            }
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;          // four chains of 16 instead of one of 64
+#pragma unroll
+                for (int t = 0; t < SB; t += 4) {
+                    a0 = fma(e[t], yb[rr][t], a0);
+                    a1 = fma(e[t + 1], yb[rr][t + 1], a1);
+                    a2 = fma(e[t + 2], yb[rr][t + 2], a2);
+                    a3 = fma(e[t + 3], yb[rr][t + 3], a3);
+                }
+                y[rr * m + i] -= (a0 + a1) + (a2 + a3);
+            }
+        }
+        __syncthreads();
+    }
+    for (int r = 0; r < NR; ++r) {
+        for (int k = tid; k < np; k += TS6) x[(size_t)r * ldx + I[k]] = y[r * m + k];
+        for (int i = np + tid; i < m; i += TS6) atomicAdd(x + (size_t)r * ldx + I[i], y[r * m + i]);
+    }
+}
+
+// backward: x_P = U11^-1 (y_P - U12 x_U);   TR: x_P = L11^-T (y_P - L21^T x_U)
+template <bool TR, int NR>
+__global__ void __launch_bounds__(TS6, 1)
+mf_backward64_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ x, int ldx) {
+    extern __shared__ double y[];          // NR x m, then (plain) the per-warp partial sums of the U12 mat-vec
+    __shared__ double yb[NR][SB];
+    __shared__ double part4[4][NR][SB];
+    const int s = nodes[blockIdx.x];
+    const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
+    if (np == 0) return;
+    const double *F = d.F + d.front_ptr[s];
+    const int *I = d.idx + d.idx_ptr[s];
+    // plain: U11^-1; transposed: (L11^-1)^T
+    const double *Dinv = d.dinv64 + (size_t)d.dinv64_ptr[s] * (2 * SB * SB) + (TR ? 0 : SB * SB);
+    const int nblk = (np + SB - 1) / SB;
+    for (int off = tid * 16; off < nblk * 2 * SB * SB; off += TS6 * 16)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(d.dinv64 + (size_t)d.dinv64_ptr[s] * (2 * SB * SB) + off));
+    for (int r = 0; r < NR; ++r)
+        for (int k = tid; k < m; k += TS6) y[r * m + k] = x[(size_t)r * ldx + I[k]];
+    __syncthreads();
+    // y_P -= U12 x_U (TR: L21^T x_U), shared by all 16 warps (see mf_backward_kernel)
+    {
+        const int lane = tid & 31, wid = tid >> 5, NW = TS6 / 32;
+        if (!TR) {
+            double *part = y + (size_t)NR * m;                 // NW x (NR x np) partial sums
+            for (int k0 = 0; k0 < np; k0 += 32) {
+                const int k = k0 + lane;
+                double a[NR];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) a[r] = 0.0;
+                if (k < np) {
+                    for (int j = np + wid; j < m; j += NW) {
+                        const double e = __ldg(F + k + (size_t)j * m);
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) a[r] = fma(e, y[r * m + j], a[r]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) part[((size_t)wid * NR + r) * np + k] = a[r];
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < NR * np; e += TS6) {
+                const int r = e / np, k = e % np;
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) sum += part[((size_t)w * NR + r) * np + k];
+                y[r * m + k] -= sum;
+            }
+        } else {
+            for (int k = wid; k < np; k += NW) {
+                double a[NR];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) a[r] = 0.0;
+                for (int j = np + lane; j < m; j += 32) {
+                    const double e = __ldg(F + j + (size_t)k * m);
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) a[r] = fma(e, y[r * m + j], a[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
+                    if (lane == 0) y[r * m + k] -= a[r];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int k0 = b * SB, kb = min(SB, np - k0);
+        // rows above the block: entries of this thread's first row, requested before the pivot-block product
+        double e[SB];
+        if (tid < k0) {
+#pragma unroll
+            for (int t = 0; t < SB; ++t) e[t] = (t < kb) ? MF_E(tid, k0 + t) : 0.0;
+        }
+        block_inverse_apply<TR, NR>(Dinv + (size_t)b * (2 * SB * SB), y, m, k0, kb, tid, part4);
+        __syncthreads();
+        if (tid < SB * NR) {
+            const int rr = tid / SB, r = tid % SB;
+            const double v = (part4[0][rr][r] + part4[1][rr][r]) + (part4[2][rr][r] + part4[3][rr][r]);
+            yb[rr][r] = v;
+            if (r < kb) y[rr * m + k0 + r] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < k0; i += TS6) {
+            if (i != tid) {
+#pragma unroll
+                for (int t = 0; t < SB; ++t) e[t] = (t < kb) ? MF_E(i, k0 + t) : 0.0;
+            }
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                for (int t = 0; t < SB; t += 4) {
+                    a0 = fma(e[t], yb[rr][t], a0);
+                    a1 = fma(e[t + 1], yb[rr][t + 1], a1);
+                    a2 = fma(e[t + 2], yb[rr][t + 2], a2);
+                    a3 = fma(e[t + 3], yb[rr][t + 3], a3);
+                }
+                y[rr * m + i] -= (a0 + a1) + (a2 + a3);
+            }
+        }
+        __syncthreads();
+    }
+    for (int r = 0; r < NR; ++r)
+        for (int k = tid; k < np; k += TS6) x[(size_t)r * ldx + I[k]] = y[r * m + k];
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
 // Large fronts (m > kBigM: the top of the tree on refined meshes, cfg5).  A front no longer fits a cluster's shared
 // memory, so a GROUP of G co-resident CTAs (cooperative launch; the SMs are shared out among the level's large fronts in
 // proportion to their flops) works on it
@@ -1200,6 +1456,10 @@ struct MultifrontalLU::Impl {
     std::vector<BigLaunch> big_launches;
     int *panel_node = nullptr;   // front of every 16-pivot block (mf_dinv_kernel)
     int npanels = 0;
+    double *dinv64 = nullptr;    // inverses of the 64 x 64 diagonal blocks of the small fronts (mf_dinv64_kernel)
+    int *dinv64_ptr = nullptr, *block_node = nullptr;
+    int nblocks64 = 0;
+    bool solve64 = true;         // 64-row-block solve kernels for the small fronts (OCP_MF_SOLVE16=1: the 16-row ones)
     int4 *cta_map = nullptr;     // per CTA of every large-front launch: (front of the launch, rank in its group, group size)
     // CUDA graphs of the factor / solve launch sequences, keyed by the (fixed) device pointer they operate on
     std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs, solve_t_graphs, solve4_graphs;
@@ -1209,7 +1469,7 @@ struct MultifrontalLU::Impl {
     MFDev dev{};
     ~Impl() {
         void *p[] = {m, np, first, idx_ptr, idx, child_ptr, child, rel_ptr, rel, level_nodes, piv, info, front_ptr,
-                     a_dest, F, prof, dinv, dinv_ptr, bar, cta_map, panel_node};
+                     a_dest, F, prof, dinv, dinv_ptr, bar, cta_map, panel_node, dinv64, dinv64_ptr, block_node};
         for (void *q : p) cudaFree(q);
         for (auto &kv : factor_graphs) cudaGraphExecDestroy(kv.second);
         for (auto &kv : solve_graphs) cudaGraphExecDestroy(kv.second);
@@ -1321,6 +1581,8 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_kernel<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_kernel<1, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward_kernel<2, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward64_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_backward64_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int v = 0; v < kNumVariants && e == cudaSuccess; ++v) {
         e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -1448,8 +1710,24 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
             return false;
         }
     }
+    {
+        // 64-pivot blocks of the SMALL fronts (the large fronts keep the 16-row solve kernels)
+        if (const char *e16 = getenv("OCP_MF_SOLVE16")) I.solve64 = atoi(e16) == 0;
+        std::vector<int> dp(S.nnodes + 1, 0);
+        for (int k = 0; k < S.nnodes; ++k) dp[k + 1] = dp[k] + (S.m[k] > big_limit ? 0 : (S.np[k] + SB - 1) / SB);
+        std::vector<int> bn(dp[S.nnodes]);
+        for (int k = 0; k < S.nnodes; ++k)
+            for (int q = dp[k]; q < dp[k + 1]; ++q) bn[q] = k;
+        I.nblocks64 = dp[S.nnodes];
+        if (!up(&I.dinv64_ptr, dp, err) || !up(&I.block_node, bn, err)) return false;
+        if (I.solve64 &&
+            cudaMalloc((void **)&I.dinv64, sizeof(double) * 2 * SB * SB * std::max(I.nblocks64, 1)) != cudaSuccess) {
+            err = "multifrontal setup: out of memory";
+            return false;
+        }
+    }
     I.dev = MFDev{I.m, I.np, I.first, I.idx_ptr, I.idx, I.child_ptr, I.child, I.rel_ptr, I.rel, I.front_ptr, I.F, I.piv,
-                  I.dinv, I.dinv_ptr};
+                  I.dinv, I.dinv_ptr, I.dinv64, I.dinv64_ptr};
     factor_nnz_ = 0;
     for (int s = 0; s < S.nnodes; ++s)
         factor_nnz_ += (long long)S.m[s] * S.m[s] - (long long)(S.m[s] - S.np[s]) * (S.m[s] - S.np[s]);
@@ -1517,6 +1795,7 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
         }
     }
     if (npanels > 0) mf_dinv_kernel<<<(2 * npanels * 32 + 255) / 256, 256, 0, s>>>(dev, panel_node, npanels);
+    if (solve64 && nblocks64 > 0) mf_dinv64_kernel<<<2 * nblocks64, SB, 0, s>>>(dev, block_node, nblocks64);
     cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, s);
     return true;
 }
@@ -1536,7 +1815,7 @@ bool MultifrontalLU::factor(const double *d_vals, cudaStream_t s, std::string &e
         }
         I.dev.F = I.F;
     }
-    g_launch_count.fetch_add(2 + I.S.nlevels + (int)I.big_launches.size(), std::memory_order_relaxed);
+    g_launch_count.fetch_add(3 + I.S.nlevels + (int)I.big_launches.size(), std::memory_order_relaxed);
     const int nnz = nnz_;
     if (!I.run(I.factor_graphs, d_vals, s, err, [&](cudaStream_t q) { return I.enqueue_factor(d_vals, nnz, q, err); }))
         return false;
@@ -1580,6 +1859,10 @@ bool MultifrontalLU::check(std::string &err) {
 template <bool TR, int NR>
 static void launch_level_fwd(const MFDev &dev, const int *nodes, int nf, int max_m, double *d_x, int ldx, cudaStream_t s) {
     if (nf <= 0) return;
+    if (dev.dinv64) {
+        mf_forward64_kernel<TR, NR><<<nf, TS6, sizeof(double) * max_m * NR, s>>>(dev, nodes, d_x, ldx);
+        return;
+    }
     if (max_m <= TS)
         mf_forward_kernel<1, TR, NR><<<nf, TS, sizeof(double) * max_m * NR, s>>>(dev, nodes, d_x, ldx);
     else
@@ -1592,6 +1875,11 @@ static void launch_level_bwd(const MFDev &dev, const int *nodes, int nf, int max
     if (nf <= 0) return;
     // y (NR x m) plus, for the plain sweep, the per-warp partial sums of the U12 mat-vec (16 x NR x np)
     const size_t smem = sizeof(double) * NR * ((size_t)max_m + (TR ? 0 : (size_t)(TS / 32) * max_np));
+    if (dev.dinv64) {
+        const size_t smem6 = sizeof(double) * NR * ((size_t)max_m + (TR ? 0 : (size_t)(TS6 / 32) * max_np));
+        mf_backward64_kernel<TR, NR><<<nf, TS6, smem6, s>>>(dev, nodes, d_x, ldx);
+        return;
+    }
     if (max_m <= TS)
         mf_backward_kernel<1, TR, NR><<<nf, TS, smem, s>>>(dev, nodes, d_x, ldx);
     else
