@@ -585,6 +585,7 @@ def run_ours(args):
             "clocks": clocks,
             "line_items_ms_per_step": dict(items, n_factor_per_step=stats["n_factor"] / nprof,
                                            n_solve_per_step=stats["n_solve"] / nprof,
+                                           n_dense_operator_applies_per_step=stats["n_dense"] / nprof,
                                            one_time_symbolic_analysis_ms=stats["analyse_ms"]),
             "dominant_by_time": {"item": dom, "ms": items[dom], "share_of_step": items[dom] / ms_step},
             "amdahl": {"replicated_fe_ms": fe_ms, "sharded_buoy_ms": ms_fwd + ms_back,

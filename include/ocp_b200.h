@@ -83,6 +83,8 @@ typedef struct {
     double solve_ms;      /* triangular solves                                      */
     double analyse_ms;    /* one-time host symbolic analysis + first factorisation  */
     int32_t n_factor, n_solve;
+    int32_t n_dense;      /* solves replaced by a precomputed dense operator (Stokes step, mass matrix)   */
+    int32_t reserved;
 } ocp_solver_stats;
 
 int ocp_version(void);

@@ -54,7 +54,8 @@ class ProblemDesc(C.Structure):
 
 class SolverStats(C.Structure):
     _fields_ = [("assemble_ms", C.c_double), ("factor_ms", C.c_double), ("solve_ms", C.c_double),
-                ("analyse_ms", C.c_double), ("n_factor", C.c_int32), ("n_solve", C.c_int32)]
+                ("analyse_ms", C.c_double), ("n_factor", C.c_int32), ("n_solve", C.c_int32),
+                ("n_dense", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None

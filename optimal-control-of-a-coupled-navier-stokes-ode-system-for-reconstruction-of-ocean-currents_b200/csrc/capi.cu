@@ -88,7 +88,7 @@ struct ocp_ctx {
     double *d_m_vals = nullptr;
     int m_nnz = 0;
     // work space
-    double *d_vals = nullptr, *d_res = nullptr, *d_rhs = nullptr, *d_tmp = nullptr, *d_rhs4 = nullptr;
+    double *d_vals = nullptr, *d_res = nullptr, *d_rhs = nullptr, *d_tmp = nullptr, *d_rhs4 = nullptr, *d_proj4 = nullptr;
     double *d_scalar = nullptr, *d_scratch = nullptr;
     double *d_cellvel = nullptr, *d_cellg = nullptr;   // per-cell coefficient records read by the buoy kernels
     double *d_bpriv = nullptr;                         // private copies of the point-source vector (per SM id)
@@ -115,6 +115,17 @@ struct ocp_ctx {
     int n_adj_reused = 0, n_adj_fallback = 0;
     bool mass_factored = false;
     int adj_refine = 0;   // iterative-refinement steps of the adjoint solve (OCP_ADJ_REFINE); 0 is already ~1e-11
+    // Dense response operators that replace a tree solve by one mat-vec where they are small enough to precompute
+    // (OCP_DENSE_OPS=0 disables): (i) the first Newton step from the zero guess is w_1 = -S^-1 F(0; f), S = the Stokes
+    // operator, and F(0; f) = -int_G1 f.v lives on the velocity dofs of Gamma_1 only: w_1 = -(S^-1 E_G1) F(0; f)|_G1;
+    // (ii) the P1 mass matrix of the grad(u) projection is constant: its inverse.
+    bool dense_ops = true;
+    int *d_g1dofs = nullptr;
+    int n_g1dofs = 0;
+    double *d_stokes_resp = nullptr;   // (ndofs x n_g1dofs) column-major: columns S^-1 e_j, j in the Gamma_1 velocity dofs
+    bool stokes_resp_valid = false;
+    double *d_minv = nullptr;          // (nv x nv) inverse of the P1 mass matrix
+    bool minv_valid = false;
     Communicator comm;    // NCCL communicator when the buoys are sharded over ranks (ocp_comm_init); 1 rank otherwise
     ocp_solver_stats stats{};
     bool profile = false;
@@ -275,6 +286,47 @@ int run_buoy_backward(ocp_ctx *c, const double *d_vel, const double *d_g, int K,
     return OCP_OK;
 }
 
+__global__ void unit_vectors_kernel(int n, int nrhs, const int *idx, int j0, int ncol, double *v) {
+    // v (nrhs x n) = unit vectors e_{idx[j0 + r]} (idx null: e_{j0 + r}); rows beyond ncol stay zero
+    const int r = blockIdx.x;
+    if (r < nrhs && threadIdx.x == 0 && j0 + r < ncol) v[(size_t)r * n + (idx ? idx[j0 + r] : j0 + r)] = 1.0;
+}
+
+// (i) columns S^-1 e_j for the Gamma_1 velocity dofs, with the Stokes factors (one-time, n_g1dofs solves)
+int build_stokes_response(ocp_ctx *c) {
+    const int n = c->ndofs, ng = c->n_g1dofs;
+    cudaStream_t s = c->stream;
+    if (!c->d_stokes_resp) CUDA_OK(c, cudaMalloc((void **)&c->d_stokes_resp, sizeof(double) * (size_t)n * ng));
+    for (int j = 0; j < ng; ++j) {
+        CUDA_OK(c, cudaMemsetAsync(c->d_tmp, 0, sizeof(double) * n, s));
+        unit_vectors_kernel<<<1, 32, 0, s>>>(n, 1, c->d_g1dofs, j, ng, c->d_tmp);
+        if (!c->lu_stokes.solve(c->d_tmp, s, c->err)) return OCP_ERR_SOLVER;
+        CUDA_OK(c, cudaMemcpyAsync(c->d_stokes_resp + (size_t)j * n, c->d_tmp, sizeof(double) * n,
+                                   cudaMemcpyDeviceToDevice, s));
+    }
+    CUDA_OK(c, cudaGetLastError());
+    c->stokes_resp_valid = true;
+    return OCP_OK;
+}
+
+// (ii) inverse of the P1 mass matrix, four columns per pass of the factored mass matrix (one-time)
+int build_mass_inverse(ocp_ctx *c) {
+    const int nv = c->nv;
+    cudaStream_t s = c->stream;
+    if (!c->d_minv) CUDA_OK(c, cudaMalloc((void **)&c->d_minv, sizeof(double) * (size_t)nv * nv));
+    for (int j = 0; j < nv; j += 4) {
+        CUDA_OK(c, cudaMemsetAsync(c->d_rhs4, 0, sizeof(double) * 4 * nv, s));
+        unit_vectors_kernel<<<4, 32, 0, s>>>(nv, 4, nullptr, j, nv, c->d_rhs4);
+        if (!c->lu_mass.solve4(c->d_rhs4, nv, s, c->err)) return OCP_ERR_SOLVER;
+        const int nc4 = std::min(4, nv - j);
+        CUDA_OK(c, cudaMemcpyAsync(c->d_minv + (size_t)j * nv, c->d_rhs4, sizeof(double) * (size_t)nc4 * nv,
+                                   cudaMemcpyDeviceToDevice, s));
+    }
+    CUDA_OK(c, cudaGetLastError());
+    c->minv_valid = true;
+    return OCP_OK;
+}
+
 int read_scalar(ocp_ctx *c, const double *d, int n, double *h) {
     CUDA_OK(c, cudaMemcpyAsync(c->h_pinned, d, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -321,6 +373,7 @@ int ocp_set_dirichlet(ocp_ctx *c, const int32_t *h_dofs, const double *h_vals, i
     c->d_dirval = nullptr;
     c->n_dir = n;
     c->stokes_valid = false;
+    c->stokes_resp_valid = false;
     int rc = upload(c, &c->d_dir, h_dofs, (size_t)n);
     if (rc != OCP_OK) return rc;
     if (h_vals) {
@@ -353,6 +406,7 @@ void ocp_set_viscosity(ocp_ctx *ctx, double viscosity) {
     if (ctx) {
         ctx->nu = viscosity;
         ctx->stokes_valid = false;
+        ctx->stokes_resp_valid = false;
     }
 }
 
@@ -368,6 +422,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     if (const char *er = getenv("OCP_ADJ_REFINE")) c->adj_refine = std::max(0, atoi(er));
     if (const char *er = getenv("OCP_ADJ_REUSE")) c->adj_reuse = atoi(er) != 0;
     if (const char *ed = getenv("OCP_DETERMINISTIC")) c->deterministic = atoi(ed) != 0;
+    if (const char *ed = getenv("OCP_DENSE_OPS")) c->dense_ops = atoi(ed) != 0;
     // staged (shared-memory / TMA) buoy kernels are opt-in: measured slower than the global-table kernels on B200
     if (const char *es = getenv("OCP_BUOY_STAGED"))
         c->buoy_staged = atoi(es) != 0 && buoy_tables_fit_shared(d->nc, d->nn, d->nv);
@@ -411,6 +466,10 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
                 g1_slots[(size_t)f * 36 + i * 6 + j] = sl;
             }
     }
+    std::vector<int> g1dof_list(g1_dofs.begin(), g1_dofs.end());
+    std::sort(g1dof_list.begin(), g1dof_list.end());
+    g1dof_list.erase(std::unique(g1dof_list.begin(), g1dof_list.end()), g1dof_list.end());
+    c->n_g1dofs = (int)g1dof_list.size();
     // P1 mass matrix (constant): pattern + values, area/12 (1 + delta_ab)
     std::vector<std::vector<std::pair<int, double>>> rows(nv);
     for (int e = 0; e < nc; ++e) {
@@ -457,6 +516,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     UP(d_dir, d->dirichlet_dofs, d->n_dirichlet);
     UP(d_g1_nodes, d->g1_nodes, (size_t)d->n_g1 * 3);
     UP(d_g1_dofs, g1_dofs.data(), g1_dofs.size());
+    UP(d_g1dofs, g1dof_list.data(), g1dof_list.size());
     UP(d_g1_slots, g1_slots.data(), g1_slots.size());
     UP(d_g1_len, d->g1_len, d->n_g1);
     UP(d_g1_normal, d->g1_normal, (size_t)d->n_g1 * 2);
@@ -471,6 +531,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     CUDA_OK(c, cudaMalloc((void **)&c->d_rhs, sizeof(double) * n));
     CUDA_OK(c, cudaMalloc((void **)&c->d_tmp, sizeof(double) * n));
     CUDA_OK(c, cudaMalloc((void **)&c->d_rhs4, sizeof(double) * 4 * nv));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_proj4, sizeof(double) * 4 * nv));
     CUDA_OK(c, cudaMalloc((void **)&c->d_scalar, sizeof(double) * 8));
     CUDA_OK(c, cudaMalloc((void **)&c->d_cellvel, sizeof(double) * 12 * (size_t)nc));
     CUDA_OK(c, cudaMalloc((void **)&c->d_cellg, sizeof(double) * 12 * (size_t)nc));
@@ -521,7 +582,8 @@ void ocp_destroy(ocp_ctx *c) {
                     c->d_dof_ux, c->d_dof_uy, c->d_dof_p, c->d_rowptr, c->d_col, c->d_dir, c->d_g1_nodes,
                     c->d_g1_dofs, c->d_g1_slots, c->d_bin_ptr, c->d_bin_cells, c->d_m_rowptr, c->d_m_col,
                     c->d_m_vals, c->d_vals, c->d_res, c->d_rhs, c->d_tmp, c->d_rhs4, c->d_scalar, c->d_scratch,
-                    c->d_counter, c->d_parked, c->d_obs_x0, c->d_obs_ud, c->d_cell_nbr, c->d_cellvel, c->d_cellg, c->d_bpriv, c->d_dirval, c->d_digits};
+                    c->d_counter, c->d_parked, c->d_obs_x0, c->d_obs_ud, c->d_cell_nbr, c->d_cellvel, c->d_cellg, c->d_bpriv, c->d_dirval, c->d_digits, c->d_g1dofs,
+                    c->d_stokes_resp, c->d_minv, c->d_proj4};
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < 8; ++i) cudaFree(c->d_stage[i]);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -595,12 +657,25 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
             c->stats.n_factor++;
             if (stokes_step) c->stokes_valid = true;
         }
+        // dense path of the Stokes step (homogeneous Dirichlet data only: F(0; f) then lives on the Gamma_1 dofs)
+        const bool dense_step = stokes_step && c->dense_ops && !c->d_dirval && c->n_g1dofs > 0 &&
+                                (size_t)n * c->n_g1dofs * sizeof(double) <= ((size_t)64 << 20);
+        if (dense_step && !c->stokes_resp_valid) {
+            int rc2 = build_stokes_response(c);
+            if (rc2 != OCP_OK) return rc2;
+        }
         {
             PhaseTimer t(c, &c->stats.solve_ms);
-            if (!lu.solve(c->d_res, s, c->err)) return OCP_ERR_SOLVER;   // d_res <- dx
             c->last_newton_lu = &lu;
-            launch_axpy(n, -1.0, c->d_res, d_w, s);
-            c->stats.n_solve++;
+            if (dense_step) {
+                launch_dense_apply(n, c->n_g1dofs, 1, c->d_stokes_resp, c->d_res, n, c->d_g1dofs, c->d_tmp, s);
+                launch_axpy(n, -1.0, c->d_tmp, d_w, s);
+                c->stats.n_dense++;
+            } else {
+                if (!lu.solve(c->d_res, s, c->err)) return OCP_ERR_SOLVER;   // d_res <- dx
+                launch_axpy(n, -1.0, c->d_res, d_w, s);
+                c->stats.n_solve++;
+            }
         }
         ++it;
     }
@@ -630,11 +705,25 @@ int ocp_project_grad(ocp_ctx *c, const double *d_w, double *d_g) {
         if (!c->lu_mass.factor(c->d_m_vals, s, c->err)) return OCP_ERR_SOLVER;
         c->mass_factored = true;
     }
+    const bool dense_mass = c->dense_ops && nv <= 2048;
+    if (dense_mass && !c->minv_valid) {
+        // (the right-hand sides are rebuilt below: the one-time construction uses the same work array)
+        int rc2 = build_mass_inverse(c);
+        if (rc2 != OCP_OK) return rc2;
+        CUDA_OK(c, cudaMemsetAsync(c->d_rhs4, 0, sizeof(double) * 4 * nv, s));
+        launch_gradproj_rhs(c->nc, nv, c->d_geom, c->d_cell_nodes, c->d_cell_dofs, d_w, c->d_rhs4, s);
+    }
     {
         PhaseTimer t(c, &c->stats.solve_ms);
-        if (!c->lu_mass.solve4(c->d_rhs4, nv, s, c->err)) return OCP_ERR_SOLVER;   // the four components at once
-        c->stats.n_solve++;
-        launch_transpose4(nv, c->d_rhs4, d_g, s);
+        if (dense_mass) {
+            launch_dense_apply(nv, nv, 4, c->d_minv, c->d_rhs4, nv, nullptr, c->d_proj4, s);
+            launch_transpose4(nv, c->d_proj4, d_g, s);
+            c->stats.n_dense++;
+        } else {
+            if (!c->lu_mass.solve4(c->d_rhs4, nv, s, c->err)) return OCP_ERR_SOLVER;   // the four components at once
+            c->stats.n_solve++;
+            launch_transpose4(nv, c->d_rhs4, d_g, s);
+        }
         CUDA_OK(c, cudaGetLastError());
     }
     return OCP_OK;

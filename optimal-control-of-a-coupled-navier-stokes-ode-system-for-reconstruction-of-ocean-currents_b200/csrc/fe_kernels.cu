@@ -317,6 +317,42 @@ fp64_peak_kernel(double *out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// out[r n + i] = sum_j R[i + j n] x[r ldx + (idx ? idx[j] : j)],  r < NR  (R column-major n x ncol): dense response
+// operators that replace a sparse triangular solve when they are small enough to precompute (see capi.cu).  One thread
+// per row, two independent partial sums per right-hand side, the gathered x staged in shared memory.
+template <int NR>
+__global__ void __launch_bounds__(128)
+dense_apply_kernel(int n, int ncol, const double *__restrict__ R, const double *__restrict__ x, int ldx,
+                   const int *__restrict__ idx, double *__restrict__ out) {
+    extern __shared__ double xs[];          // NR x ncol
+    for (int e = threadIdx.x; e < NR * ncol; e += blockDim.x) {
+        const int r = e / ncol, j = e - r * ncol;
+        xs[e] = x[(size_t)r * ldx + (idx ? idx[j] : j)];
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a[NR], b[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) a[r] = b[r] = 0.0;
+    int j = 0;
+    for (; j + 2 <= ncol; j += 2) {
+        const double e0 = __ldg(R + i + (size_t)j * n), e1 = __ldg(R + i + (size_t)(j + 1) * n);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            a[r] = fma(e0, xs[r * ncol + j], a[r]);
+            b[r] = fma(e1, xs[r * ncol + j + 1], b[r]);
+        }
+    }
+    if (j < ncol) {
+        const double e0 = __ldg(R + i + (size_t)j * n);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) a[r] = fma(e0, xs[r * ncol + j], a[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) out[(size_t)r * n + i] = a[r] + b[r];
+}
+
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
@@ -405,6 +441,23 @@ void launch_field_norms(int nc, const double *geom, const int *cell_dofs, const 
                         double *scratch, unsigned *counter, cudaStream_t s) {
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     field_norms_kernel<<<cdiv(nc, 128), 128, 0, s>>>(nc, geom, cell_dofs, w, out3, scratch, counter);
+}
+
+void launch_dense_apply(int n, int ncol, int nrhs, const double *R, const double *x, int ldx, const int *idx,
+                        double *out, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    const size_t smem = sizeof(double) * ncol * nrhs;
+    if (nrhs == 4) {
+        static bool once = cudaFuncSetAttribute(dense_apply_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess;
+        (void)once;
+        dense_apply_kernel<4><<<cdiv(n, 128), 128, smem, s>>>(n, ncol, R, x, ldx, idx, out);
+    } else {
+        static bool once = cudaFuncSetAttribute(dense_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess;
+        (void)once;
+        for (int r = 0; r < nrhs; ++r)
+            dense_apply_kernel<1><<<cdiv(n, 128), 128, sizeof(double) * ncol, s>>>(n, ncol, R, x + (size_t)r * ldx, ldx, idx,
+                                                                                 out + (size_t)r * n);
+    }
 }
 
 double launch_fp64_peak(double *out, int blocks, int threads, int iters, cudaStream_t s) {

@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Profiling driver: a few full gradient evaluations of the cfg3 workload (10 000 buoys, square 32 x 32) - the bench
+step without the bench harness, for ncu launch lists and captures:
+
+    ncu --cache-control none --clock-control none --metrics gpu__time_duration.sum --csv python tools/prof_step.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ocp_b200  # noqa: E402,F401
+from ocp_b200.fespace import TaylorHood  # noqa: E402
+from ocp_b200.mesh import square_mesh  # noqa: E402
+from ocp_b200.pipeline import OCP, Parameters, initial_control  # noqa: E402
+
+N = int(os.environ.get("MESH_N", "32"))
+STEPS = int(os.environ.get("STEPS", "3"))
+V = TaylorHood(square_mesh(N))
+gx, gy = np.meshgrid(np.linspace(0.1, 0.4, 100), np.linspace(0.25, 1.75, 100))
+x0 = np.stack([gx.ravel(), gy.ravel()], 1)
+K = x0.shape[0]
+ocp = OCP(V, Parameters(), x0, None)
+f0 = torch.from_numpy(initial_control(V, "PL")).cuda()
+if N == 32:
+    w = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "fields.npz"))["velocity_100"]).cuda()
+else:
+    w = ocp.forward_solve(1.3 * f0).d_w
+ocp._primal(w, ocp.d_x, ocp.d_u, ocp.d_mask)
+ocp.d_ud.copy_(ocp.d_u)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+for it in range(STEPS):
+    ocp.d_f.copy_(f0)
+    ev[0].record()
+    ocp.gradient_step(ocp.d_f)
+    ev[1].record()
+    torch.cuda.synchronize()
+    print(f"step {it}: {ev[0].elapsed_time(ev[1]):.3f} ms, newton its {ocp.last_newton_its}", flush=True)
+print("J", ocp._cost_from_acc(ocp.d_f))
