@@ -239,6 +239,12 @@ int64_t ocp_host_mf_probe(int32_t n, const int32_t *rowptr, const int32_t *col, 
  * value = partial pivoting restricted to the front's fully-summed rows (used by tests to validate static pivoting). */
 void ocp_host_mf_set_pivot_window(int rows);
 
+/* Host emulation of the atomic-free (gather) assembly on the tables ocp_create builds for it: cell part of the Newton
+ * matrix (vals, nnz) and residual (res, ndofs) at w, and - when vals_t is given - its transpose through the pattern's
+ * transposition permutation.  stats4 = [#CTAs, max rounds, facet colours, shared-memory bytes].  For CPU-only tests. */
+int64_t ocp_host_gather_probe(const ocp_problem_desc *desc, const double *w, double nu, double *vals, double *res,
+                              double *vals_t, int32_t *stats4);
+
 /* ---- element-level self-tests (host evaluation of the kernels' __host__ __device__ element arithmetic for one
  * element; used by CPU-only unit tests, never by a compute path).  coef15 = [u_x(6) u_y(6) p(3)];
  * uv6 = [u_x(va,vb,mid) u_y(va,vb,mid)], f6 likewise for the control. */

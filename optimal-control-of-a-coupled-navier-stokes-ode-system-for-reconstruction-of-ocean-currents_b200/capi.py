@@ -29,7 +29,7 @@ SYMBOLS = [
     "ocp_solve_primal_ode_host", "ocp_solve_adjoint_ode_host", "ocp_set_observations_host", "ocp_gradient_host",
     "ocp_launch_count", "ocp_get_solver_info", "ocp_selftest_fp64_peak",
     "ocp_comm_get_unique_id", "ocp_comm_init", "ocp_comm_size", "ocp_comm_nccl_version", "ocp_allreduce",
-    "ocp_host_lu_probe", "ocp_host_mf_probe", "ocp_host_mf_set_pivot_window", "ocp_selftest_cell_matrix", "ocp_selftest_facet_matrix",
+    "ocp_host_gather_probe", "ocp_host_lu_probe", "ocp_host_mf_probe", "ocp_host_mf_set_pivot_window", "ocp_selftest_cell_matrix", "ocp_selftest_facet_matrix",
 ]
 
 
@@ -75,6 +75,7 @@ def load_library() -> C.CDLL:
         lib.ocp_destroy.restype = None
         lib.ocp_host_lu_probe.restype = C.c_int64
         lib.ocp_host_mf_probe.restype = C.c_int64
+        lib.ocp_host_gather_probe.restype = C.c_int64
         lib.ocp_host_mf_set_pivot_window.restype = None
         lib.ocp_launch_count.restype = C.c_longlong
         lib.ocp_set_viscosity.argtypes = [C.c_void_p, C.c_double]
@@ -106,6 +107,47 @@ def _dp(t):
     if not t.is_cuda or not t.is_contiguous():
         raise OcpError("expected a contiguous CUDA tensor")
     return C.c_void_p(t.data_ptr())
+
+
+def problem_desc(V, viscosity: float, dt: float, nt: int, center):
+    """(ProblemDesc, arrays that must stay alive) for a TaylorHood space."""
+    m = V.mesh
+    keep = dict(
+        geom=np.ascontiguousarray(V.cell_geom, np.float64),
+        cn=np.ascontiguousarray(V.cell_nodes, np.int32),
+        nbr=np.ascontiguousarray(V.cell_nbr, np.int32),
+        xy=np.ascontiguousarray(V.node_coords, np.float64),
+        ux=np.ascontiguousarray(V.dof_ux, np.int32), uy=np.ascontiguousarray(V.dof_uy, np.int32),
+        pp=np.ascontiguousarray(V.dof_p, np.int32),
+        rp=np.ascontiguousarray(V.csr_rowptr, np.int32), ci=np.ascontiguousarray(V.csr_col, np.int32),
+        dd=np.ascontiguousarray(V.dirichlet_dofs, np.int32),
+        g1n=np.ascontiguousarray(V.g1_nodes, np.int32), g1l=np.ascontiguousarray(V.g1_len, np.float64),
+        g1m=np.ascontiguousarray(V.g1_normal, np.float64),
+        bp=np.ascontiguousarray(V.bin_ptr, np.int32), bc=np.ascontiguousarray(V.bin_cells, np.int32),
+    )
+    d = ProblemDesc(
+        m.num_vertices, V.num_nodes, m.num_cells, V.ndofs, int(V.csr_col.size), int(V.dirichlet_dofs.size),
+        int(V.g1_cell.size), int(nt),
+        _hp(keep["geom"]), _hp(keep["cn"]), _hp(keep["nbr"]), _hp(keep["xy"]), _hp(keep["ux"]), _hp(keep["uy"]), _hp(keep["pp"]),
+        _hp(keep["rp"]), _hp(keep["ci"]), _hp(keep["dd"]), _hp(keep["g1n"]), _hp(keep["g1l"]), _hp(keep["g1m"]),
+        float(V.bin_origin[0]), float(V.bin_origin[1]), float(V.bin_inv_h[0]), float(V.bin_inv_h[1]),
+        int(V.bin_dims[0]), int(V.bin_dims[1]), _hp(keep["bp"]), _hp(keep["bc"]),
+        float(viscosity), float(dt), float(center[0]), float(center[1]),
+    )
+    return d, keep
+
+
+def host_gather_probe(V, w, nu: float = 1.0):
+    """Host emulation of the atomic-free assembly tables: returns (vals, res, vals_transposed, stats)."""
+    lib = load_library()
+    d, keep = problem_desc(V, nu, 0.005, 200, (1.0, 1.0))
+    w = np.ascontiguousarray(w, np.float64)
+    vals, res, vt = np.zeros(int(V.csr_col.size)), np.zeros(V.ndofs), np.zeros(int(V.csr_col.size))
+    st = np.zeros(4, np.int32)
+    rc = lib.ocp_host_gather_probe(C.byref(d), _hp(w), C.c_double(nu), _hp(vals), _hp(res), _hp(vt), _hp(st))
+    if rc < 0:
+        raise OcpError(f"gather tables not representable for this mesh ({ERRORS.get(rc, rc)})")
+    return vals, res, vt, dict(ctas=int(st[0]), rounds=int(st[1]), colors=int(st[2]), smem_bytes=int(st[3]))
 
 
 class Context:

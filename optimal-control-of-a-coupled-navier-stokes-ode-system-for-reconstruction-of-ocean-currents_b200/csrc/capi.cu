@@ -115,6 +115,11 @@ struct ocp_ctx {
     int n_adj_reused = 0, n_adj_fallback = 0;
     bool mass_factored = false;
     int adj_refine = 0;   // iterative-refinement steps of the adjoint solve (OCP_ADJ_REFINE); 0 is already ~1e-11
+    // atomic-free, bit-reproducible assembly (default; OCP_ASSEMBLY=atomic selects the fp64-atomic scatter kernels)
+    bool gather = false;
+    GatherTables gt{};
+    void *d_gather[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *d_vals2 = nullptr;    // un-transposed values of the adjoint assembly in gather mode
     // Dense response operators that replace a tree solve by one mat-vec where they are small enough to precompute
     // (OCP_DENSE_OPS=0 disables): (i) the first Newton step from the zero guess is w_1 = -S^-1 F(0; f), S = the Stokes
     // operator, and F(0; f) = -int_G1 f.v lives on the velocity dofs of Gamma_1 only: w_1 = -(S^-1 E_G1) F(0; f)|_G1;
@@ -224,14 +229,175 @@ struct PhaseTimer {
     }
 };
 
+// Host tables of the gather assembly (see fe_kernels.cu): (row, cell) pairs ordered by row, a partition of the rows
+// into CTAs of <= 256 pairs / <= 4096 CSR entries, per pair the positions of its 15 element columns inside the CSR
+// row, a colouring of the Gamma_1 facets, and the transposition permutation of the (symmetric) pattern.
+struct GatherHostCta { int first_pair, npairs, first_entry, nentries, first_row, nrows, rounds, pad; };
+struct GatherHost {
+    std::vector<GatherHostCta> ctas;
+    std::vector<int> pair_cell, cptr, cfac, tperm;
+    std::vector<unsigned> meta;
+    std::vector<unsigned char> pos;
+    int ncolors = 0;
+    size_t smem = 0;
+};
+
+// Returns false (the caller keeps the atomic kernels) if a limit of the packed encoding is exceeded.
+bool build_gather_host(const ocp_problem_desc *d, const std::vector<int> &cell_dofs, const std::vector<int> &slots,
+                       GatherHost &G) {
+    const int n = d->ndofs, nc = d->nc;
+    const int *rowptr = d->csr_rowptr;
+    std::vector<int> rp(n + 1, 0);
+    for (size_t k = 0; k < cell_dofs.size(); ++k) rp[cell_dofs[k] + 1]++;
+    for (int i = 0; i < n; ++i) {
+        if (rp[i + 1] == 0 || rp[i + 1] > 15) return false;      // a dof without a cell / more than 15 adjacent cells
+        rp[i + 1] += rp[i];
+    }
+    const int npairs = rp[n];
+    std::vector<int> fill(rp.begin(), rp.end() - 1), pair_lrow(npairs);
+    G.pair_cell.assign(npairs, 0);
+    for (int e = 0; e < nc; ++e)
+        for (int i = 0; i < 15; ++i) {
+            const int p = fill[cell_dofs[(size_t)e * 15 + i]]++;
+            G.pair_cell[p] = e;
+            pair_lrow[p] = i;
+        }
+    G.meta.assign(npairs, 0u);
+    G.pos.assign((size_t)npairs * 16, 0);
+    for (int r0 = 0; r0 < n;) {
+        int r1 = r0, rounds = 0;
+        while (r1 < n && rp[r1 + 1] - rp[r0] <= 256 && rowptr[r1 + 1] - rowptr[r0] <= 4096 && r1 - r0 < 256) {
+            rounds = std::max(rounds, rp[r1 + 1] - rp[r1]);
+            ++r1;
+        }
+        if (r1 == r0) return false;                               // a single row exceeds the CTA limits
+        for (int r = r0; r < r1; ++r) {
+            const int len = rowptr[r + 1] - rowptr[r];
+            if (len > 256) return false;
+            for (int p = rp[r]; p < rp[r + 1]; ++p) {
+                G.meta[p] = ((unsigned)(rowptr[r] - rowptr[r0]) << 16) | ((unsigned)(r - r0) << 8) |
+                            ((unsigned)pair_lrow[p] << 4) | (unsigned)(p - rp[r]);
+                for (int j = 0; j < 15; ++j) {
+                    const int sl = slots[(size_t)G.pair_cell[p] * 225 + pair_lrow[p] * 15 + j] - rowptr[r];
+                    if (sl < 0 || sl >= len) return false;
+                    G.pos[(size_t)p * 16 + j] = (unsigned char)sl;
+                }
+            }
+        }
+        GatherHostCta ct{rp[r0], rp[r1] - rp[r0], rowptr[r0], rowptr[r1] - rowptr[r0], r0, r1 - r0, rounds, 0};
+        G.smem = std::max(G.smem, sizeof(double) * (size_t)(ct.nentries + ct.nrows));
+        G.ctas.push_back(ct);
+        r0 = r1;
+    }
+    // colouring of the Gamma_1 facets: facets of one colour share no node
+    std::vector<int> color(d->n_g1, -1);
+    G.ncolors = 0;
+    for (int f = 0; f < d->n_g1; ++f) {
+        for (int col = 0;; ++col) {
+            bool ok = true;
+            for (int g = 0; g < f && ok; ++g)
+                if (color[g] == col)
+                    for (int a = 0; a < 3 && ok; ++a)
+                        for (int b = 0; b < 3 && ok; ++b)
+                            if (d->g1_nodes[3 * f + a] == d->g1_nodes[3 * g + b]) ok = false;
+            if (ok) {
+                color[f] = col;
+                G.ncolors = std::max(G.ncolors, col + 1);
+                break;
+            }
+        }
+    }
+    G.cptr.assign(G.ncolors + 1, 0);
+    G.cfac.assign(d->n_g1, 0);
+    for (int f = 0; f < d->n_g1; ++f) G.cptr[color[f] + 1]++;
+    for (int k = 0; k < G.ncolors; ++k) G.cptr[k + 1] += G.cptr[k];
+    {
+        std::vector<int> w(G.cptr.begin(), G.cptr.end() - 1);
+        for (int f = 0; f < d->n_g1; ++f) G.cfac[w[color[f]]++] = f;
+    }
+    // transposition permutation
+    G.tperm.assign(d->nnz, 0);
+    for (int i = 0; i < n; ++i)
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int t = find_slot(d->csr_rowptr, d->csr_col, d->csr_col[k], i);
+            if (t < 0) return false;
+            G.tperm[k] = t;
+        }
+    return true;
+}
+
+// cell dofs and the CSR slot of every element entry (host); false if the pattern misses an entry
+bool build_cell_tables(const ocp_problem_desc *d, std::vector<int> &cell_dofs, std::vector<int> &slots, std::string &err) {
+    const int nc = d->nc, nn = d->nn, nv = d->nv;
+    cell_dofs.assign((size_t)nc * 15, 0);
+    slots.assign((size_t)nc * 225, 0);
+    for (int e = 0; e < nc; ++e) {
+        const int *cn = d->cell_nodes + 6 * (size_t)e;
+        int *cd = cell_dofs.data() + 15 * (size_t)e;
+        for (int a = 0; a < 6; ++a) {
+            if (cn[a] < 0 || cn[a] >= nn) { err = "cell_nodes out of range"; return false; }
+            cd[a] = d->dof_ux[cn[a]];
+            cd[6 + a] = d->dof_uy[cn[a]];
+        }
+        for (int a = 0; a < 3; ++a) {
+            if (cn[a] >= nv) { err = "cell vertex index >= nv"; return false; }
+            cd[12 + a] = d->dof_p[cn[a]];
+        }
+        for (int i = 0; i < 15; ++i)
+            for (int j = 0; j < 15; ++j) {
+                int sl = find_slot(d->csr_rowptr, d->csr_col, cd[i], cd[j]);
+                if (sl < 0) { err = "CSR pattern misses an element entry"; return false; }
+                slots[(size_t)e * 225 + i * 15 + j] = sl;
+            }
+    }
+    return true;
+}
+
+bool build_gather_tables(ocp_ctx *c, const ocp_problem_desc *d, const std::vector<int> &cell_dofs,
+                         const std::vector<int> &slots) {
+    GatherHost G;
+    if (!build_gather_host(d, cell_dofs, slots, G)) return false;
+    auto upv = [&](int slot, const void *src, size_t bytes) {
+        if (cudaMalloc(&c->d_gather[slot], std::max<size_t>(bytes, 16)) != cudaSuccess) return false;
+        return bytes == 0 || cudaMemcpy(c->d_gather[slot], src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    if (!upv(0, G.ctas.data(), sizeof(GatherHostCta) * G.ctas.size()) ||
+        !upv(1, G.pair_cell.data(), sizeof(int) * G.pair_cell.size()) ||
+        !upv(2, G.meta.data(), sizeof(unsigned) * G.meta.size()) || !upv(3, G.pos.data(), G.pos.size()) ||
+        !upv(4, G.cptr.data(), sizeof(int) * G.cptr.size()) || !upv(5, G.cfac.data(), sizeof(int) * G.cfac.size()) ||
+        !upv(6, G.tperm.data(), sizeof(int) * G.tperm.size()) ||
+        cudaMalloc((void **)&c->d_vals2, sizeof(double) * std::max(d->nnz, 1)) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    c->gt.nctas = (int)G.ctas.size();
+    c->gt.ncolors = G.ncolors;
+    c->gt.smem_bytes = G.smem;
+    c->gt.ctas = c->d_gather[0];
+    c->gt.pair_cell = (const int *)c->d_gather[1];
+    c->gt.pair_meta = (const unsigned *)c->d_gather[2];
+    c->gt.pair_pos = c->d_gather[3];
+    c->gt.color_ptr = (const int *)c->d_gather[4];
+    c->gt.color_facets = (const int *)c->d_gather[5];
+    c->gt.tperm = (const int *)c->d_gather[6];
+    return true;
+}
+
 // forward residual / matrix assembly on the context's work arrays
 int assemble_forward(ocp_ctx *c, const double *d_w, const double *d_f, double *d_vals, double *d_res, bool bc) {
     cudaStream_t s = c->stream;
-    if (d_vals) CUDA_OK(c, cudaMemsetAsync(d_vals, 0, sizeof(double) * c->nnz, s));
-    if (d_res) CUDA_OK(c, cudaMemsetAsync(d_res, 0, sizeof(double) * c->ndofs, s));
-    launch_assemble_cells(c->nc, c->d_geom, c->d_cell_dofs, c->d_cell_slots, d_w, c->nu, false, d_vals, d_res, s);
-    launch_assemble_facets(c->n_g1, c->d_g1_nodes, c->d_g1_dofs, c->d_g1_slots, c->d_g1_len, c->d_g1_normal,
-                           c->d_dof_ux, c->d_dof_uy, d_w, d_f, false, d_vals, d_res, s);
+    if (c->gather) {
+        // every CSR value / residual entry is written exactly once (fixed summation order): no memset, no atomics
+        launch_assemble_gather(c->gt, c->d_geom, c->d_cell_dofs, d_w, c->nu, d_vals, d_res, s);
+        launch_assemble_facets_ordered(c->gt, c->n_g1, c->d_g1_nodes, c->d_g1_dofs, c->d_g1_slots, c->d_g1_len,
+                                       c->d_g1_normal, c->d_dof_ux, c->d_dof_uy, d_w, d_f, false, d_vals, d_res, s);
+    } else {
+        if (d_vals) CUDA_OK(c, cudaMemsetAsync(d_vals, 0, sizeof(double) * c->nnz, s));
+        if (d_res) CUDA_OK(c, cudaMemsetAsync(d_res, 0, sizeof(double) * c->ndofs, s));
+        launch_assemble_cells(c->nc, c->d_geom, c->d_cell_dofs, c->d_cell_slots, d_w, c->nu, false, d_vals, d_res, s);
+        launch_assemble_facets(c->n_g1, c->d_g1_nodes, c->d_g1_dofs, c->d_g1_slots, c->d_g1_len, c->d_g1_normal,
+                               c->d_dof_ux, c->d_dof_uy, d_w, d_f, false, d_vals, d_res, s);
+    }
     if (bc) launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, d_vals, d_res, d_w, c->d_dirval, s);
     CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
@@ -239,11 +405,19 @@ int assemble_forward(ocp_ctx *c, const double *d_w, const double *d_f, double *d
 
 int assemble_adjoint(ocp_ctx *c, const double *d_w, double *d_vals, bool bc) {
     cudaStream_t s = c->stream;
-    CUDA_OK(c, cudaMemsetAsync(d_vals, 0, sizeof(double) * c->nnz, s));
     // the adjoint form carries no viscosity factor (OCP_dolfin.py:344): nu := 1
-    launch_assemble_cells(c->nc, c->d_geom, c->d_cell_dofs, c->d_cell_slots, d_w, 1.0, true, d_vals, nullptr, s);
-    launch_assemble_facets(c->n_g1, c->d_g1_nodes, c->d_g1_dofs, c->d_g1_slots, c->d_g1_len, c->d_g1_normal,
-                           c->d_dof_ux, c->d_dof_uy, d_w, nullptr, true, d_vals, nullptr, s);
+    if (c->gather) {
+        // transpose of the nu = 1 Newton matrix: assembled row-wise, then moved through the pattern's transposition
+        launch_assemble_gather(c->gt, c->d_geom, c->d_cell_dofs, d_w, 1.0, c->d_vals2, nullptr, s);
+        launch_assemble_facets_ordered(c->gt, c->n_g1, c->d_g1_nodes, c->d_g1_dofs, c->d_g1_slots, c->d_g1_len,
+                                       c->d_g1_normal, c->d_dof_ux, c->d_dof_uy, d_w, nullptr, false, c->d_vals2, nullptr, s);
+        launch_permute_values(c->nnz, c->gt.tperm, c->d_vals2, d_vals, s);
+    } else {
+        CUDA_OK(c, cudaMemsetAsync(d_vals, 0, sizeof(double) * c->nnz, s));
+        launch_assemble_cells(c->nc, c->d_geom, c->d_cell_dofs, c->d_cell_slots, d_w, 1.0, true, d_vals, nullptr, s);
+        launch_assemble_facets(c->n_g1, c->d_g1_nodes, c->d_g1_dofs, c->d_g1_slots, c->d_g1_len, c->d_g1_normal,
+                               c->d_dof_ux, c->d_dof_uy, d_w, nullptr, true, d_vals, nullptr, s);
+    }
     if (bc) launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, d_vals, nullptr, nullptr, nullptr, s);
     CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
@@ -399,6 +573,7 @@ int ocp_get_option(const ocp_ctx *ctx, const char *name) {
     if (n == "deterministic") return ctx->deterministic ? 1 : 0;
     if (n == "buoy_staged") return ctx->buoy_staged ? 1 : 0;
     if (n == "adj_reuse") return ctx->adj_reuse ? 1 : 0;
+    if (n == "gather_assembly") return ctx->gather ? 1 : 0;
     return -1;
 }
 
@@ -432,26 +607,8 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     const int nc = d->nc, nn = d->nn, nv = d->nv, n = d->ndofs;
 
     // derived host tables: cell dofs, CSR slots of every element / facet entry
-    std::vector<int> cell_dofs((size_t)nc * 15), slots((size_t)nc * 225);
-    for (int e = 0; e < nc; ++e) {
-        const int *cn = d->cell_nodes + 6 * (size_t)e;
-        int *cd = cell_dofs.data() + 15 * (size_t)e;
-        for (int a = 0; a < 6; ++a) {
-            if (cn[a] < 0 || cn[a] >= nn) { c->err = "cell_nodes out of range"; return OCP_ERR_INVALID; }
-            cd[a] = d->dof_ux[cn[a]];
-            cd[6 + a] = d->dof_uy[cn[a]];
-        }
-        for (int a = 0; a < 3; ++a) {
-            if (cn[a] >= nv) { c->err = "cell vertex index >= nv"; return OCP_ERR_INVALID; }
-            cd[12 + a] = d->dof_p[cn[a]];
-        }
-        for (int i = 0; i < 15; ++i)
-            for (int j = 0; j < 15; ++j) {
-                int sl = find_slot(d->csr_rowptr, d->csr_col, cd[i], cd[j]);
-                if (sl < 0) { c->err = "CSR pattern misses an element entry"; return OCP_ERR_INVALID; }
-                slots[(size_t)e * 225 + i * 15 + j] = sl;
-            }
-    }
+    std::vector<int> cell_dofs, slots;
+    if (!build_cell_tables(d, cell_dofs, slots, c->err)) return OCP_ERR_INVALID;
     std::vector<int> g1_dofs((size_t)d->n_g1 * 6), g1_slots((size_t)d->n_g1 * 36);
     for (int f = 0; f < d->n_g1; ++f) {
         int *gd = g1_dofs.data() + 6 * (size_t)f;
@@ -526,6 +683,13 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     UP(d_m_col, m_col.data(), m_col.size());
     UP(d_m_vals, m_val.data(), m_val.size());
 #undef UP
+    {
+        const char *ea = getenv("OCP_ASSEMBLY");
+        const bool want = !(ea && std::string(ea) == "atomic");
+        c->gather = want && build_gather_tables(c, d, cell_dofs, slots);
+        if (want && !c->gather && getenv("OCP_SOLVER_VERBOSE"))
+            fprintf(stderr, "[ocp_b200] gather assembly tables not representable for this mesh: atomic kernels\n");
+    }
     CUDA_OK(c, cudaMalloc((void **)&c->d_vals, sizeof(double) * d->nnz));
     CUDA_OK(c, cudaMalloc((void **)&c->d_res, sizeof(double) * n));
     CUDA_OK(c, cudaMalloc((void **)&c->d_rhs, sizeof(double) * n));
@@ -586,6 +750,8 @@ void ocp_destroy(ocp_ctx *c) {
                     c->d_stokes_resp, c->d_minv, c->d_proj4};
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < 8; ++i) cudaFree(c->d_stage[i]);
+    for (int i = 0; i < 7; ++i) cudaFree(c->d_gather[i]);
+    cudaFree(c->d_vals2);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1072,6 +1238,48 @@ void ocp_selftest_cell_matrix(const double *geom6, const double *coef15, double 
 void ocp_selftest_facet_matrix(double len, double nx, double ny, const double *uv6, const double *f6, double *A36,
                                double *R6) {
     for (int r = 0; r < 6; ++r) facet_row(len, nx, ny, uv6, uv6 + 3, f6, f6 + 3, r, A36 + 6 * r, R6[r]);
+}
+
+// Host emulation of the gather assembly on its own tables (same CTA partition, same rounds, the kernels' element
+// arithmetic): cell part of dF/dw and F at w, written into vals (nnz) / res (ndofs); then out-of-place transposition
+// through the permutation into vals_t when given.  Returns the number of CTAs, or a negative error.
+int64_t ocp_host_gather_probe(const ocp_problem_desc *d, const double *w, double nu, double *vals, double *res,
+                              double *vals_t, int32_t *stats4) {
+    if (!d || !w || !vals || !res) return OCP_ERR_INVALID;
+    std::vector<int> cell_dofs, slots;
+    std::string err;
+    if (!build_cell_tables(d, cell_dofs, slots, err)) return OCP_ERR_INVALID;
+    GatherHost G;
+    if (!build_gather_host(d, cell_dofs, slots, G)) return OCP_ERR_SOLVER;
+    int max_rounds = 0;
+    for (const GatherHostCta &ct : G.ctas) {
+        std::vector<double> buf(ct.nentries, 0.0), rbuf(ct.nrows, 0.0);
+        for (int q = 0; q < ct.rounds; ++q)
+            for (int t = 0; t < ct.npairs; ++t) {
+                const int p = ct.first_pair + t;
+                const unsigned meta = G.meta[p];
+                if ((int)(meta & 15u) != q) continue;
+                const int cell = G.pair_cell[p], lrow = (int)((meta >> 4) & 15u);
+                double coef[15], A[15], R;
+                for (int i = 0; i < 15; ++i) coef[i] = w[cell_dofs[(size_t)cell * 15 + i]];
+                cell_row(d->cell_geom + 6 * (size_t)cell, coef, coef + 6, coef + 12, nu, lrow, A, R);
+                const int ncol = lrow < 12 ? 15 : 12;
+                for (int j = 0; j < ncol; ++j) buf[(meta >> 16) + G.pos[(size_t)p * 16 + j]] += A[j];
+                rbuf[(meta >> 8) & 255u] += R;
+            }
+        for (int e = 0; e < ct.nentries; ++e) vals[ct.first_entry + e] = buf[e];
+        for (int r = 0; r < ct.nrows; ++r) res[ct.first_row + r] = rbuf[r];
+        max_rounds = std::max(max_rounds, ct.rounds);
+    }
+    if (vals_t)
+        for (int k = 0; k < d->nnz; ++k) vals_t[k] = vals[G.tperm[k]];
+    if (stats4) {
+        stats4[0] = (int32_t)G.ctas.size();
+        stats4[1] = max_rounds;
+        stats4[2] = G.ncolors;
+        stats4[3] = (int32_t)G.smem;
+    }
+    return (int64_t)G.ctas.size();
 }
 
 void ocp_host_mf_set_pivot_window(int rows) { ocp::g_mf_host_window = rows < 1 ? 1 : rows; }

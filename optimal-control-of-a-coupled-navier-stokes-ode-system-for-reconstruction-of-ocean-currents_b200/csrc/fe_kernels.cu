@@ -86,6 +86,126 @@ assemble_cells_kernel(int nc, const double *__restrict__ geom, const int *__rest
     if (res) atomicAdd(res + __ldg(dofs + row), R);
 }
 
+// ---- atomic-free (gather) assembly ----------------------------------------------------------------------------------
+// The scatter kernel above adds 213 fp64 REDs per cell into the CSR values: on refined meshes it is bound by the
+// chip's fp64 atomic rate, reads a 900-byte slot table per cell, and the matrix changes in its last bits from run to
+// run.  Here the work is organised by ROW instead: a CTA owns a run of consecutive dof rows, hence a contiguous range
+// of CSR entries, which it accumulates in shared memory and writes exactly once (no memset, no atomics).
+//   thread  = one (row, adjacent cell) pair: it evaluates that row of the cell's 15 x 15 element matrix - every element
+//             row is still computed exactly once overall;
+//   rounds  = pairs of the same row add into the row's entries one after the other (round q = the q-th cell of every
+//             row; within a round all rows are disjoint), so the summation order is fixed: bit-reproducible matrices;
+//   tables  = per pair 24 bytes (cell, packed offsets, 15 one-byte positions inside the row): 360 B per cell instead
+//             of the 900 B slot table.
+struct GatherCta {
+    int first_pair, npairs, first_entry, nentries, first_row, nrows, rounds, pad;
+};
+
+__global__ void __launch_bounds__(256, 2)
+assemble_gather_kernel(const GatherCta *__restrict__ ctas, const int *__restrict__ pair_cell,
+                       const unsigned *__restrict__ pair_meta, const uint4 *__restrict__ pair_pos,
+                       const double *__restrict__ geom, const int *__restrict__ cell_dofs, const double *__restrict__ w,
+                       double nu, double *__restrict__ vals, double *__restrict__ res) {
+    extern __shared__ double buf[];                     // nentries values, then nrows residual entries
+    const GatherCta info = ctas[blockIdx.x];
+    double *rbuf = buf + info.nentries;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < info.nentries + info.nrows; e += blockDim.x) buf[e] = 0.0;
+    double A[15], R = 0.0;
+    unsigned meta = 0;
+    uint4 pos = make_uint4(0, 0, 0, 0);
+    const bool active = tid < info.npairs;
+    if (active) {
+        const int p = info.first_pair + tid;
+        const int cell = __ldg(pair_cell + p);
+        meta = __ldg(pair_meta + p);
+        pos = __ldg(pair_pos + p);
+        double g[6], U[6], V[6], Pr[3];
+        const double2 *gp = reinterpret_cast<const double2 *>(geom) + 3 * (size_t)cell;
+        const double2 ga = __ldg(gp), gb = __ldg(gp + 1), gc = __ldg(gp + 2);
+        g[0] = ga.x; g[1] = ga.y; g[2] = gb.x; g[3] = gb.y; g[4] = gc.x; g[5] = gc.y;
+        const int *dofs = cell_dofs + 15 * (size_t)cell;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            U[i] = __ldg(w + __ldg(dofs + i));
+            V[i] = __ldg(w + __ldg(dofs + 6 + i));
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Pr[i] = __ldg(w + __ldg(dofs + 12 + i));
+        cell_row(g, U, V, Pr, nu, (int)((meta >> 4) & 15u), A, R);
+    }
+    __syncthreads();
+    const int rowoff = (int)(meta >> 16), rowlocal = (int)((meta >> 8) & 255u), myq = (int)(meta & 15u);
+    const int ncol = ((meta >> 4) & 15u) < 12u ? 15 : 12;       // the p-p block is structurally present but zero
+    const unsigned char *pb = reinterpret_cast<const unsigned char *>(&pos);
+    for (int q = 0; q < info.rounds; ++q) {
+        if (active && myq == q) {
+            if (vals) {
+#pragma unroll
+                for (int j = 0; j < 15; ++j)
+                    if (j < ncol) buf[rowoff + pb[j]] += A[j];
+            }
+            rbuf[rowlocal] += R;
+        }
+        __syncthreads();
+    }
+    if (vals)
+        for (int e = tid; e < info.nentries; e += blockDim.x) vals[info.first_entry + e] = buf[e];
+    if (res)
+        for (int r = tid; r < info.nrows; r += blockDim.x) res[info.first_row + r] = rbuf[r];
+}
+
+// Gamma_1 facet blocks without atomics: ONE CTA walks the facets colour by colour (facets of a colour share no node,
+// so their read-modify-writes of the CSR values never collide; a block barrier separates the colours).
+template <bool kTranspose>
+__global__ void __launch_bounds__(512)
+assemble_facets_ordered_kernel(int ncolors, const int *__restrict__ color_ptr, const int *__restrict__ color_facets,
+                               const int *__restrict__ g1_nodes, const int *__restrict__ g1_dofs,
+                               const int *__restrict__ g1_slots, const double *__restrict__ g1_len,
+                               const double *__restrict__ g1_normal, const int *__restrict__ dof_ux,
+                               const int *__restrict__ dof_uy, const double *__restrict__ w, const double *__restrict__ f,
+                               double *__restrict__ vals, double *__restrict__ res) {
+    for (int col = 0; col < ncolors; ++col) {
+        const int f0 = color_ptr[col], nf = color_ptr[col + 1] - f0;
+        for (int t = threadIdx.x; t < nf * 8; t += blockDim.x) {
+            const int fct = color_facets[f0 + (t >> 3)], r = t & 7;
+            if (r >= 6) continue;
+            double U[3], V[3], Fx[3] = {0.0, 0.0, 0.0}, Fy[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int n = __ldg(g1_nodes + 3 * fct + a);
+                U[a] = __ldg(w + __ldg(dof_ux + n));
+                V[a] = __ldg(w + __ldg(dof_uy + n));
+                if (f) {
+                    Fx[a] = __ldg(f + 2 * (size_t)n);
+                    Fy[a] = __ldg(f + 2 * (size_t)n + 1);
+                }
+            }
+            double A[6], R;
+            facet_row(__ldg(g1_len + fct), __ldg(g1_normal + 2 * fct), __ldg(g1_normal + 2 * fct + 1), U, V, Fx, Fy, r, A, R);
+            if (vals) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    double *dst = vals + __ldg(g1_slots + 36 * fct + (kTranspose ? j * 6 + r : r * 6 + j));
+                    *dst = *dst + A[j];
+                }
+            }
+            if (res) {
+                double *dst = res + __ldg(g1_dofs + 6 * fct + r);
+                *dst = *dst + R;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// out[k] = in[perm[k]]: the adjoint operator is the transpose of the nu = 1 Newton matrix on the same (symmetric) pattern
+__global__ void permute_values_kernel(int n, const int *__restrict__ perm, const double *__restrict__ in,
+                                      double *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = in[__ldg(perm + k)];
+}
+
 // 8 lanes per facet, lane r < 6 owns row r of the 6x6 facet block.
 template <bool kTranspose>
 __global__ void __launch_bounds__(128)
@@ -380,6 +500,33 @@ void launch_assemble_facets(int n_g1, const int *g1_nodes, const int *g1_dofs, c
     else
         assemble_facets_kernel<false><<<blocks, 128, 0, s>>>(n_g1, g1_nodes, g1_dofs, g1_slots, g1_len, g1_normal,
                                                              dof_ux, dof_uy, w, f, vals, res);
+}
+
+void launch_assemble_gather(const GatherTables &gt, const double *geom, const int *cell_dofs, const double *w, double nu,
+                            double *vals, double *res, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    assemble_gather_kernel<<<gt.nctas, 256, gt.smem_bytes, s>>>(reinterpret_cast<const GatherCta *>(gt.ctas), gt.pair_cell,
+                                                                gt.pair_meta, reinterpret_cast<const uint4 *>(gt.pair_pos),
+                                                                geom, cell_dofs, w, nu, vals, res);
+}
+
+void launch_assemble_facets_ordered(const GatherTables &gt, int n_g1, const int *g1_nodes, const int *g1_dofs,
+                                    const int *g1_slots, const double *g1_len, const double *g1_normal,
+                                    const int *dof_ux, const int *dof_uy, const double *w, const double *f,
+                                    bool transpose, double *vals, double *res, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    if (n_g1 <= 0) return;
+    if (transpose)
+        assemble_facets_ordered_kernel<true><<<1, 512, 0, s>>>(gt.ncolors, gt.color_ptr, gt.color_facets, g1_nodes, g1_dofs,
+                                                               g1_slots, g1_len, g1_normal, dof_ux, dof_uy, w, f, vals, res);
+    else
+        assemble_facets_ordered_kernel<false><<<1, 512, 0, s>>>(gt.ncolors, gt.color_ptr, gt.color_facets, g1_nodes, g1_dofs,
+                                                                g1_slots, g1_len, g1_normal, dof_ux, dof_uy, w, f, vals, res);
+}
+
+void launch_permute_values(int n, const int *perm, const double *in, double *out, cudaStream_t s) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    permute_values_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, perm, in, out);
 }
 
 void launch_dirichlet(int n_dir, const int *dir, const int *rowptr, const int *col, double *vals, double *res,

@@ -54,6 +54,25 @@ void launch_assemble_facets(int n_g1, const int *g1_nodes, const int *g1_dofs, c
                             const double *g1_len, const double *g1_normal, const int *dof_ux, const int *dof_uy,
                             const double *w, const double *f, bool transpose, double *vals, double *res,
                             cudaStream_t s);
+// ---- atomic-free assembly (fe_kernels.cu): device tables built once by ocp_create (capi.cu: build_gather_tables)
+struct GatherTables {
+    int nctas = 0, ncolors = 0;
+    size_t smem_bytes = 0;             // largest CTA: (entries + rows) doubles
+    const void *ctas = nullptr;        // GatherCta[nctas]
+    const int *pair_cell = nullptr;    // per (row, cell) pair, ordered by row then cell
+    const unsigned *pair_meta = nullptr;   // row offset in the CTA's entry range << 16 | local row index << 8 | element row << 4 | round
+    const void *pair_pos = nullptr;    // 16 bytes per pair: position of element column j inside the CSR row
+    const int *color_ptr = nullptr, *color_facets = nullptr;   // Gamma_1 facets grouped by colour
+    const int *tperm = nullptr;        // CSR position of the transposed entry
+};
+// vals / res are WRITTEN (every entry exactly once), not accumulated: no memset beforehand
+void launch_assemble_gather(const GatherTables &gt, const double *geom, const int *cell_dofs, const double *w, double nu,
+                            double *vals, double *res, cudaStream_t s);
+void launch_assemble_facets_ordered(const GatherTables &gt, int n_g1, const int *g1_nodes, const int *g1_dofs,
+                                    const int *g1_slots, const double *g1_len, const double *g1_normal,
+                                    const int *dof_ux, const int *dof_uy, const double *w, const double *f,
+                                    bool transpose, double *vals, double *res, cudaStream_t s);
+void launch_permute_values(int n, const int *perm, const double *in, double *out, cudaStream_t s);
 // rows -> identity on the CSR values; res[d] = w[d] - dirval[d] (w null -> res[d] = 0; dirval null -> 0)
 void launch_dirichlet(int n_dir, const int *dir, const int *rowptr, const int *col, double *vals, double *res,
                       const double *w, const double *dirval, cudaStream_t s);

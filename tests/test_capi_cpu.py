@@ -171,3 +171,25 @@ def test_problem_desc_bindings_match_the_header():
     exec(code, ns)
     assert [(n, kinds[t]) for n, t in ns["ProblemDesc"]._fields_] == hdr
     assert C.sizeof(ns["ProblemDesc"]) == C.sizeof(capi.ProblemDesc)
+
+
+@pytest.mark.parametrize("mesh", ["square32", "lshape", "square20"])
+def test_gather_assembly_tables_reproduce_the_oracle_matrix(lib, mesh):
+    """The atomic-free assembly is organised by CSR row (CTAs of consecutive rows, one (row, cell) pair per thread,
+    rounds over the cells of a row).  Its tables are emulated on the host with the kernels' element arithmetic:
+    cell part of the Newton matrix and residual, and the transposition permutation used for the adjoint operator."""
+    from ocp_b200.fespace import TaylorHood
+    from ocp_b200.mesh import square_mesh
+    V = {"square32": H.square32, "lshape": H.lshape, "square20": lambda: TaylorHood(square_mesh(20))}[mesh]()
+    O = FEOracle(V, 0.7)
+    w = 0.3 * np.random.default_rng(2).standard_normal(V.ndofs)
+    vals, res, vt, st = capi.host_gather_probe(V, w, 0.7)
+    n = V.ndofs
+    Jc = sp.coo_matrix((O.cell_jacobian(w).reshape(-1), (O._rows, O._cols)), shape=(n, n)).tocsr()
+    assert H.rel(vals, O.on_pattern(Jc)) < 1e-12
+    assert H.rel(vt, O.on_pattern(Jc.T.tocsr())) < 1e-12
+    Rc = np.zeros(n)
+    np.add.at(Rc, V.cell_dofs.reshape(-1), O.cell_residual(w).reshape(-1))
+    assert H.rel(res, Rc) < 1e-12
+    assert 1 <= st["rounds"] <= 15 and st["colors"] >= 2 and st["smem_bytes"] <= 40 * 1024
+    assert st["ctas"] >= 15 * V.mesh.num_cells // 256

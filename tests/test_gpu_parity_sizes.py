@@ -352,3 +352,44 @@ def test_deterministic_deposit_is_bit_reproducible(K, staged, monkeypatch):
     muo = B.adjoint(g, xo, uo, ud, mo, H.H)
     bo = B.point_sources(V.velocity_nodal(w), xo, ud, muo, mo, H.H, H.CENTER)
     assert H.rel(r1["acc"][:nn2].reshape(-1, 2), bo) < 1e-12
+
+
+def _assemble_all(V, w, f, nu):
+    ocp = OCP(V, Parameters(viscosity=nu), np.array([[1.0, 0.5]]), np.zeros((1, 200, 2)), device=dev())
+    nnz = V.csr_col.size
+    out = {"gather": ocp.ctx.option("gather_assembly")}
+    for name, bc in (("J", False), ("Jbc", True)):
+        vals = torch.full((nnz,), 7.0, device=dev(), dtype=torch.float64)      # stale content must be overwritten
+        res = torch.full((V.ndofs,), -3.0, device=dev(), dtype=torch.float64)
+        ocp.ctx.assemble_forward(T(w), T(f), vals, res, bc)
+        out[name], out["R" + name] = vals.cpu().numpy(), res.cpu().numpy()
+    vals = torch.full((nnz,), 7.0, device=dev(), dtype=torch.float64)
+    ocp.ctx.assemble_adjoint(T(w), vals, True)
+    out["A"] = vals.cpu().numpy()
+    ocp.close()
+    return out
+
+
+@pytest.mark.parametrize("mesh", ["square32", "lshape", "square48"])
+def test_atomic_free_assembly_matches_oracle_and_is_bit_reproducible(mesh, monkeypatch):
+    """The default assembly gathers by CSR row (no fp64 atomics, fixed summation order): 1e-12 against the oracle like
+    the atomic scatter kernels (OCP_ASSEMBLY=atomic), and bit-identical from run to run."""
+    from ocp_b200.fespace import TaylorHood
+    from ocp_b200.mesh import square_mesh
+    V = {"square32": H.square32, "lshape": H.lshape, "square48": lambda: TaylorHood(square_mesh(48))}[mesh]()
+    nu = 0.3
+    O = FEOracle(V, nu)
+    w = 0.3 * np.random.default_rng(8).standard_normal(V.ndofs)
+    f = initial_control(V, "OCP")
+    a = _assemble_all(V, w, f, nu)
+    b = _assemble_all(V, w, f, nu)
+    monkeypatch.setenv("OCP_ASSEMBLY", "atomic")
+    c = _assemble_all(V, w, f, nu)
+    assert a["gather"] == 1 and c["gather"] == 0
+    for k in ("J", "Jbc", "A", "RJ", "RJbc"):
+        assert np.array_equal(a[k], b[k]), k                        # bit-reproducible
+        assert H.rel(a[k], c[k]) < 1e-12, k                         # equals the atomic variant to round-off
+    assert H.rel(a["J"], O.on_pattern(O.jacobian_unconstrained(w))) < 1e-12
+    assert H.rel(a["Jbc"], O.on_pattern(O.forward_jacobian(w))) < 1e-12
+    assert H.rel(a["A"], O.on_pattern(O.adjoint_matrix(w))) < 1e-12
+    assert H.rel(a["RJ"], O.forward_residual(w, f)) < 1e-12
