@@ -992,10 +992,17 @@ buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /
     double m00 = 1.0, m01 = 0.0, m10 = 0.0, m11 = 1.0, v0 = 0.0, v1 = 0.0;
     if (run && j > 0) {                    // (chunk 0's map is never needed)
         int hint = -1;
+        // (the three streams are read one sample ahead, as in the serial sweep)
+        double2 pn = __ldg(x + (size_t)khi * K + b), Un = __ldg(u + (size_t)khi * K + b), Dn = __ldg(ud + (size_t)khi * K + b);
         for (int k = khi; k >= klo; --k) {
             const size_t o = (size_t)k * K + b;
-            double2 p = __ldg(x + o);
-            const double2 U = __ldg(u + o), D = __ldg(ud + o);
+            double2 p = pn;
+            const double2 U = Un, D = Dn;
+            if (k > klo) {
+                pn = __ldg(x + o - K);
+                Un = __ldg(u + o - K);
+                Dn = __ldg(ud + o - K);
+            }
             double l0, l1, l2;
             bool lost;
             const int c = locate_sample(k, p, hint, l0, l1, l2, lost);
@@ -1026,15 +1033,25 @@ buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /
         }
     }
     // ---- pass 2: the ordinary sweep over the chunk
+    int pending_cell = -1;
+    double pending[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) pending[i] = 0.0;
     if (alive) {
         double acc[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) acc[i] = 0.0;
         int acc_cell = -1, hint = -1;
+        double2 pn = __ldg(x + (size_t)khi * K + b), Un = __ldg(u + (size_t)khi * K + b), Dn = __ldg(ud + (size_t)khi * K + b);
         for (int k = khi; k >= klo; --k) {
             const size_t o = (size_t)k * K + b;
-            double2 p = __ldg(x + o);
-            const double2 U = __ldg(u + o), D = __ldg(ud + o);
+            double2 p = pn;
+            const double2 U = Un, D = Dn;
+            if (k > klo) {
+                pn = __ldg(x + o - K);
+                Un = __ldg(u + o - K);
+                Dn = __ldg(ud + o - K);
+            }
             const double ex = U.x - D.x, ey = U.y - D.y;
             misfit += ex * ex + ey * ey;
             if (masked) {
@@ -1080,12 +1097,30 @@ buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /
                 }
             }
         }
-        if (acc_cell >= 0) {
-            if (X)
-                flush_sources_exact<false>(digits, dovf, t.cell_nodes, acc_cell, acc);
-            else
-                flush_sources_g(acc_out, t, acc_cell, acc);
+        // The T lanes of a buoy mostly end in the same cell: their pending deposits are combined by a shuffle tree
+        // (lane j takes over lane j + d when both hold the same cell) so that a buoy flushes once instead of T times.
+        // [all lanes of the warp reach this point: `alive` lanes only differ in the trip counts above]
+        pending_cell = acc_cell;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) pending[i] = acc[i];
+    }
+    for (int dlt = 1; dlt < T; dlt <<= 1) {
+        const int other_cell = __shfl_down_sync(0xffffffffu, pending_cell, dlt);
+        const int below_cell = __shfl_up_sync(0xffffffffu, pending_cell, dlt);
+        const bool take = (j % (2 * dlt) == 0) && (j + dlt < T) && pending_cell >= 0 && other_cell == pending_cell;
+        const bool give = (j % (2 * dlt) == dlt) && pending_cell >= 0 && below_cell == pending_cell;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const double v = __shfl_down_sync(0xffffffffu, pending[i], dlt);
+            if (take) pending[i] += v;
         }
+        if (give) pending_cell = -1;
+    }
+    if (pending_cell >= 0) {
+        if (X)
+            flush_sources_exact<false>(digits, dovf, t.cell_nodes, pending_cell, pending);
+        else
+            flush_sources_g(acc_out, t, pending_cell, pending);
     }
     block_finish2(misfit, nmasked, scratch, counter, acc_out + 2 * (size_t)t.nn, acc_out + 2 * (size_t)t.nn + 1,
                   0.5 * h);

@@ -129,6 +129,7 @@ struct ocp_ctx {
     int n_g1dofs = 0;
     double *d_stokes_resp = nullptr;   // (ndofs x n_g1dofs) column-major: columns S^-1 e_j, j in the Gamma_1 velocity dofs
     bool stokes_resp_valid = false;
+    double *d_dense_part = nullptr;    // partial sums of the dense applies
     double *d_minv = nullptr;          // (nv x nv) inverse of the P1 mass matrix
     bool minv_valid = false;
     Communicator comm;    // NCCL communicator when the buoys are sharded over ranks (ocp_comm_init); 1 rank otherwise
@@ -696,6 +697,9 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     CUDA_OK(c, cudaMalloc((void **)&c->d_tmp, sizeof(double) * n));
     CUDA_OK(c, cudaMalloc((void **)&c->d_rhs4, sizeof(double) * 4 * nv));
     CUDA_OK(c, cudaMalloc((void **)&c->d_proj4, sizeof(double) * 4 * nv));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_dense_part,
+                          sizeof(double) * std::max(dense_apply_scratch(n, std::max(c->n_g1dofs, 1), 1),
+                                                    dense_apply_scratch(nv, nv, 4))));
     CUDA_OK(c, cudaMalloc((void **)&c->d_scalar, sizeof(double) * 8));
     CUDA_OK(c, cudaMalloc((void **)&c->d_cellvel, sizeof(double) * 12 * (size_t)nc));
     CUDA_OK(c, cudaMalloc((void **)&c->d_cellg, sizeof(double) * 12 * (size_t)nc));
@@ -747,7 +751,7 @@ void ocp_destroy(ocp_ctx *c) {
                     c->d_g1_dofs, c->d_g1_slots, c->d_bin_ptr, c->d_bin_cells, c->d_m_rowptr, c->d_m_col,
                     c->d_m_vals, c->d_vals, c->d_res, c->d_rhs, c->d_tmp, c->d_rhs4, c->d_scalar, c->d_scratch,
                     c->d_counter, c->d_parked, c->d_obs_x0, c->d_obs_ud, c->d_cell_nbr, c->d_cellvel, c->d_cellg, c->d_bpriv, c->d_dirval, c->d_digits, c->d_g1dofs,
-                    c->d_stokes_resp, c->d_minv, c->d_proj4};
+                    c->d_stokes_resp, c->d_minv, c->d_proj4, c->d_dense_part};
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < 8; ++i) cudaFree(c->d_stage[i]);
     for (int i = 0; i < 7; ++i) cudaFree(c->d_gather[i]);
@@ -834,7 +838,7 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
             PhaseTimer t(c, &c->stats.solve_ms);
             c->last_newton_lu = &lu;
             if (dense_step) {
-                launch_dense_apply(n, c->n_g1dofs, 1, c->d_stokes_resp, c->d_res, n, c->d_g1dofs, c->d_tmp, s);
+                launch_dense_apply(n, c->n_g1dofs, 1, c->d_stokes_resp, c->d_res, n, c->d_g1dofs, c->d_tmp, c->d_dense_part, s);
                 launch_axpy(n, -1.0, c->d_tmp, d_w, s);
                 c->stats.n_dense++;
             } else {
@@ -882,7 +886,7 @@ int ocp_project_grad(ocp_ctx *c, const double *d_w, double *d_g) {
     {
         PhaseTimer t(c, &c->stats.solve_ms);
         if (dense_mass) {
-            launch_dense_apply(nv, nv, 4, c->d_minv, c->d_rhs4, nv, nullptr, c->d_proj4, s);
+            launch_dense_apply(nv, nv, 4, c->d_minv, c->d_rhs4, nv, nullptr, c->d_proj4, c->d_dense_part, s);
             launch_transpose4(nv, c->d_proj4, d_g, s);
             c->stats.n_dense++;
         } else {

@@ -1,6 +1,8 @@
 // Finite-element kernels: cell-parallel assembly of the Taylor-Hood Newton matrix / residual and of the
 // adjoint operator (atomic fp64 scatter into the precomputed CSR pattern through per-cell slot tables),
 // Gamma_1 facet blocks, Dirichlet rows, the grad(u) projection right-hand side, boundary forms and norms.
+#include <algorithm>
+
 #include "element_math.cuh"
 #include "kernels.cuh"
 
@@ -437,40 +439,53 @@ fp64_peak_kernel(double *out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
-// out[r n + i] = sum_j R[i + j n] x[r ldx + (idx ? idx[j] : j)],  r < NR  (R column-major n x ncol): dense response
-// operators that replace a sparse triangular solve when they are small enough to precompute (see capi.cu).  One thread
-// per row, two independent partial sums per right-hand side, the gathered x staged in shared memory.
+// part[(sp NR + r) n + i] = sum_{j in split sp} R[i + j n] x[r ldx + (idx ? idx[j] : j)],  r < NR  (R column-major
+// n x ncol): dense response operators that replace a sparse triangular solve when they are small enough to precompute
+// (see capi.cu).  grid = (row blocks of 128, column splits): ~600 CTAs keep the whole chip streaming R; one thread per
+// row, eight independent loads in flight; the column splits are summed in a fixed order by dense_reduce_kernel.
 template <int NR>
 __global__ void __launch_bounds__(128)
-dense_apply_kernel(int n, int ncol, const double *__restrict__ R, const double *__restrict__ x, int ldx,
-                   const int *__restrict__ idx, double *__restrict__ out) {
-    extern __shared__ double xs[];          // NR x ncol
-    for (int e = threadIdx.x; e < NR * ncol; e += blockDim.x) {
-        const int r = e / ncol, j = e - r * ncol;
-        xs[e] = x[(size_t)r * ldx + (idx ? idx[j] : j)];
+dense_apply_kernel(int n, int ncol, int cols_per_split, const double *__restrict__ R, const double *__restrict__ x,
+                   int ldx, const int *__restrict__ idx, double *__restrict__ part) {
+    extern __shared__ double xs[];          // NR x cols_per_split
+    const int j0 = blockIdx.y * cols_per_split, nj = min(cols_per_split, ncol - j0);
+    for (int e = threadIdx.x; e < NR * nj; e += blockDim.x) {
+        const int r = e / nj, j = e - r * nj;
+        xs[r * cols_per_split + j] = x[(size_t)r * ldx + (idx ? idx[j0 + j] : j0 + j)];
     }
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double a[NR], b[NR];
+    double a[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) a[r] = b[r] = 0.0;
+    for (int r = 0; r < NR; ++r) a[r] = 0.0;
+    const double *Rp = R + i + (size_t)j0 * n;
     int j = 0;
-    for (; j + 2 <= ncol; j += 2) {
-        const double e0 = __ldg(R + i + (size_t)j * n), e1 = __ldg(R + i + (size_t)(j + 1) * n);
+    for (; j + 8 <= nj; j += 8) {
+        double e[8];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            a[r] = fma(e0, xs[r * ncol + j], a[r]);
-            b[r] = fma(e1, xs[r * ncol + j + 1], b[r]);
-        }
+        for (int q = 0; q < 8; ++q) e[q] = __ldcs(Rp + (size_t)(j + q) * n);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) a[r] = fma(e[q], xs[r * cols_per_split + j + q], a[r]);
     }
-    if (j < ncol) {
-        const double e0 = __ldg(R + i + (size_t)j * n);
+    for (; j < nj; ++j) {
+        const double e0 = __ldcs(Rp + (size_t)j * n);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) a[r] = fma(e0, xs[r * ncol + j], a[r]);
+        for (int r = 0; r < NR; ++r) a[r] = fma(e0, xs[r * cols_per_split + j], a[r]);
     }
 #pragma unroll
-    for (int r = 0; r < NR; ++r) out[(size_t)r * n + i] = a[r] + b[r];
+    for (int r = 0; r < NR; ++r) part[((size_t)blockIdx.y * NR + r) * n + i] = a[r];
+}
+
+// out[e] = sum over the splits (fixed order), e < NR n
+__global__ void dense_reduce_kernel(int total, int nsplit, const double *__restrict__ part, double *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    double s = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) s += part[(size_t)sp * total + e];
+    out[e] = s;
 }
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
@@ -590,21 +605,27 @@ void launch_field_norms(int nc, const double *geom, const int *cell_dofs, const 
     field_norms_kernel<<<cdiv(nc, 128), 128, 0, s>>>(nc, geom, cell_dofs, w, out3, scratch, counter);
 }
 
+size_t dense_apply_scratch(int n, int ncol, int nrhs) {
+    const int rb = cdiv(n, 128);
+    const int nsplit = std::max(1, std::min(600 / rb, cdiv(ncol, 16)));
+    return (size_t)nsplit * nrhs * n;
+}
+
 void launch_dense_apply(int n, int ncol, int nrhs, const double *R, const double *x, int ldx, const int *idx,
-                        double *out, cudaStream_t s) {
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    const size_t smem = sizeof(double) * ncol * nrhs;
-    if (nrhs == 4) {
-        static bool once = cudaFuncSetAttribute(dense_apply_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess;
-        (void)once;
-        dense_apply_kernel<4><<<cdiv(n, 128), 128, smem, s>>>(n, ncol, R, x, ldx, idx, out);
-    } else {
-        static bool once = cudaFuncSetAttribute(dense_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess;
-        (void)once;
-        for (int r = 0; r < nrhs; ++r)
-            dense_apply_kernel<1><<<cdiv(n, 128), 128, sizeof(double) * ncol, s>>>(n, ncol, R, x + (size_t)r * ldx, ldx, idx,
-                                                                                 out + (size_t)r * n);
-    }
+                        double *out, double *part, cudaStream_t s) {
+    g_launch_count.fetch_add(2, std::memory_order_relaxed);
+    const int rb = cdiv(n, 128);
+    const int nsplit = std::max(1, std::min(600 / rb, cdiv(ncol, 16)));
+    const int cps = cdiv(ncol, nsplit);
+    const int ns = cdiv(ncol, cps);
+    dim3 grid(rb, ns);
+    const size_t smem = sizeof(double) * cps * nrhs;
+    if (nrhs == 4)
+        dense_apply_kernel<4><<<grid, 128, smem, s>>>(n, ncol, cps, R, x, ldx, idx, part);
+    else
+        dense_apply_kernel<1><<<grid, 128, smem, s>>>(n, ncol, cps, R, x, ldx, idx, part);
+    const int total = n * (nrhs == 4 ? 4 : 1);
+    dense_reduce_kernel<<<cdiv(total, 256), 256, 0, s>>>(total, ns, part, out);
 }
 
 double launch_fp64_peak(double *out, int blocks, int threads, int iters, cudaStream_t s) {

@@ -92,9 +92,11 @@ void launch_field_norms(int nc, const double *geom, const int *cell_dofs, const 
 void launch_spmv_residual(int n, const int *rowptr, const int *col, const double *vals, const double *x,
                           const double *b, double *r, cudaStream_t s);                   // r = b - A x
 
-// out[r n + i] = sum_j R[i + j n] x[r ldx + (idx ? idx[j] : j)], r < nrhs (1 or 4); R column-major n x ncol
+// out[r n + i] = sum_j R[i + j n] x[r ldx + (idx ? idx[j] : j)], r < nrhs (1 or 4); R column-major n x ncol;
+// part: dense_apply_scratch(n, ncol, nrhs) doubles of work space (partial sums of the column splits)
+size_t dense_apply_scratch(int n, int ncol, int nrhs);
 void launch_dense_apply(int n, int ncol, int nrhs, const double *R, const double *x, int ldx, const int *idx,
-                        double *out, cudaStream_t s);
+                        double *out, double *part, cudaStream_t s);
 // register-resident DFMA loop (8 independent chains per thread): the fp64 FMA-pipe peak the LU roofline is quoted
 // against; returns the flop count of the launch
 double launch_fp64_peak(double *out, int blocks, int threads, int iters, cudaStream_t s);
