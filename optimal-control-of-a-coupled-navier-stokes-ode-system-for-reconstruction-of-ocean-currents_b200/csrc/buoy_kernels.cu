@@ -940,18 +940,20 @@ buoy_adjoint_scatter_global_kernel(DeviceTables t, const double2 *__restrict__ v
 // walking 200 dependent samples (~0.8 us each): the launch is bound by that chain, not by bandwidth.  The adjoint
 // recursion is AFFINE in mu,
 //     mu_{k-1} = (I + h G_k^T) mu_k - h G_k^T e_k,      G_k = G(x_k), e_k = u_k - u_d,k,
-// so T threads share one buoy: thread j owns a contiguous chunk of samples and
+// so T lanes share one buoy: lane j owns a contiguous chunk of samples and
 //   pass 1  composes the affine map of its chunk (point location + G per sample, no deposits),
-//   scan    the incoming mu of every chunk follows from the maps of the chunks after it (shared memory),
+//   scan    the incoming mu of every chunk follows from the chunks after it (T-1 shuffle steps),
 //   pass 2  runs the ordinary per-sample sweep over its chunk from that incoming mu (deposits, misfit, mu output).
-// A CTA holds 32 buoys x T chunks with WARP = CHUNK: the 32 lanes of a warp are 32 neighbouring buoys at the same
-// sample, so stream accesses stay 512-byte coalesced and the lanes sit in the same few cells (a first version with
-// the chunks of a buoy in adjacent lanes ran into the L1 throughput limit: 8 rows and up to 32 cells per load).
+// Measured on B200 (cfg3, K = 10^4, in-step, L2 flushed): serial sweep 0.157 ms, this kernel 0.102 ms (ncu: 23 M warp
+// instructions, issue-active 28 %, L1/TEX 86 % - the eight sample rows a warp touches per load cost wavefronts); the
+// alternative mapping WARP = CHUNK (32 neighbouring buoys per warp, chunks of a buoy in different warps of a CTA, scan
+// through shared memory) keeps every access coalesced but couples eight warps by a block barrier between the passes
+// and measured 0.131 ms, so the lane mapping stays.
 // The dependent chain shrinks from nt to 2 nt / T samples and T times as many warps are in flight.  mu at the chunk
 // boundaries is formed through the composed maps, i.e. with a different (equally valid) rounding sequence than the
 // serial sweep: mu and b agree with it to ~1e-15 relative (tests: 1e-12 against the oracle).
 template <int T, bool X>
-__global__ void __launch_bounds__(32 * T)
+__global__ void __launch_bounds__(kBuoyThreads)
 buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /* per-cell records */,
                                const double2 *__restrict__ g /* per-cell vertex gradients */, int K, int nt, double h,
                                double cx, double cy, const double2 *__restrict__ x, const double2 *__restrict__ u,
@@ -959,9 +961,10 @@ buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /
                                const uint8_t *__restrict__ parked, double2 *__restrict__ mu,
                                double *__restrict__ acc_out, double *scratch, unsigned *counter,
                                long long *__restrict__ digits) {
-    __shared__ double s_map[T][6][32];                         // per chunk and buoy: m00 m01 m10 m11 v0 v1
-    const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;   // j = chunk index (= warp), chunk T-1 holds the last samples
-    const long long bl = (long long)blockIdx.x * 32 + lane;
+    constexpr int G = 32 / T;                                  // buoys per warp
+    const int lane = threadIdx.x & 31, j = lane % T;           // j = chunk index, chunk T-1 holds the last samples
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long bl = warp * G + lane / T;
     const bool alive = bl < K;
     const int b = alive ? (int)bl : 0;
     const int klo = (int)(((long long)j * nt) / T), khi = (int)(((long long)(j + 1) * nt) / T) - 1;
@@ -970,7 +973,8 @@ buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /
     const bool run = alive && !masked;
     long long *const dovf = X ? digits + 8 * (size_t)t.nn : nullptr;
     double misfit = 0.0, nmasked = (masked && j == 0) ? 1.0 : 0.0;
-    auto locate_sample = [&](double2 &p, int &hint, double &l0, double &l1, double &l2, bool &lost) -> int {
+    // G(x_k)^T-step coefficients of one sample: returns false when the sample leaves mu unchanged
+    auto locate_sample = [&](int k, double2 &p, int &hint, double &l0, double &l1, double &l2, bool &lost) -> int {
         int c = locate_g(t, p.x, p.y, hint, l0, l1, l2);
         lost = c < 0;
         if (lost) {                                            // `except` of OCP_dolfin.py:359-361: point = centre
@@ -989,9 +993,9 @@ buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /
         G2 = l0 * a1.x + l1 * b1.x + l2 * c1.x;
         G3 = l0 * a1.y + l1 * b1.y + l2 * c1.y;
     };
-    // ---- pass 1: affine map of the chunk, mu_{klo-1} = M mu_{khi} + v  (chunk 0's map is never needed)
+    // ---- pass 1: affine map of the chunk, mu_{klo-1} = M mu_{khi} + v
     double m00 = 1.0, m01 = 0.0, m10 = 0.0, m11 = 1.0, v0 = 0.0, v1 = 0.0;
-    if (run && j > 0) {
+    if (run && j > 0) {                    // (chunk 0's map is never needed)
         int hint = -1;
         // (the three streams are read one sample ahead, as in the serial sweep)
         double2 pn = __ldg(x + (size_t)khi * K + b), Un = __ldg(u + (size_t)khi * K + b), Dn = __ldg(ud + (size_t)khi * K + b);
@@ -1006,7 +1010,7 @@ buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /
             }
             double l0, l1, l2;
             bool lost;
-            const int c = locate_sample(p, hint, l0, l1, l2, lost);
+            const int c = locate_sample(k, p, hint, l0, l1, l2, lost);
             if (c >= 0 && k > 0) {
                 double G0, G1, G2, G3;
                 grad_at(c, l0, l1, l2, G0, G1, G2, G3);
@@ -1021,18 +1025,23 @@ buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /
             }
         }
     }
-    s_map[j][0][lane] = m00; s_map[j][1][lane] = m01; s_map[j][2][lane] = m10; s_map[j][3][lane] = m11;
-    s_map[j][4][lane] = v0; s_map[j][5][lane] = v1;
-    __syncthreads();
-    // ---- scan: incoming mu of chunk j = the maps of chunks T-1 ... j+1 applied in turn to mu_{nt-1} = 0
+    // ---- scan over the chunks of a buoy, last chunk first: incoming mu of chunk s-1 = map of chunk s applied to its own
     double mux = 0.0, muy = 0.0;
-    for (int sc = T - 1; sc > j; --sc) {
-        const double ox = s_map[sc][0][lane] * mux + s_map[sc][1][lane] * muy + s_map[sc][4][lane];
-        const double oy = s_map[sc][2][lane] * mux + s_map[sc][3][lane] * muy + s_map[sc][5][lane];
-        mux = ox;
-        muy = oy;
+#pragma unroll 1
+    for (int s_ = T - 1; s_ >= 1; --s_) {
+        const double ox = m00 * mux + m01 * muy + v0, oy = m10 * mux + m11 * muy + v1;
+        const int src = (lane / T) * T + s_;
+        const double rx = __shfl_sync(0xffffffffu, ox, src), ry = __shfl_sync(0xffffffffu, oy, src);
+        if (j == s_ - 1) {
+            mux = rx;
+            muy = ry;
+        }
     }
     // ---- pass 2: the ordinary sweep over the chunk
+    int pending_cell = -1;
+    double pending[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) pending[i] = 0.0;
     if (alive) {
         double acc[12];
 #pragma unroll
@@ -1057,7 +1066,7 @@ buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /
             double l0, l1, l2;
             double ukx = U.x, uky = U.y;
             bool lost;
-            const int c = locate_sample(p, hint, l0, l1, l2, lost);
+            const int c = locate_sample(k, p, hint, l0, l1, l2, lost);
             if (lost) {
                 ukx = 0.0;
                 uky = 0.0;
@@ -1093,12 +1102,30 @@ buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /
                 }
             }
         }
-        if (acc_cell >= 0) {
-            if (X)
-                flush_sources_exact<false>(digits, dovf, t.cell_nodes, acc_cell, acc);
-            else
-                flush_sources_g(acc_out, t, acc_cell, acc);
+        // The T lanes of a buoy mostly end in the same cell: their pending deposits are combined by a shuffle tree
+        // (lane j takes over lane j + d when both hold the same cell) so that a buoy flushes once instead of T times.
+        // [all lanes of the warp reach this point: `alive` lanes only differ in the trip counts above]
+        pending_cell = acc_cell;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) pending[i] = acc[i];
+    }
+    for (int dlt = 1; dlt < T; dlt <<= 1) {
+        const int other_cell = __shfl_down_sync(0xffffffffu, pending_cell, dlt);
+        const int below_cell = __shfl_up_sync(0xffffffffu, pending_cell, dlt);
+        const bool take = (j % (2 * dlt) == 0) && (j + dlt < T) && pending_cell >= 0 && other_cell == pending_cell;
+        const bool give = (j % (2 * dlt) == dlt) && pending_cell >= 0 && below_cell == pending_cell;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const double v = __shfl_down_sync(0xffffffffu, pending[i], dlt);
+            if (take) pending[i] += v;
         }
+        if (give) pending_cell = -1;
+    }
+    if (pending_cell >= 0) {
+        if (X)
+            flush_sources_exact<false>(digits, dovf, t.cell_nodes, pending_cell, pending);
+        else
+            flush_sources_g(acc_out, t, pending_cell, pending);
     }
     block_finish2(misfit, nmasked, scratch, counter, acc_out + 2 * (size_t)t.nn, acc_out + 2 * (size_t)t.nn + 1,
                   0.5 * h);
@@ -1208,8 +1235,8 @@ bool allow_smem(Kern k, size_t bytes) {
 
 }  // namespace
 
-// Threads per buoy of the time-parallel backward sweep: 16 for the thesis' smaller buoy counts (<= 2000), 8 up to the
-// 10 000-buoy run, 1 (serial sweep, bandwidth-bound) beyond.  OCP_BUOY_TP=0 forces the serial sweep.
+// Lanes per buoy of the time-parallel backward sweep: 32 for the thesis' buoy counts (<= 2000), 8 up to the 10 000-buoy
+// run, 1 (serial sweep, bandwidth-bound) beyond.  OCP_BUOY_TP=0 forces the serial sweep.
 int time_parallel_lanes(int K, int nt, int nrep) {
     static int enabled = -1;
     if (enabled < 0) {
@@ -1217,7 +1244,7 @@ int time_parallel_lanes(int K, int nt, int nrep) {
         enabled = (e && atoi(e) == 0) ? 0 : 1;
     }
     if (!enabled || nrep > 1 || nt < 64) return 1;
-    if (K <= 2000) return 16;
+    if (K <= 2000) return 32;
     if (K <= 12000) return 8;
     return 1;
 }
@@ -1292,21 +1319,21 @@ void launch_buoy_adjoint_scatter(const DeviceTables &t, bool staged, const doubl
                 buoy_adjoint_scatter_kernel<true, kDepthLarge, false><<<sh.grid, sh.threads, smem, s>>>(OCP_BWD_ARGS);
         }
     } else if (time_parallel_lanes(K, nt, nrep) > 1) {
-        // small launch: T threads per buoy, CTA = 32 buoys x T chunks (see buoy_adjoint_scatter_tp_kernel); no private
-        // copies at these sizes
+        // small launch: T lanes per buoy (see buoy_adjoint_scatter_tp_kernel); no private copies at these sizes
         const int T = time_parallel_lanes(K, nt, nrep);
-        const int grid = (K + 31) / 32;
+        const long long threads = (long long)((K + (32 / T) - 1) / (32 / T)) * 32;
+        const int grid = (int)((threads + kBuoyThreads - 1) / kBuoyThreads);
 #define OCP_TP_ARGS t, fv, fg, K, nt, h, cx, cy, x2, u2, d2, mask, parked, mu2, acc, scratch, counter, digits
-        if (T == 16) {
+        if (T == 32) {
             if (exact)
-                buoy_adjoint_scatter_tp_kernel<16, true><<<grid, 32 * 16, 0, s>>>(OCP_TP_ARGS);
+                buoy_adjoint_scatter_tp_kernel<32, true><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
             else
-                buoy_adjoint_scatter_tp_kernel<16, false><<<grid, 32 * 16, 0, s>>>(OCP_TP_ARGS);
+                buoy_adjoint_scatter_tp_kernel<32, false><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
         } else {
             if (exact)
-                buoy_adjoint_scatter_tp_kernel<8, true><<<grid, 32 * 8, 0, s>>>(OCP_TP_ARGS);
+                buoy_adjoint_scatter_tp_kernel<8, true><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
             else
-                buoy_adjoint_scatter_tp_kernel<8, false><<<grid, 32 * 8, 0, s>>>(OCP_TP_ARGS);
+                buoy_adjoint_scatter_tp_kernel<8, false><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
         }
 #undef OCP_TP_ARGS
     } else {
