@@ -1292,7 +1292,7 @@ int64_t ocp_host_mf_probe(int32_t n, const int32_t *rowptr, const int32_t *col, 
                           const uint8_t *kind, double *rhs_inout, double *stats8) {
     if (n <= 0 || !rowptr || !col || !xy || !kind) return OCP_ERR_INVALID;
     MFSymbolic S;
-    mf_analyse(n, rowptr, col, xy, kind, 48, S);
+    mf_analyse(n, rowptr, col, xy, kind, mf_leaf_size(), S);
     MFHostNumeric N;
     if (val) {   // val == NULL: symbolic analysis only (statistics of large meshes)
         if (!mf_factor_host(S, val, N)) return OCP_ERR_SOLVER;

@@ -1,6 +1,7 @@
 // See multifrontal.hpp: host symbolic analysis + host restatement of the numeric phase.
 #include "multifrontal.hpp"
 
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -77,6 +78,13 @@ struct Builder {
 };
 
 }  // namespace
+
+int mf_leaf_size() {
+    // 80: on the 32 x 32 reference mesh 128 leaves (one wave of CTAs) and 8 tree levels instead of 158 / 9 with 48;
+    // measured step 3.15 ms vs 3.20 ms (profiles/README.md, round 2: leaf-size sweep 48 ... 128)
+    if (const char *e = getenv("OCP_MF_LEAF")) return std::max(8, atoi(e));
+    return 80;
+}
 
 void mf_analyse(int n, const int *rowptr, const int *col, const double *xy, const uint8_t *kind, int leaf,
                 MFSymbolic &S) {

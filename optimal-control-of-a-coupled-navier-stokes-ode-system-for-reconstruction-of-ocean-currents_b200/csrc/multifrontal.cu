@@ -1526,7 +1526,7 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     if (share && share->impl_ && share->n_ == n && share->nnz_ == nnz)
         I.S = share->impl_->S;
     else
-        mf_analyse(n, h_rowptr, h_col, xy, kind, 48, I.S);
+        mf_analyse(n, h_rowptr, h_col, xy, kind, mf_leaf_size(), I.S);
     const MFSymbolic &S = I.S;
     for (long long dd : S.a_dest)
         if (dd < 0) {

@@ -29,6 +29,9 @@ struct MFSymbolic {
     double flops = 0.0;
 };
 
+// largest dof set that is not dissected further (a leaf front): 80, or environment OCP_MF_LEAF
+int mf_leaf_size();
+
 // kind: 0 velocity-like, 1 pressure-like (ordered last inside a front); leaf: max dofs of a leaf front
 void mf_analyse(int n, const int *rowptr, const int *col, const double *xy, const uint8_t *kind, int leaf,
                 MFSymbolic &S);

@@ -4,8 +4,9 @@
 
     MESH_N=256 REPS=5 python tools/prof_assembly.py
 
-Algorithmic bytes per cell: 48 (geometry) + 60 (15 dof ids) + 96..120 (coefficients) + 900
-(225-entry slot table) + the cell's share of the CSR values (nnz * 8 / nc, written once) + 15 * 8 residual.
+Algorithmic bytes per cell: 48 (geometry) + 60 (15 dof ids) + 120 (coefficients)
++ the cell's share of the CSR values (nnz * 8 / nc, written once) + 15 * 8 residual ~ 1.3 KB.  The default gather
+assembly adds 360 B per cell of pair tables, the atomic scatter kernels (OCP_ASSEMBLY=atomic) a 900 B slot table.
 """
 import json
 import os
@@ -34,7 +35,8 @@ vals = torch.empty(nnz, dtype=torch.float64, device=dev)
 res = torch.empty(n, dtype=torch.float64, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-alg = nc * (48 + 60 + 120 + 900 + 120) + nnz * 8.0     # bytes per forward assembly (values read-modify-written once)
+alg = nc * (48 + 60 + 120 + 120) + nnz * 8.0     # algorithmic bytes per forward assembly (values written once)
+print("gather assembly" if ctx.option("gather_assembly") else "atomic scatter assembly", flush=True)
 out = []
 for rep in range(REPS):
     flush.zero_()
@@ -53,4 +55,5 @@ for rep in range(REPS):
 tf, ta = min(o[0] for o in out), min(o[1] for o in out)
 print(json.dumps({"mesh": N, "cells": nc, "nnz": nnz, "forward_ms": tf, "adjoint_ms": ta,
                   "algorithmic_bytes": alg, "forward_gbs": alg / tf / 1e6,
-                  "note": "times include the two memsets and the facet kernel of ocp_assemble_forward"}))
+                  "mode": "gather" if ctx.option("gather_assembly") else "atomic",
+                  "note": "times include the facet kernel (and, in atomic mode, the two memsets) of ocp_assemble_forward"}))
