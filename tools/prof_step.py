@@ -32,6 +32,10 @@ else:
 ocp._primal(w, ocp.d_x, ocp.d_u, ocp.d_mask)
 ocp.d_ud.copy_(ocp.d_u)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+ocp.d_f.copy_(f0)
+ocp.gradient_step(ocp.d_f)            # one-time work (symbolic reuse, dense operators, CUDA graphs) outside the region
+torch.cuda.synchronize()
+torch.cuda.profiler.start()           # `ncu --profile-from-start off` then sees only the steady-state steps
 for it in range(STEPS):
     ocp.d_f.copy_(f0)
     ev[0].record()
@@ -39,4 +43,5 @@ for it in range(STEPS):
     ev[1].record()
     torch.cuda.synchronize()
     print(f"step {it}: {ev[0].elapsed_time(ev[1]):.3f} ms, newton its {ocp.last_newton_its}", flush=True)
+torch.cuda.profiler.stop()
 print("J", ocp._cost_from_acc(ocp.d_f))
