@@ -80,6 +80,7 @@ class RunResult:
     exit_reason: str = "num_steps"
     f: Optional[np.ndarray] = None
     grad_tables: Optional[dict] = None
+    plots: Optional[dict] = None
 
 
 class State:
@@ -465,7 +466,8 @@ class OCP:
     def save_run(self, res: RunResult, out_dir: str, kn: Knobs):
         """The files the reference writes at the end of a run, same names and text formats: ``timings.txt``
         (OCP_dolfin.py:476-482), ``q_backup/q.xdmf`` (485-486), ``u_divergence.txt`` (489-492), ``variables.txt``
-        (495-507), ``J_array.npy`` (510-511), ``paraview/checkpoint/{u,p}.xdmf`` (578-588).  Plots are out of scope."""
+        (495-507), ``J_array.npy`` (510-511), ``paraview/checkpoint/{u,p}.xdmf`` (578-588), and the figures through
+        ``report.save_plots`` (455-575; PNGs need matplotlib, ``J.svg`` is always written)."""
         from . import checkpoint
         os.makedirs(os.path.join(out_dir, "q_backup"), exist_ok=True)
         with open(os.path.join(out_dir, "timings.txt"), "w") as fh:
@@ -496,6 +498,9 @@ class OCP:
             fh.write("gradient descent steps: %s \n" % kn.num_steps)
         np.save(os.path.join(out_dir, "J_array.npy"), np.array(res.J_array))
         checkpoint.write_state(os.path.join(out_dir, "paraview", "checkpoint"), self.V, self.d_w.cpu().numpy())
+        # figures of OCP_dolfin.py:455-575 (J.svg always; the PNGs when matplotlib is installed)
+        from . import report
+        res.plots = report.save_plots(self, res, out_dir)
 
     def field_norms(self, w: State):
         """(||div u||, ||u||_L2, ||u||_H1) - OCP_dolfin.py:430, Pipeline_limits.py:433-443."""

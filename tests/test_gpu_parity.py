@@ -495,7 +495,7 @@ def test_run_writes_the_reference_output_files_and_resumes(tmp_path):
     f0 = initial_control(V, "OCP")
     r3 = ocp.run(f0, Knobs(num_steps=3, use_line_search=True))
     r2 = ocp.run(f0, Knobs(num_steps=2, use_line_search=True), out_dir=out)
-    for name in ("timings.txt", "u_divergence.txt", "variables.txt", "J_array.npy", "q_backup/q.xdmf", "q_backup/q.h5",
+    for name in ("timings.txt", "u_divergence.txt", "variables.txt", "J_array.npy", "J.svg", "q_backup/q.xdmf", "q_backup/q.h5",
                  "checkpoints/q.h5", "paraview/checkpoint/u.h5", "paraview/checkpoint/p.xdmf"):
         assert os.path.exists(os.path.join(out, name)), name
     assert np.allclose(np.load(os.path.join(out, "J_array.npy")), r2.J_array)
@@ -503,6 +503,8 @@ def test_run_writes_the_reference_output_files_and_resumes(tmp_path):
     # resume: third iteration from the checkpointed control equals the uninterrupted run
     q = checkpoint.read_control(os.path.join(out, "checkpoints", "q.h5"), V)
     assert np.array_equal(q, r2.f)
+    from ocp_b200 import h5lite
+    assert h5lite.checkpoint_counters(os.path.join(out, "checkpoints", "q.h5"), "f") == [0, 1]   # one group per iteration
     r1 = ocp.run(q, Knobs(num_steps=1, use_line_search=True), LR=r2.LR)
     assert abs(r1.J_array[0] - r3.J_array[2]) <= 1e-10 * abs(r3.J_array[2])
     w = checkpoint.read_state(os.path.join(out, "paraview/checkpoint/u.h5"), V, "u")
