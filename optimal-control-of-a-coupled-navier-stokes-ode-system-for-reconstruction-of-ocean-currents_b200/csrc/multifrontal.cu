@@ -26,6 +26,9 @@ namespace ocp {
 
 namespace {
 
+// factor-kernel variant chosen in "auto" mode (measured, profiles/README.md round 2)
+#define MF_AUTO_VARIANT(max_m, legacy) (legacy)
+
 constexpr int NB = 16;     // panel width
 constexpr int CWO = 4;     // column-ownership granularity inside a cluster (= tile width)
 
@@ -1414,13 +1417,39 @@ mf_backward_big_kernel(MFDev d, const int *__restrict__ nodes, double *__restric
 // kernel variants: <threads, panel rows per thread>; one warp of every CTA is the look-ahead warp, the others take one
 // or two panel rows each.  The thread counts keep the register budget per thread above what the kernel needs
 // (65536 / 288 = 227, / 416 = 157) - at 512 threads (128 registers) it spills.
-enum { kVar288 = 0, kVar416 = 1, kVar512 = 2, kVar512x2 = 3, kNumVariants = 4 };
-inline int factor_variant(int max_m) { return max_m <= 256 ? kVar288 : (max_m <= 384 ? kVar416 : (max_m <= 480 ? kVar512 : kVar512x2)); }
-inline int variant_threads(int v) { return v == kVar288 ? 288 : (v == kVar416 ? 416 : 512); }
+enum { kVar288 = 0, kVar416 = 1, kVar512 = 2, kVar512x2 = 3, kVar256x2 = 4, kVar384x2 = 5, kNumVariants = 6 };
+// Register budget: a warp scheduler owns 16384 registers and the warps of a CTA are dealt round-robin, so a CTA of
+// 9 warps (288 threads) may use 168 registers per thread, 12 warps (384) 168, but 13 warps (416) or 16 (512) only 128 -
+// `ptxas -v` (profiles/ptxas_r2.txt) shows the 416- and 512-thread variants spilling 300-500 bytes per thread.  The
+// x2 variants give every worker two panel rows instead: 256 threads (7 worker warps, 255 registers) cover fronts of
+// order <= 448, 384 threads (11 worker warps, 168 registers) <= 704.  OCP_MF_THREADS selects: "auto" (default, the
+// measured best), "legacy" (288 / 416 / 512), "256", "384".
+inline int factor_variant(int max_m) {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("OCP_MF_THREADS");
+        const std::string v = e ? e : "auto";
+        mode = v == "legacy" ? 0 : (v == "256" ? 1 : (v == "384" ? 2 : 3));
+    }
+    const int legacy = max_m <= 256 ? kVar288 : (max_m <= 384 ? kVar416 : (max_m <= 480 ? kVar512 : kVar512x2));
+    if (mode == 1) return max_m <= 448 ? kVar256x2 : (max_m <= 704 ? kVar384x2 : kVar512x2);
+    if (mode == 2) return max_m <= 704 ? kVar384x2 : kVar512x2;
+    if (mode == 3) return MF_AUTO_VARIANT(max_m, legacy);
+    return legacy;
+}
+inline int variant_threads(int v) {
+    return v == kVar288 ? 288 : (v == kVar416 ? 416 : (v == kVar256x2 ? 256 : (v == kVar384x2 ? 384 : 512)));
+}
 typedef void (*FactorKernel)(MFDev, const int *, int, int *, long long *);
 inline FactorKernel factor_kernel(int v) {
-    return v == kVar288 ? mf_factor_kernel<288, 1>
-                        : (v == kVar416 ? mf_factor_kernel<416, 1> : (v == kVar512 ? mf_factor_kernel<512, 1> : mf_factor_kernel<512, 2>));
+    switch (v) {
+        case kVar288: return mf_factor_kernel<288, 1>;
+        case kVar416: return mf_factor_kernel<416, 1>;
+        case kVar512: return mf_factor_kernel<512, 1>;
+        case kVar256x2: return mf_factor_kernel<256, 2>;
+        case kVar384x2: return mf_factor_kernel<384, 2>;
+        default: return mf_factor_kernel<512, 2>;
+    }
 }
 
 template <class T>
