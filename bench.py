@@ -38,7 +38,8 @@ K_GLOBAL = 10_000
 NT = 200
 PUBLISHED_BUOY_STEPS_PER_S = 4.0e3          # BASELINE.md section 1 (derived from 1500 s / iteration)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full captures (profiles/)
-NCU_TRAFFIC_INSTEP_BACKWARD = 96_212_736 + 3_859_456          # K = 10 000: algorithmic 96 000 000 B
+NCU_TRAFFIC_INSTEP_BACKWARD = 114_538_752 + 4_786_944         # K = 10 000, time-parallel sweep (two passes over the streams,
+                                                              # the second mostly from L2): algorithmic 96 000 000 B
 NCU_TRAFFIC_SWEEP_BACKWARD = 10_081_863_000 + 5_742_000       # K = 2^20:   algorithmic 10 066 329 600 B
 NCU_TRAFFIC_SWEEP_FORWARD = 19_127_000 + 6_656_207_000        # K = 2^20:   algorithmic  6 710 886 400 B
 METRIC = "gd_buoy_steps_per_sec"
@@ -603,13 +604,14 @@ def run_ours(args):
                        "note": "strong scaling of cfg3 divides only the buoy sweeps; the 9539-dof FE solve is "
                                "replicated on every rank (cheaper than communicating it), so the step is bounded "
                                "below by replicated_fe_ms - see sweep_strong for the scaling target"},
-            "roofline": {"bound": "hbm", "kernel": "buoy_adjoint_scatter_kernel", "achieved": ach, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "buoy_adjoint_scatter_tp_kernel (in-step backward sweep)", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_INSTEP_BACKWARD if world == 1 else None,
-                         "traffic_source": "profiles/prof_instep_backward.raw.txt (ncu --set full, dram read+write)",
+                         "traffic_source": "profiles/prof_r2_tp.summary.txt (ncu --set full, dram read+write)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_back, "ms": ms_back,
-                         "note": "in-step launch (this rank's share of the 10000 buoys); "
-                                 "see roofline_sweep for the same kernel at 2^20 buoys"},
+                         "note": "in-step launch (this rank's share of the 10000 buoys): latency-bound, the "
+                                 "time-parallel sweep is used at this size; see roofline_sweep for the serial sweep "
+                                 "kernels at 2^20 buoys, where the path is bandwidth-bound"},
             "roofline_sweep": sweep,
             "roofline_lu": lu,
             "sweep_strong": ss,
