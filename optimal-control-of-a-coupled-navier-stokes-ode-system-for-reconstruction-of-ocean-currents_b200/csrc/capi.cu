@@ -108,6 +108,14 @@ struct ocp_ctx {
     // resident observations (the reference's module globals u_d, xsarr, ysarr; OCP_dolfin.py:176-183)
     double *d_obs_x0 = nullptr, *d_obs_ud = nullptr;
     int obs_K = 0;
+    // device-side Newton control: residual history, convergence flag and iterate count live on the device, so the host
+    // can enqueue the iterates it expects (newton_pred = count of the previous zero-initialised solve) without a round
+    // trip per iterate; updates after convergence are skipped on the device (OCP_NEWTON_SPECULATE=0 disables)
+    double *d_nhist = nullptr;     // 64 doubles: ||F||_2 per iterate
+    int *d_nstate = nullptr;       // [0] converged, [1] iterate count at convergence, [2] NaN seen
+    double *h_nhist = nullptr;     // pinned mirror (64 doubles + 4 ints)
+    int newton_pred = -1;
+    bool newton_speculate = true;
     DirectSolver lu_fwd, lu_adj, lu_mass, lu_stokes;
     bool stokes_valid = false;   // lu_stokes holds the factors of dF/dw at w = 0 (the Stokes operator + BC rows)
     DirectSolver *last_newton_lu = nullptr;   // factors used by the last Newton step of the last forward solve
@@ -461,6 +469,36 @@ int run_buoy_backward(ocp_ctx *c, const double *d_vel, const double *d_g, int K,
     return OCP_OK;
 }
 
+// dolfin's NewtonSolver stop test on the device: hist[it] = ||F||, converged once ||F|| < atol or ||F|| / ||F_0|| < rtol
+__global__ void newton_check_kernel(const double *sumsq, int it, double atol, double rtol, double *hist, int *state) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (it == 0) {
+        state[0] = 0;
+        state[1] = -1;
+        state[2] = 0;
+    }
+    const double r = sqrt(sumsq[0]);
+    if (state[0]) return;              // already converged: later (speculative) iterates leave the record untouched
+    hist[it] = r;
+    const double r0 = hist[0];
+    if (!(r == r)) {
+        state[0] = 1;
+        state[1] = it;
+        state[2] = 1;
+    } else if (r < atol || (r0 > 0.0 && r / r0 < rtol)) {
+        state[0] = 1;
+        state[1] = it;
+    }
+}
+
+// y += a x unless the Newton loop has already converged
+__global__ void axpy_unless_kernel(int n, double a, const double *__restrict__ x, double *__restrict__ y,
+                                   const int *__restrict__ converged) {
+    if (*converged) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += a * x[i];
+}
+
 __global__ void unit_vectors_kernel(int n, int nrhs, const int *idx, int j0, int ncol, double *v) {
     // v (nrhs x n) = unit vectors e_{idx[j0 + r]} (idx null: e_{j0 + r}); rows beyond ncol stay zero
     const int r = blockIdx.x;
@@ -599,6 +637,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     if (const char *er = getenv("OCP_ADJ_REUSE")) c->adj_reuse = atoi(er) != 0;
     if (const char *ed = getenv("OCP_DETERMINISTIC")) c->deterministic = atoi(ed) != 0;
     if (const char *ed = getenv("OCP_DENSE_OPS")) c->dense_ops = atoi(ed) != 0;
+    if (const char *ed = getenv("OCP_NEWTON_SPECULATE")) c->newton_speculate = atoi(ed) != 0;
     // staged (shared-memory / TMA) buoy kernels are opt-in: measured slower than the global-table kernels on B200
     if (const char *es = getenv("OCP_BUOY_STAGED"))
         c->buoy_staged = atoi(es) != 0 && buoy_tables_fit_shared(d->nc, d->nn, d->nv);
@@ -706,6 +745,9 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     CUDA_OK(c, cudaMalloc((void **)&c->d_counter, sizeof(unsigned)));
     CUDA_OK(c, cudaMemset(c->d_counter, 0, sizeof(unsigned)));
     CUDA_OK(c, cudaMallocHost((void **)&c->h_pinned, sizeof(double) * 8));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_nhist, sizeof(double) * 64));
+    CUDA_OK(c, cudaMalloc((void **)&c->d_nstate, sizeof(int) * 4));
+    CUDA_OK(c, cudaMallocHost((void **)&c->h_nhist, sizeof(double) * 66));
     CUDA_OK(c, cudaEventCreate(&c->ev0));
     CUDA_OK(c, cudaEventCreate(&c->ev1));
     int rc = ensure_scratch(c, 3 * (size_t)((nc + 127) / 128) + 1024);
@@ -757,6 +799,9 @@ void ocp_destroy(ocp_ctx *c) {
     for (int i = 0; i < 7; ++i) cudaFree(c->d_gather[i]);
     cudaFree(c->d_vals2);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_nhist) cudaFreeHost(c->h_nhist);
+    cudaFree(c->d_nhist);
+    cudaFree(c->d_nstate);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -787,8 +832,11 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
     const double atol = 1e-10, rtol = 1e-9;
     const int maxit = 50;
     if (zero_init) CUDA_OK(c, cudaMemsetAsync(d_w, 0, sizeof(double) * n, s));
-    double r0 = 0.0, r = 0.0;
-    int it = 0;
+    // iterates 0 .. pred-1 are enqueued without asking the host whether the loop has converged (it has not, if this
+    // solve behaves like the previous one); the stop test runs on the device either way and updates after
+    // convergence are skipped there, so the iterates and their count are exactly those of the synchronous loop
+    const int pred = (zero_init && c->newton_speculate && !c->profile) ? c->newton_pred : -1;
+    int it = 0, its = -1;
     for (;;) {
         // The Newton matrix at the zero initial guess is the Stokes operator (convection and the Gamma_1 term vanish
         // at u = 0): it does not depend on the control, so its factors are computed once per context and reused by the
@@ -801,24 +849,29 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
             int rc = assemble_forward(c, d_w, d_f, vals, c->d_res, true);
             if (rc != OCP_OK) return rc;
             launch_sumsq(n, c->d_res, c->d_scalar, c->d_scratch, c->d_counter, s);
+            newton_check_kernel<<<1, 32, 0, s>>>(c->d_scalar, it, atol, rtol, c->d_nhist, c->d_nstate);
         }
-        double ss;
-        int rc = read_scalar(c, c->d_scalar, 1, &ss);
-        if (rc != OCP_OK) return rc;
-        if (!c->lu_fwd.check(c->err) || !c->lu_stokes.check(c->err)) return OCP_ERR_SOLVER;   // stream is idle: pivot flags
-        r = std::sqrt(ss);
-        if (it == 0) r0 = r;
-        if (h_res_hist) h_res_hist[it] = r;
-        if (!(r == r)) {
-            c->err = "Newton residual is NaN";
-            if (newton_its) *newton_its = it;
-            return OCP_ERR_NOT_CONVERGED;
-        }
-        if (r < atol || (r0 > 0.0 && r / r0 < rtol)) break;
-        if (it >= maxit) {
-            c->err = "Newton solver did not converge in 50 iterations";
-            if (newton_its) *newton_its = it;
-            return OCP_ERR_NOT_CONVERGED;
+        if (it >= pred) {
+            // host decision point
+            CUDA_OK(c, cudaMemcpyAsync(c->h_nhist, c->d_nhist, sizeof(double) * 64, cudaMemcpyDeviceToHost, s));
+            CUDA_OK(c, cudaMemcpyAsync(c->h_nhist + 64, c->d_nstate, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_OK(c, cudaStreamSynchronize(s));
+            if (!c->lu_fwd.check(c->err) || !c->lu_stokes.check(c->err)) return OCP_ERR_SOLVER;   // stream is idle: pivot flags
+            const int *st = reinterpret_cast<const int *>(c->h_nhist + 64);
+            if (st[0]) {
+                its = st[1];
+                if (st[2]) {
+                    c->err = "Newton residual is NaN";
+                    if (newton_its) *newton_its = its;
+                    return OCP_ERR_NOT_CONVERGED;
+                }
+                break;
+            }
+            if (it >= maxit) {
+                c->err = "Newton solver did not converge in 50 iterations";
+                if (newton_its) *newton_its = it;
+                return OCP_ERR_NOT_CONVERGED;
+            }
         }
         DirectSolver &lu = stokes_step ? c->lu_stokes : c->lu_fwd;
         if (!(stokes_step && c->stokes_valid)) {
@@ -837,19 +890,25 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
         {
             PhaseTimer t(c, &c->stats.solve_ms);
             c->last_newton_lu = &lu;
+            const double *dx = c->d_res;
             if (dense_step) {
                 launch_dense_apply(n, c->n_g1dofs, 1, c->d_stokes_resp, c->d_res, n, c->d_g1dofs, c->d_tmp, c->d_dense_part, s);
-                launch_axpy(n, -1.0, c->d_tmp, d_w, s);
+                dx = c->d_tmp;
                 c->stats.n_dense++;
             } else {
                 if (!lu.solve(c->d_res, s, c->err)) return OCP_ERR_SOLVER;   // d_res <- dx
-                launch_axpy(n, -1.0, c->d_res, d_w, s);
                 c->stats.n_solve++;
             }
+            g_launch_count.fetch_add(1, std::memory_order_relaxed);
+            axpy_unless_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, -1.0, dx, d_w, c->d_nstate);
         }
         ++it;
     }
-    if (newton_its) *newton_its = it;
+    if (zero_init) c->newton_pred = its;
+    if (h_res_hist)
+        for (int k = 0; k <= its; ++k) h_res_hist[k] = c->h_nhist[k];
+    if (newton_its) *newton_its = its;
+    CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
 }
 
