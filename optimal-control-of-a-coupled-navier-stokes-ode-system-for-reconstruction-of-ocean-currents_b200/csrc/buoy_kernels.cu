@@ -1238,15 +1238,16 @@ bool allow_smem(Kern k, size_t bytes) {
 // Lanes per buoy of the time-parallel backward sweep: 32 for the thesis' buoy counts (<= 2000), 8 up to the 10 000-buoy
 // run, 1 (serial sweep, bandwidth-bound) beyond.  OCP_BUOY_TP=0 forces the serial sweep.
 int time_parallel_lanes(int K, int nt, int nrep) {
-    static int enabled = -1;
+    static int enabled = -1, forced = 0;
     if (enabled < 0) {
         const char *e = getenv("OCP_BUOY_TP");
         enabled = (e && atoi(e) == 0) ? 0 : 1;
+        if (const char *l = getenv("OCP_BUOY_TP_LANES")) forced = atoi(l) == 32 ? 32 : (atoi(l) == 8 ? 8 : 0);
     }
     if (!enabled || nrep > 1 || nt < 64) return 1;
-    if (K <= 2000) return 32;
-    if (K <= 12000) return 8;
-    return 1;
+    if (K > 12000) return 1;
+    if (forced) return forced;
+    return K <= 2000 ? 32 : 8;
 }
 
 bool buoy_tables_fit_shared(int nc, int nn, int nv) {

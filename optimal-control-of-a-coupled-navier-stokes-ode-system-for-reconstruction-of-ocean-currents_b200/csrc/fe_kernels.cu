@@ -185,17 +185,19 @@ assemble_facets_ordered_kernel(int ncolors, const int *__restrict__ color_ptr, c
             }
             double A[6], R;
             facet_row(__ldg(g1_len + fct), __ldg(g1_normal + 2 * fct), __ldg(g1_normal + 2 * fct + 1), U, V, Fx, Fy, r, A, R);
-            if (vals) {
+            // all read-modify-writes of this (facet, row) are issued together: one L2 round trip, not seven
+            double *dst[7];
+            double cur[7];
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    double *dst = vals + __ldg(g1_slots + 36 * fct + (kTranspose ? j * 6 + r : r * 6 + j));
-                    *dst = *dst + A[j];
-                }
-            }
-            if (res) {
-                double *dst = res + __ldg(g1_dofs + 6 * fct + r);
-                *dst = *dst + R;
-            }
+            for (int j = 0; j < 6; ++j)
+                dst[j] = vals ? vals + __ldg(g1_slots + 36 * fct + (kTranspose ? j * 6 + r : r * 6 + j)) : nullptr;
+            dst[6] = res ? res + __ldg(g1_dofs + 6 * fct + r) : nullptr;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) cur[j] = dst[j] ? __ldcg(dst[j]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                if (dst[j]) __stcg(dst[j], cur[j] + A[j]);
+            if (dst[6]) __stcg(dst[6], cur[6] + R);
         }
         __syncthreads();
     }
