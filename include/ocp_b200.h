@@ -221,6 +221,22 @@ void ocp_get_solver_info(const ocp_ctx *ctx, double *out8);
  * events).  The denominator of the sparse-LU roofline; MEASURED_PEAKS.json holds no fp64 figure. */
 int ocp_selftest_fp64_peak(ocp_ctx *ctx, double *tflops);
 
+/* ---- one gradient evaluation on DEVICE buffers: the "outer" block OCP_dolfin.py:313-371 in one call ---------------
+ * forward solve from the zero guess with control d_f (nn,2), projection, primal ODE from d_x0 (K,2), backward sweep
+ * against d_ud (nt,K,2), all-reduce (when a communicator is set), adjoint solve; d_mask (K) and d_acc (2 nn + 2) are
+ * zeroed inside.  Outputs: d_w, d_g (nv,4), d_vel (nn,2), d_x, d_u (nt,K,2), d_mask, d_parked, d_acc, d_z and, when both
+ * d_znod and d_grad are given, grad j = alpha f - z on the nodes (OCP_dolfin.py:379).  Once a plain evaluation has
+ * run, the whole call is replayed as ONE CUDA graph per (buffers, expected Newton count); the host decisions of
+ * the block (Newton converged, adjoint residual gate, pivot flags) are verified after the replay and the plain path
+ * re-runs the evaluation if they do not hold (OCP_STEP_GRAPH=0 disables).  The call returns with the stream idle. */
+int ocp_gradient_device(ocp_ctx *ctx, const double *d_f, const double *d_x0, const double *d_ud, int K, double *d_w,
+                        double *d_g, double *d_vel, double *d_x, double *d_u, double *d_mask, uint8_t *d_parked,
+                        double *d_acc, double *d_z, double *d_znod, double *d_grad, double alpha, int *newton_its);
+
+/* ||F||_2 per Newton iterate of the LAST completed forward solve (the history lives on the device and is copied to the
+ * host at the solve's one synchronisation); returns the number of entries written (iterates + 1). */
+int ocp_newton_history(const ocp_ctx *ctx, double *h_hist, int max_entries);
+
 /* Number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 long long ocp_launch_count(void);
 

@@ -27,6 +27,7 @@ SYMBOLS = [
     "ocp_velocity_nodal", "ocp_buoy_forward", "ocp_buoy_adjoint_scatter", "ocp_misfit",
     "ocp_adjoint_solve", "ocp_boundary_inner", "ocp_nodal_axpby", "ocp_field_norms", "ocp_traj_transpose",
     "ocp_solve_primal_ode_host", "ocp_solve_adjoint_ode_host", "ocp_set_observations_host", "ocp_gradient_host",
+    "ocp_gradient_device", "ocp_newton_history",
     "ocp_launch_count", "ocp_get_solver_info", "ocp_selftest_fp64_peak",
     "ocp_comm_get_unique_id", "ocp_comm_init", "ocp_comm_size", "ocp_comm_nccl_version", "ocp_allreduce",
     "ocp_host_gather_probe", "ocp_host_lu_probe", "ocp_host_mf_probe", "ocp_host_mf_set_pivot_window", "ocp_selftest_cell_matrix", "ocp_selftest_facet_matrix",
@@ -318,6 +319,21 @@ class Context:
     def traj_transpose(self, d_src, d_dst, K, to_time_major: bool):
         self._check(self.lib.ocp_traj_transpose(self._h, _dp(d_src), _dp(d_dst), int(K), int(to_time_major)),
                     "ocp_traj_transpose")
+
+    def gradient_device(self, d_f, d_x0, d_ud, K, d_w, d_g, d_vel, d_x, d_u, d_mask, d_parked, d_acc, d_z, d_znod,
+                        d_grad, alpha: float) -> int:
+        """The whole "outer" block on device buffers (one CUDA graph replay once warm); returns the Newton count."""
+        its = C.c_int(0)
+        rc = self.lib.ocp_gradient_device(self._h, _dp(d_f), _dp(d_x0), _dp(d_ud), int(K), _dp(d_w), _dp(d_g), _dp(d_vel),
+                                          _dp(d_x), _dp(d_u), _dp(d_mask), _dp(d_parked), _dp(d_acc), _dp(d_z),
+                                          _dp(d_znod), _dp(d_grad), C.c_double(alpha), C.byref(its))
+        self._check(rc, "ocp_gradient_device")
+        return its.value
+
+    def newton_history(self):
+        hist = (C.c_double * 64)()
+        n = self.lib.ocp_newton_history(self._h, hist, 64)
+        return [hist[i] for i in range(n)]
 
     # -- host-buffer entry points (numpy in / numpy out, copies inside the call) -------------------------------
     def solve_primal_ode_host(self, w: np.ndarray, x0: np.ndarray, mask: np.ndarray):

@@ -68,6 +68,10 @@ struct DirectSolver {
         return mf.solve(d_x, s, err, true);
     }
     bool check(std::string &err) { return use_mf ? mf.check(err) : true; }
+    void set_direct_enqueue(bool on) {
+        if (use_mf) mf.set_direct_enqueue(on);
+    }
+    bool capturable() const { return use_mf && !mf.needs_cooperative_launch(); }
 };
 
 struct ocp_ctx {
@@ -108,6 +112,21 @@ struct ocp_ctx {
     // resident observations (the reference's module globals u_d, xsarr, ysarr; OCP_dolfin.py:176-183)
     double *d_obs_x0 = nullptr, *d_obs_ud = nullptr;
     int obs_K = 0;
+    // One CUDA graph per gradient evaluation (ocp_gradient_device): the launches of a whole "outer" block are captured
+    // once per (buffers, expected Newton count) and replayed; the two host decisions of the block - Newton converged
+    // within the expected count, adjoint residual gate - are verified AFTER the replay from values the graph copied to
+    // pinned memory, and the plain path re-runs the evaluation if either fails.  OCP_STEP_GRAPH=0 disables.
+    struct StepGraph {
+        std::vector<unsigned char> key;
+        int pred = 0;
+        long long launches = 0;       // kernel launches captured in the graph
+        cudaGraphExec_t exec = nullptr;
+    };
+    std::vector<StepGraph> step_graphs;
+    bool step_graph = true, capturing = false;
+    cudaStream_t cap_stream = nullptr;
+    int warm_K = -1;              // a plain evaluation with this buoy count has run (work arrays sized, operators built)
+    int n_step_graph = 0, n_step_plain = 0;
     // device-side Newton control: residual history, convergence flag and iterate count live on the device, so the host
     // can enqueue the iterates it expects (newton_pred = count of the previous zero-initialised solve) without a round
     // trip per iterate; updates after convergence are skipped on the device (OCP_NEWTON_SPECULATE=0 disables)
@@ -613,6 +632,8 @@ int ocp_get_option(const ocp_ctx *ctx, const char *name) {
     if (n == "buoy_staged") return ctx->buoy_staged ? 1 : 0;
     if (n == "adj_reuse") return ctx->adj_reuse ? 1 : 0;
     if (n == "gather_assembly") return ctx->gather ? 1 : 0;
+    if (n == "step_graph_replays") return ctx->n_step_graph;
+    if (n == "step_plain_runs") return ctx->n_step_plain;
     return -1;
 }
 
@@ -638,6 +659,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     if (const char *ed = getenv("OCP_DETERMINISTIC")) c->deterministic = atoi(ed) != 0;
     if (const char *ed = getenv("OCP_DENSE_OPS")) c->dense_ops = atoi(ed) != 0;
     if (const char *ed = getenv("OCP_NEWTON_SPECULATE")) c->newton_speculate = atoi(ed) != 0;
+    if (const char *ed = getenv("OCP_STEP_GRAPH")) c->step_graph = atoi(ed) != 0;
     // staged (shared-memory / TMA) buoy kernels are opt-in: measured slower than the global-table kernels on B200
     if (const char *es = getenv("OCP_BUOY_STAGED"))
         c->buoy_staged = atoi(es) != 0 && buoy_tables_fit_shared(d->nc, d->nn, d->nv);
@@ -802,6 +824,9 @@ void ocp_destroy(ocp_ctx *c) {
     if (c->h_nhist) cudaFreeHost(c->h_nhist);
     cudaFree(c->d_nhist);
     cudaFree(c->d_nstate);
+    for (auto &g : c->step_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -855,6 +880,10 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
             // host decision point
             CUDA_OK(c, cudaMemcpyAsync(c->h_nhist, c->d_nhist, sizeof(double) * 64, cudaMemcpyDeviceToHost, s));
             CUDA_OK(c, cudaMemcpyAsync(c->h_nhist + 64, c->d_nstate, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+            if (c->capturing) {      // the decision is verified after the graph has run (gradient_step)
+                its = it;
+                break;
+            }
             CUDA_OK(c, cudaStreamSynchronize(s));
             if (!c->lu_fwd.check(c->err) || !c->lu_stokes.check(c->err)) return OCP_ERR_SOLVER;   // stream is idle: pivot flags
             const int *st = reinterpret_cast<const int *>(c->h_nhist + 64);
@@ -904,8 +933,8 @@ int ocp_forward_solve(ocp_ctx *c, const double *d_f, double *d_w, int zero_init,
         }
         ++it;
     }
-    if (zero_init) c->newton_pred = its;
-    if (h_res_hist)
+    if (zero_init && !c->capturing) c->newton_pred = its;
+    if (h_res_hist && !c->capturing)
         for (int k = 0; k <= its; ++k) h_res_hist[k] = c->h_nhist[k];
     if (newton_its) *newton_its = its;
     CUDA_OK(c, cudaGetLastError());
@@ -1018,6 +1047,10 @@ int ocp_adjoint_solve(ocp_ctx *c, const double *d_w, const double *d_bnode, doub
         launch_sumsq(n, c->d_tmp, c->d_scalar, c->d_scratch, c->d_counter, s);
         launch_sumsq(n, c->d_rhs, c->d_scalar + 1, c->d_scratch, c->d_counter, s);
         CUDA_OK(c, cudaGetLastError());
+        if (c->capturing) {      // the gate is evaluated after the graph has run (gradient_step)
+            CUDA_OK(c, cudaMemcpyAsync(c->h_pinned + 4, c->d_scalar, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+            return OCP_OK;
+        }
         double ss[2];
         int rc = read_scalar(c, c->d_scalar, 2, ss);
         if (rc != OCP_OK) return rc;
@@ -1183,6 +1216,148 @@ int ocp_set_observations_host(ocp_ctx *c, const double *h_x0, const double *h_ud
     return OCP_OK;
 }
 
+// ---- one gradient evaluation on device buffers -------------------------------------------------------------------
+struct StepArgs {
+    const double *d_f, *d_x0, *d_ud;
+    int K;
+    double *d_w, *d_g, *d_vel, *d_x, *d_u, *d_mask;
+    uint8_t *d_parked;
+    double *d_acc, *d_z, *d_znod, *d_grad;
+    double alpha;
+};
+
+static int enqueue_gradient_step(ocp_ctx *c, const StepArgs &a, int *its) {
+    cudaStream_t s = c->stream;
+    const size_t nacc = 2 * (size_t)c->nn + 2;
+    int rc;
+    CUDA_OK(c, cudaMemsetAsync(a.d_mask, 0, sizeof(double) * a.K, s));
+    CUDA_OK(c, cudaMemsetAsync(a.d_acc, 0, sizeof(double) * nacc, s));
+    if ((rc = ocp_forward_solve(c, a.d_f, a.d_w, 1, its, nullptr))) return rc;
+    if ((rc = ocp_project_grad(c, a.d_w, a.d_g))) return rc;
+    launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, a.d_w, a.d_vel, s);
+    run_buoy_forward(c, a.d_vel, a.d_x0, a.K, a.d_x, a.d_u, nullptr, a.d_mask, a.d_parked);
+    if ((rc = run_buoy_backward(c, a.d_vel, a.d_g, a.K, a.d_x, a.d_u, a.d_ud, a.d_mask, a.d_parked, nullptr, a.d_acc, true)))
+        return rc;
+    // buoys sharded over ranks: the sum over buoys (OCP_dolfin.py:353-366) is completed across GPUs here
+    if (!c->comm.allreduce_sum(a.d_acc, nacc, s, c->err)) return OCP_ERR_COMM;
+    if ((rc = ocp_adjoint_solve(c, a.d_w, a.d_acc, a.d_z))) return rc;
+    if (a.d_znod && a.d_grad) {       // grad j = alpha f - z on the nodes (OCP_dolfin.py:379)
+        launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, a.d_z, a.d_znod, s);
+        launch_axpby(2 * c->nn, a.alpha, a.d_f, -1.0, a.d_znod, a.d_grad, s);
+    }
+    CUDA_OK(c, cudaGetLastError());
+    return OCP_OK;
+}
+
+static int gradient_step(ocp_ctx *c, const StepArgs &a, int *its_out) {
+    int its = 0;
+    const bool eligible = c->step_graph && !c->profile && c->newton_speculate && c->newton_pred >= 1 && c->warm_K == a.K &&
+                          c->stokes_valid && c->adj_reuse && c->nu == 1.0 && c->lu_fwd.capturable() &&
+                          c->lu_stokes.capturable() && c->lu_mass.capturable() &&
+                          c->comm.size() == 1;   // (sharded runs: a rank-local fall-back would issue an unmatched collective)
+    if (eligible) {
+        std::vector<unsigned char> key(sizeof(StepArgs));
+        memcpy(key.data(), &a, sizeof(StepArgs));
+        ocp_ctx::StepGraph *entry = nullptr;
+        for (auto &g : c->step_graphs)
+            if (g.pred == c->newton_pred && g.key == key) entry = &g;
+        if (!entry) {
+            if (!c->cap_stream && cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+                cudaGetLastError();
+                c->step_graph = false;
+            } else {
+                CUDA_OK(c, cudaStreamSynchronize(c->stream));
+                cudaStream_t user = c->stream;
+                cudaGraph_t g = nullptr;
+                cudaGraphExec_t ge = nullptr;
+                long long captured_launches = 0;
+                bool ok = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                if (ok) {
+                    c->stream = c->cap_stream;
+                    c->capturing = true;
+                    DirectSolver *solvers[] = {&c->lu_fwd, &c->lu_stokes, &c->lu_mass, &c->lu_adj};
+                    for (DirectSolver *d : solvers) d->set_direct_enqueue(true);
+                    int dummy = 0;
+                    const ocp_solver_stats keep = c->stats;
+                    const long long l0 = g_launch_count.load();
+                    const int rc = enqueue_gradient_step(c, a, &dummy);
+                    captured_launches = g_launch_count.load() - l0;
+                    g_launch_count.store(l0);       // nothing ran: captured launches are counted per replay
+                    c->stats = keep;
+                    for (DirectSolver *d : solvers) d->set_direct_enqueue(false);
+                    c->capturing = false;
+                    c->stream = user;
+                    cudaError_t e = cudaStreamEndCapture(c->cap_stream, &g);
+                    ok = rc == OCP_OK && e == cudaSuccess && g != nullptr;
+                    if (ok) ok = cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
+                    if (g) cudaGraphDestroy(g);
+                }
+                if (!ok) {
+                    cudaGetLastError();
+                    c->step_graph = false;      // capture not possible here: plain path from now on
+                    if (getenv("OCP_SOLVER_VERBOSE")) fprintf(stderr, "[ocp_b200] step graph capture failed: %s\n", c->err.c_str());
+                } else {
+                    if (c->step_graphs.size() >= 8) {
+                        cudaGraphExecDestroy(c->step_graphs.front().exec);
+                        c->step_graphs.erase(c->step_graphs.begin());
+                    }
+                    ocp_ctx::StepGraph sg;
+                    sg.key = key;
+                    sg.pred = c->newton_pred;
+                    sg.launches = captured_launches;
+                    sg.exec = ge;
+                    c->step_graphs.push_back(sg);
+                    entry = &c->step_graphs.back();
+                }
+            }
+        }
+        if (entry) {
+            g_launch_count.fetch_add(entry->launches, std::memory_order_relaxed);    // kernel nodes of the replayed graph
+            CUDA_OK(c, cudaGraphLaunch(entry->exec, c->stream));
+            CUDA_OK(c, cudaStreamSynchronize(c->stream));
+            const int *st = reinterpret_cast<const int *>(c->h_nhist + 64);
+            const double r0 = c->h_pinned[4], b0 = c->h_pinned[5];
+            std::string e2;
+            const bool newton_ok = st[0] == 1 && st[2] == 0 && st[1] <= entry->pred;
+            const bool adjoint_ok = r0 == r0 && r0 <= 1e-24 * b0;
+            const bool pivots_ok = c->lu_fwd.check(e2) && c->lu_stokes.check(e2);
+            if (newton_ok && adjoint_ok && pivots_ok) {
+                its = st[1];
+                c->newton_pred = its;
+                c->last_newton_lu = its >= 2 || entry->pred >= 2 ? &c->lu_fwd : &c->lu_stokes;
+                c->stats.n_factor += std::max(0, entry->pred - 1);
+                c->stats.n_solve += std::max(0, entry->pred - 1) + 2;
+                c->n_adj_reused++;
+                c->n_step_graph++;
+                if (its_out) *its_out = its;
+                return OCP_OK;
+            }
+            // expectations not met (more Newton iterates needed, gate rejected, pivot flag): plain path from scratch
+        }
+    }
+    const int rc = enqueue_gradient_step(c, a, &its);
+    if (rc == OCP_OK) {
+        c->warm_K = a.K;
+        c->n_step_plain++;
+    }
+    if (its_out) *its_out = its;
+    return rc;
+}
+
+int ocp_gradient_device(ocp_ctx *c, const double *d_f, const double *d_x0, const double *d_ud, int K, double *d_w,
+                        double *d_g, double *d_vel, double *d_x, double *d_u, double *d_mask, uint8_t *d_parked,
+                        double *d_acc, double *d_z, double *d_znod, double *d_grad, double alpha, int *newton_its) {
+    if (!c || !d_f || !d_x0 || !d_ud || K <= 0 || !d_w || !d_g || !d_vel || !d_x || !d_u || !d_mask || !d_parked ||
+        !d_acc || !d_z)
+        return OCP_ERR_INVALID;
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.d_f = d_f; a.d_x0 = d_x0; a.d_ud = d_ud; a.K = K; a.d_w = d_w; a.d_g = d_g; a.d_vel = d_vel; a.d_x = d_x;
+    a.d_u = d_u; a.d_mask = d_mask; a.d_parked = d_parked; a.d_acc = d_acc; a.d_z = d_z; a.d_znod = d_znod;
+    a.d_grad = d_grad; a.alpha = alpha;
+    return gradient_step(c, a, newton_its);
+}
+
 int ocp_gradient_host(ocp_ctx *c, const double *h_f, double *h_w, double *h_z, double *h_mask, double *h_scalars) {
     if (!c || !h_f || !h_w || !h_z || !h_mask || !h_scalars) return OCP_ERR_INVALID;
     if (c->obs_K <= 0) {
@@ -1204,18 +1379,12 @@ int ocp_gradient_host(ocp_ctx *c, const double *h_f, double *h_w, double *h_z, d
     double *d_x = c->d_stage[2], *d_u = c->d_stage[3];
     double *d_mask = c->d_stage[6], *d_vel = c->d_stage[7];
     CUDA_OK(c, cudaMemcpyAsync(d_f, h_f, sizeof(double) * 2 * c->nn, cudaMemcpyHostToDevice, s));
-    CUDA_OK(c, cudaMemsetAsync(d_mask, 0, sizeof(double) * K, s));
-    CUDA_OK(c, cudaMemsetAsync(d_acc, 0, sizeof(double) * nacc, s));
     int its = 0;
-    if ((rc = ocp_forward_solve(c, d_f, d_w, 1, &its, nullptr))) return rc;
-    if ((rc = ocp_project_grad(c, d_w, d_g))) return rc;
-    launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, d_w, d_vel, s);
-    run_buoy_forward(c, d_vel, c->d_obs_x0, K, d_x, d_u, nullptr, d_mask, c->d_parked);
-    if ((rc = ocp_buoy_adjoint_scatter(c, d_vel, d_g, K, d_x, d_u, c->d_obs_ud, d_mask, c->d_parked, nullptr, d_acc)))
-        return rc;
-    // buoys sharded over ranks: the sum over buoys (OCP_dolfin.py:353-366) is completed across GPUs here
-    if (!c->comm.allreduce_sum(d_acc, nacc, s, c->err)) return OCP_ERR_COMM;
-    if ((rc = ocp_adjoint_solve(c, d_w, d_acc, d_z))) return rc;
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.d_f = d_f; a.d_x0 = c->d_obs_x0; a.d_ud = c->d_obs_ud; a.K = K; a.d_w = d_w; a.d_g = d_g; a.d_vel = d_vel;
+    a.d_x = d_x; a.d_u = d_u; a.d_mask = d_mask; a.d_parked = c->d_parked; a.d_acc = d_acc; a.d_z = d_z;
+    if ((rc = gradient_step(c, a, &its))) return rc;
     launch_boundary_inner(c->n_g1, c->d_g1_nodes, c->d_g1_len, d_f, d_f, c->d_scalar, s);
     CUDA_OK(c, cudaMemcpyAsync(h_w, d_w, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     CUDA_OK(c, cudaMemcpyAsync(h_z, d_z, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
@@ -1288,6 +1457,14 @@ int ocp_selftest_fp64_peak(ocp_ctx *c, double *tflops) {
     *tflops = best;
     CUDA_OK(c, cudaGetLastError());
     return OCP_OK;
+}
+
+int ocp_newton_history(const ocp_ctx *c, double *h_hist, int max_entries) {
+    if (!c || !h_hist || max_entries <= 0) return 0;
+    const int *st = reinterpret_cast<const int *>(c->h_nhist + 64);
+    const int n = std::min(max_entries, std::min(64, (st[0] ? st[1] : 0) + 1));
+    for (int k = 0; k < n; ++k) h_hist[k] = c->h_nhist[k];
+    return n;
 }
 
 long long ocp_launch_count(void) { return ocp::g_launch_count.load(); }

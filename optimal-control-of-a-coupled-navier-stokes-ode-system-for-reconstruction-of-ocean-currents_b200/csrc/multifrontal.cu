@@ -1494,6 +1494,7 @@ struct MultifrontalLU::Impl {
     std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs, solve_t_graphs, solve4_graphs;
     cudaStream_t cap_stream = nullptr;
     bool use_graphs = true;
+    bool direct = false;         // enqueue directly (an outer graph is being captured)
     int *h_info = nullptr;       // pinned: zero-pivot flag of the most recent factorisations (checked lazily)
     MFDev dev{};
     ~Impl() {
@@ -1511,7 +1512,7 @@ struct MultifrontalLU::Impl {
     bool enqueue_solve(double *d_x, int variant, cudaStream_t s, std::string &err);
     template <class Fn>
     bool run(std::map<const void *, cudaGraphExec_t> &cache, const void *key, cudaStream_t s, std::string &err, Fn enqueue) {
-        if (!use_graphs || prof) return enqueue(s);
+        if (!use_graphs || prof || direct) return enqueue(s);
         auto it = cache.find(key);
         if (it == cache.end()) {
             cudaGraph_t g = nullptr;
@@ -1542,6 +1543,10 @@ struct MultifrontalLU::Impl {
 };
 
 MultifrontalLU::MultifrontalLU() = default;
+void MultifrontalLU::set_direct_enqueue(bool on) {
+    if (impl_) impl_->direct = on;
+}
+bool MultifrontalLU::needs_cooperative_launch() const { return impl_ && !impl_->big_launches.empty(); }
 MultifrontalLU::~MultifrontalLU() { delete impl_; }
 
 bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h_col, const double *xy,

@@ -27,6 +27,10 @@ class MultifrontalLU {
     // four right-hand sides at once: vector r occupies d_x[r * n .. r * n + n)
     bool solve4(double *d_x, cudaStream_t s, std::string &err);
     bool check(std::string &err);   // zero-pivot flag of completed factorisations (non-blocking)
+    // while set, factor / solve enqueue their kernels directly on the given stream instead of launching their own
+    // CUDA graphs: the caller is capturing a larger graph around them
+    void set_direct_enqueue(bool on);
+    bool needs_cooperative_launch() const;   // large fronts present (group kernels): not captured into outer graphs
     long long factor_nnz() const { return factor_nnz_; }
     double flops() const { return flops_; }
     int levels() const { return nlevels_; }

@@ -393,3 +393,41 @@ def test_atomic_free_assembly_matches_oracle_and_is_bit_reproducible(mesh, monke
     assert H.rel(a["Jbc"], O.on_pattern(O.forward_jacobian(w))) < 1e-12
     assert H.rel(a["A"], O.on_pattern(O.adjoint_matrix(w))) < 1e-12
     assert H.rel(a["RJ"], O.forward_residual(w, f)) < 1e-12
+
+
+def test_step_graph_replay_equals_the_plain_path_and_falls_back():
+    """ocp_gradient_device replays one CUDA graph per gradient evaluation once warm.  The replay must give what the plain
+    (launch by launch, host-decided) path gives, for a changing control too; when the expected Newton count does not
+    hold (a much larger control needs more iterates) the evaluation is re-run on the plain path with the same result
+    as a context that never used graphs."""
+    V = H.square32()
+    xr, ud = H.traj(100)
+    x0 = xr[:, 0, :].copy()
+    f = initial_control(V, "PL")
+    controls = [f, 1.05 * f, 0.9 * f, 40.0 * f, f]          # 40 f: convection dominated, more Newton iterates
+    out = {}
+    for graph in (True, False):
+        os.environ["OCP_STEP_GRAPH"] = "1" if graph else "0"
+        try:
+            ocp = OCP(V, Parameters(), x0, ud, device=dev())
+        finally:
+            del os.environ["OCP_STEP_GRAPH"]
+        rows = []
+        for fc in controls:
+            ocp.set_control(fc)
+            ocp.gradient_step(ocp.d_f)
+            rows.append((ocp.last_newton_its, list(ocp.last_res_hist), ocp.d_w.cpu().numpy(), ocp.d_z.cpu().numpy(),
+                         ocp.d_acc.cpu().numpy(), ocp.d_grad.cpu().numpy()))
+        out[graph] = (rows, ocp.ctx.option("step_graph_replays"), ocp.ctx.option("step_plain_runs"))
+        ocp.close()
+    (rg, n_replay, n_plain_g), (rp, n_replay_p, n_plain_p) = out[True], out[False]
+    assert n_replay_p == 0 and n_plain_p == len(controls)
+    assert n_replay >= 2 and n_plain_g >= 2                      # first call + the fall-back(s) ran plain
+    its = [r[0] for r in rp]
+    assert its[3] > its[0] and its[4] == its[0]
+    nn2 = 2 * V.num_nodes
+    for a, b in zip(rg, rp):
+        assert a[0] == b[0]                                       # Newton counts
+        assert np.allclose(a[1][:-1], b[1][:-1], rtol=1e-6) and len(a[1]) == len(b[1])
+        assert H.rel(a[2], b[2]) < 1e-12 and H.rel(a[3], b[3]) < 1e-9
+        assert H.rel(a[4][:nn2], b[4][:nn2]) < 1e-11 and H.rel(a[5], b[5]) < 1e-9
