@@ -179,7 +179,9 @@ __device__ __forceinline__ void diag16_factor(double (&r)[NB], int lane, int kb,
 }
 
 // U11^-1 of a factored 16 x 16 block (D: L below / U on and above the diagonal, rd: reciprocals of the diagonal), one
-// column per lane by back substitution; the lanes only read D (broadcast loads), no shuffles.  With it the rows below
+// column per lane by back substitution; the lanes only read D (broadcast loads), no shuffles.  Formed by the first
+// worker warp at the start of a panel (on the look-ahead warp it lengthened the critical path: factorisation 0.87 ->
+// 0.90 ms).  With it the rows below
 // the block become a PRODUCT, L21 = A21 U11^-1: 16 independent dot products per row instead of a 16-step recurrence
 // (tools/microbench/lrows.cu: 4.2 k -> 1.8 k cycles per panel for 256 rows on one CTA).
 __device__ __forceinline__ void upper_inverse16(const double (*D)[NB + 1], const double *rd, int lane, double (*Ui)[NB + 1]) {
@@ -220,7 +222,7 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
     __shared__ double s_rd[2][NB];                // reciprocals of its diagonal
     __shared__ __align__(16) double s_prow[2][NB];   // pivot row of the current / next elimination step
     __shared__ double s_T[NB][NB + 1];            // U12' of the look-ahead corner
-    __shared__ double s_Ui[2][NB][NB + 1];        // U11^-1 of the current / next diagonal block
+    __shared__ double s_Ui[2][NB][NB + 1];        // U11^-1 of the current diagonal block (alternating buffers)
     cg::cluster_group cl = cg::this_cluster();
     const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     const int ldu = (max_m + CWO + 3) & ~3;       // leading dimension of the U12 staging area (multiple of 4)
@@ -259,8 +261,6 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
 #pragma unroll
             for (int jj = 0; jj < NB; ++jj) s_D[0][lane][jj] = r[jj];
         }
-        __syncwarp();
-        upper_inverse16(s_D[0], s_rd[0], lane, s_Ui[0]);
     }
     __syncthreads();
     MF_TICK(acc_diag);
@@ -299,19 +299,16 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
 #pragma unroll
                     for (int t = 0; t < NB; ++t) s_T[t][lane] = u[t];
                 }
-                // L21' = A21 U11^{-1} (phase c arithmetic: product with the explicit inverse)
-                {
-                    double l21[NB];
+                // L21' = A21 U11^{-1} by the 16-step recurrence: the look-ahead warp starts before the workers have formed
+                // U11^-1, and its 16 rows are cheap.  (The workers use the product form below, so the next diagonal block
+                // and the rows beneath it differ by a rounding-level perturbation - backward stable like the LU itself.)
 #pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        double acc = 0.0;
+                for (int t = 0; t < NB; ++t) {
+                    const double l = a21[t] * rd[t];
+                    a21[t] = l;
 #pragma unroll
-                        for (int t = 0; t < NB; ++t)
-                            if (t <= jj) acc = fma(a21[t], Ui[t][jj], acc);
-                        l21[jj] = acc;
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) a21[jj] = l21[jj];
+                    for (int jj = 0; jj < NB; ++jj)
+                        if (jj > t) a21[jj] = fma(-l, D[t][jj], a21[jj]);
                 }
                 __syncwarp();
                 // A22 - L21' U12' (phase e arithmetic: accumulate over t, subtract once)
@@ -335,8 +332,6 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) s_D[cur ^ 1][lane][jj] = r[jj];
                 }
-                __syncwarp();
-                upper_inverse16(s_D[cur ^ 1], s_rd[cur ^ 1], lane, s_Ui[cur ^ 1]);
             }
             cluster_wait();
         } else {
@@ -353,7 +348,11 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
             // arrive with release semantics AFTER the panel loads: CTA 0's store of the L panel into these very entries
             // comes after its wait (acquire) below, hence after every worker's loads above
             cluster_arrive();
-            if (prof) { worker_sync<TW>(); MF_TICK(acc_load); }
+            // U11^-1 of this panel, by the first worker warp while the panel loads are in flight; the barrier behind it
+            // costs the other warps nothing they would not spend waiting for their loads
+            if (tid < 32) upper_inverse16(D, rd, lane, s_Ui[cur]);
+            worker_sync<TW>();
+            if (prof) { MF_TICK(acc_load); }
             // (d) U12 = L11^{-1} F12 for the own trailing columns.  Runs on the highest worker ids, whose panel rows
             // (phase c) mostly do not exist (m < TW), so this serial 16-step substitution overlaps phase (c).
             for (int idx = TW - 1 - tid; idx < nown * CWO; idx += TW) {
