@@ -178,32 +178,12 @@ __device__ __forceinline__ void diag16_factor(double (&r)[NB], int lane, int kb,
     }
 }
 
-// U11^-1 of a factored 16 x 16 block (D: L below / U on and above the diagonal, rd: reciprocals of the diagonal), one
-// column per lane by back substitution; the lanes only read D (broadcast loads), no shuffles.  Formed by the first
-// worker warp at the start of a panel (on the look-ahead warp it lengthened the critical path: factorisation 0.87 ->
-// 0.90 ms).  With it the rows below
-// the block become a PRODUCT, L21 = A21 U11^-1: 16 independent dot products per row instead of a 16-step recurrence
-// (tools/microbench/lrows.cu: 4.2 k -> 1.8 k cycles per panel for 256 rows on one CTA).
-__device__ __forceinline__ void upper_inverse16(const double (*D)[NB + 1], const double *rd, int lane, double (*Ui)[NB + 1]) {
-    if (lane < NB) {
-        double x[NB];
-#pragma unroll
-        for (int i = 0; i < NB; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = NB - 1; k >= 0; --k) {
-            if (k <= lane) {
-                const double xk = x[k] * rd[k];
-                x[k] = xk;
-#pragma unroll
-                for (int i = 0; i < NB; ++i)
-                    if (i < k) x[i] = fma(-D[i][k], xk, x[i]);
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < NB; ++t) Ui[t][lane] = (t <= lane) ? x[t] : 0.0;
-    }
-}
-
+// Measured and NOT kept (round 2, tools/microbench/lrows.cu, OCP_MF_PROF): the rows below the block as a product with an
+// explicit U11^-1 instead of the 16-step recurrence.  In isolation 4.2 k -> 1.8 k cycles per panel (256 rows, one
+// CTA); in the kernel the row phase of the root front dropped from 6.8 k to 4.2 k cycles per panel, but forming the
+// inverse costs 3.2 k cycles of one warp per panel: on the look-ahead warp it lengthened that (co-critical) path
+// (factorisation 0.867 -> 0.899 ms), on the first worker warp behind the panel loads it was not hidden either
+// (0.914 ms).  The recurrence stays.
 // TF threads = TF - 32 workers + one LOOK-AHEAD warp.  While the workers run panel k (rows below the block, U12, trailing
 // update), the look-ahead warp of every CTA produces the factored diagonal block of panel k+1 on its own: it reads the
 // 32 x 32 corner [A11 A12; A21 A22] of the trailing matrix right after the cluster barrier, forms U12' = L11^{-1} A12,
@@ -222,7 +202,6 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
     __shared__ double s_rd[2][NB];                // reciprocals of its diagonal
     __shared__ __align__(16) double s_prow[2][NB];   // pivot row of the current / next elimination step
     __shared__ double s_T[NB][NB + 1];            // U12' of the look-ahead corner
-    __shared__ double s_Ui[2][NB][NB + 1];        // U11^-1 of the current diagonal block (alternating buffers)
     cg::cluster_group cl = cg::this_cluster();
     const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     const int ldu = (max_m + CWO + 3) & ~3;       // leading dimension of the U12 staging area (multiple of 4)
@@ -270,7 +249,6 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
         const int kb = min(NB, np - k0), mp = m - k0, ctrail = k0 + kb;
         const int ldp = (mp + 3) & ~3;          // panel leading dimension, multiple of 4 so that tiles load as 2 x 16 B
         const double (*D)[NB + 1] = s_D[cur];
-        const double (*Ui)[NB + 1] = s_Ui[cur];
         const double *rd = s_rd[cur];
         if (!worker) {
             // ================= look-ahead warp: diagonal block of the NEXT panel =================
@@ -299,9 +277,7 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
 #pragma unroll
                     for (int t = 0; t < NB; ++t) s_T[t][lane] = u[t];
                 }
-                // L21' = A21 U11^{-1} by the 16-step recurrence: the look-ahead warp starts before the workers have formed
-                // U11^-1, and its 16 rows are cheap.  (The workers use the product form below, so the next diagonal block
-                // and the rows beneath it differ by a rounding-level perturbation - backward stable like the LU itself.)
+                // L21' = A21 U11^{-1} (phase c arithmetic)
 #pragma unroll
                 for (int t = 0; t < NB; ++t) {
                     const double l = a21[t] * rd[t];
@@ -348,11 +324,7 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
             // arrive with release semantics AFTER the panel loads: CTA 0's store of the L panel into these very entries
             // comes after its wait (acquire) below, hence after every worker's loads above
             cluster_arrive();
-            // U11^-1 of this panel, by the first worker warp while the panel loads are in flight; the barrier behind it
-            // costs the other warps nothing they would not spend waiting for their loads
-            if (tid < 32) upper_inverse16(D, rd, lane, s_Ui[cur]);
-            worker_sync<TW>();
-            if (prof) { MF_TICK(acc_load); }
+            if (prof) { worker_sync<TW>(); MF_TICK(acc_load); }
             // (d) U12 = L11^{-1} F12 for the own trailing columns.  Runs on the highest worker ids, whose panel rows
             // (phase c) mostly do not exist (m < TW), so this serial 16-step substitution overlaps phase (c).
             for (int idx = TW - 1 - tid; idx < nown * CWO; idx += TW) {
@@ -381,18 +353,16 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
                 const int i = tid + q * TW;
                 if (i < mp) {
                     if (i >= kb) {
-                        // product with U11^-1 (identity-padded beyond kb): 16 independent dot products
-                        double l[NB];
 #pragma unroll
-                        for (int jj = 0; jj < NB; ++jj) {
-                            double acc = 0.0;
+                        for (int t = 0; t < NB; ++t) {
+                            if (t < kb) {
+                                const double l = a[q][t] * rd[t];
+                                a[q][t] = l;
 #pragma unroll
-                            for (int t = 0; t < NB; ++t)
-                                if (t <= jj) acc = fma(a[q][t], Ui[t][jj], acc);
-                            l[jj] = acc;
+                                for (int jj = 0; jj < NB; ++jj)
+                                    if (jj > t && jj < kb) a[q][jj] = fma(-l, D[t][jj], a[q][jj]);
+                            }
                         }
-#pragma unroll
-                        for (int jj = 0; jj < NB; ++jj) a[q][jj] = l[jj];
                     } else {
 #pragma unroll
                         for (int jj = 0; jj < NB; ++jj) a[q][jj] = D[i][jj];     // the factored block itself
