@@ -115,7 +115,8 @@ struct ocp_ctx {
     // One CUDA graph per gradient evaluation (ocp_gradient_device): the launches of a whole "outer" block are captured
     // once per (buffers, expected Newton count) and replayed; the two host decisions of the block - Newton converged
     // within the expected count, adjoint residual gate - are verified AFTER the replay from values the graph copied to
-    // pinned memory, and the plain path re-runs the evaluation if either fails.  OCP_STEP_GRAPH=0 disables.
+    // pinned memory, and the plain path re-runs the evaluation if either fails (sharded runs agree on that through one
+    // extra 8-byte all-reduce).  OCP_STEP_GRAPH=0 disables.
     struct StepGraph {
         std::vector<unsigned char> key;
         int pred = 0;
@@ -1253,8 +1254,7 @@ static int gradient_step(ocp_ctx *c, const StepArgs &a, int *its_out) {
     int its = 0;
     const bool eligible = c->step_graph && !c->profile && c->newton_speculate && c->newton_pred >= 1 && c->warm_K == a.K &&
                           c->stokes_valid && c->adj_reuse && c->nu == 1.0 && c->lu_fwd.capturable() &&
-                          c->lu_stokes.capturable() && c->lu_mass.capturable() &&
-                          c->comm.size() == 1;   // (sharded runs: a rank-local fall-back would issue an unmatched collective)
+                          c->lu_stokes.capturable() && c->lu_mass.capturable();
     if (eligible) {
         std::vector<unsigned char> key(sizeof(StepArgs));
         memcpy(key.data(), &a, sizeof(StepArgs));
@@ -1321,7 +1321,18 @@ static int gradient_step(ocp_ctx *c, const StepArgs &a, int *its_out) {
             const bool newton_ok = st[0] == 1 && st[2] == 0 && st[1] <= entry->pred;
             const bool adjoint_ok = r0 == r0 && r0 <= 1e-24 * b0;
             const bool pivots_ok = c->lu_fwd.check(e2) && c->lu_stokes.check(e2);
-            if (newton_ok && adjoint_ok && pivots_ok) {
+            bool all_ok = newton_ok && adjoint_ok && pivots_ok;
+            if (c->comm.size() > 1) {
+                // sharded: the ranks must take the fall-back together (the plain path holds a collective), so the verdict
+                // is summed over the ranks - one 8-byte all-reduce
+                c->h_pinned[6] = all_ok ? 0.0 : 1.0;
+                CUDA_OK(c, cudaMemcpyAsync(c->d_scalar + 4, c->h_pinned + 6, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+                if (!c->comm.allreduce_sum(c->d_scalar + 4, 1, c->stream, c->err)) return OCP_ERR_COMM;
+                CUDA_OK(c, cudaMemcpyAsync(c->h_pinned + 7, c->d_scalar + 4, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                CUDA_OK(c, cudaStreamSynchronize(c->stream));
+                all_ok = c->h_pinned[7] == 0.0;
+            }
+            if (all_ok) {
                 its = st[1];
                 c->newton_pred = its;
                 c->last_newton_lu = its >= 2 || entry->pred >= 2 ? &c->lu_fwd : &c->lu_stokes;

@@ -78,7 +78,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // by the blocked triangular solves.  One launch after the numeric factorisation, one warp per (block, factor): the
 // inversions are shuffle-heavy and used to sit on the critical path of every panel.
 __global__ void __launch_bounds__(256)
-mf_dinv_kernel(MFDev d, const int *__restrict__ panel_node, int npanels) {
+mf_dinv_kernel(MFDev d, const int *__restrict__ panel_node, int npanels, int *info) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int p = w >> 1, which = w & 1;                 // which = 1: L11^{-1}, 0: U11^{-1}
     if (p >= npanels) return;
@@ -89,6 +89,18 @@ mf_dinv_kernel(MFDev d, const int *__restrict__ panel_node, int npanels) {
     double r[NB];                                        // row `lane` of the factored block
 #pragma unroll
     for (int c = 0; c < NB; ++c) r[c] = (lane < kb && c < kb) ? __ldcg(F + (k0 + lane) + (size_t)(k0 + c) * m) : 0.0;
+    // Growth check of the static pivoting, off the critical path of the factorisation: a pivot that is tiny against the
+    // rest of its row of U11 (relative 1e-11) marks the factorisation as unreliable - reported like a zero pivot
+    // (OCP_ERR_SOLVER) instead of relying on the residual checks downstream.
+    if (!which && lane < kb) {
+        double rowmax = 0.0, piv = 0.0;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            if (c == lane) piv = fabs(r[c]);
+            if (c >= lane && c < kb) rowmax = fmax(rowmax, fabs(r[c]));
+        }
+        if (!(piv > 1e-11 * rowmax)) atomicExch(info, s + 1);
+    }
     double X[NB];
 #pragma unroll
     for (int c = 0; c < NB; ++c) X[c] = (c == lane) ? 1.0 : 0.0;
@@ -1834,7 +1846,7 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
             }
         }
     }
-    if (npanels > 0) mf_dinv_kernel<<<(2 * npanels * 32 + 255) / 256, 256, 0, s>>>(dev, panel_node, npanels);
+    if (npanels > 0) mf_dinv_kernel<<<(2 * npanels * 32 + 255) / 256, 256, 0, s>>>(dev, panel_node, npanels, info);
     if (solve64 && nblocks64 > 0) mf_dinv64_kernel<<<2 * nblocks64, SB, 0, s>>>(dev, block_node, nblocks64);
     cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, s);
     return true;
@@ -1887,7 +1899,7 @@ bool MultifrontalLU::factor(const double *d_vals, cudaStream_t s, std::string &e
 // it has synchronised the stream).
 bool MultifrontalLU::check(std::string &err) {
     if (impl_ && impl_->h_info && *impl_->h_info != 0) {
-        err = "multifrontal factor: zero pivot in front " + std::to_string(*impl_->h_info - 1) +
+        err = "multifrontal factor: zero or tiny pivot in front " + std::to_string(*impl_->h_info - 1) +
               " (static pivoting broke down; run with OCP_SOLVER=rf)";
         *impl_->h_info = 0;
         cudaMemsetAsync(impl_->info, 0, sizeof(int), nullptr);
