@@ -752,6 +752,13 @@ mf_backward_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__ 
 //   (b) y_i  -= E(i, blk) y_blk   one thread per remaining row, its 64 factor entries requested up front - before
 //                                 (a) - so that their L2 latency overlaps the pivot-block product.
 constexpr int SB = 64;
+// Programmatic dependent launch between the level kernels of one sweep (OCP_MF_PDL, default on): a level kernel lets
+// the next level's grid start at once (launch_dependents) and the next level does everything that only touches the
+// READ-ONLY data of a solve - front metadata, index list, inverse blocks, its first factor entries - before it waits
+// (griddepcontrol.wait) for the previous level's right-hand-side updates.  Both instructions are no-ops in a launch
+// without the attribute.  Every exit path waits, so a level never completes before its predecessor has.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 constexpr int TS6 = 384;     // threads of the 64-row-block solve kernels: 168 registers each keep the 64 entries of a row resident
 
 // One CTA of 64 threads per (64-pivot block, L or U): thread c forms column c of the inverse by substitution with the
@@ -829,9 +836,13 @@ mf_forward64_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__
     extern __shared__ double y[];          // NR vectors of length m
     __shared__ double yb[NR][SB];
     __shared__ double part[4][NR][SB];
+    pdl_launch_dependents();
     const int s = nodes[blockIdx.x];
     const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
-    if (np == 0) return;
+    if (np == 0) {
+        pdl_wait();
+        return;
+    }
     const double *F = d.F + d.front_ptr[s];
     const int *I = d.idx + d.idx_ptr[s];
     // plain: L11^-1; transposed: (U11^-1)^T
@@ -839,15 +850,29 @@ mf_forward64_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__
     const int nblk = (np + SB - 1) / SB;
     for (int off = tid * 16; off < nblk * 2 * SB * SB; off += TS6 * 16)
         asm volatile("prefetch.global.L1 [%0];" ::"l"(d.dinv64 + (size_t)d.dinv64_ptr[s] * (2 * SB * SB) + off));
+    // read-only prologue (ahead of the previous level's completion under PDL): the thread's entries of the index list
+    // and the factor entries of its first remaining row
+    const int ik0 = tid < m ? I[tid] : 0, ik1 = tid + TS6 < m ? I[tid + TS6] : 0;
+    double e[SB];
+    {
+        const int kb = min(SB, np), i0 = kb + tid;
+        if (i0 < m) {
+#pragma unroll
+            for (int t = 0; t < SB; ++t) e[t] = (t < kb) ? MF_E(i0, t) : 0.0;
+        }
+    }
+    pdl_wait();
     for (int r = 0; r < NR; ++r)
-        for (int k = tid; k < m; k += TS6) y[r * m + k] = k < np ? x[(size_t)r * ldx + I[k]] : 0.0;
+        for (int k = tid, j = 0; k < m; k += TS6, ++j) {
+            const int ii = j == 0 ? ik0 : (j == 1 ? ik1 : I[k]);
+            y[r * m + k] = k < np ? __ldcg(x + (size_t)r * ldx + ii) : 0.0;
+        }
     __syncthreads();
     for (int b = 0; b < nblk; ++b) {
         const int k0 = b * SB, kb = min(SB, np - k0);
         // factor entries of this thread's first remaining row: requested before the pivot-block product
         const int i0 = k0 + kb + tid;
-        double e[SB];
-        if (i0 < m) {
+        if (b > 0 && i0 < m) {
 #pragma unroll
             for (int t = 0; t < SB; ++t) e[t] = (t < kb) ? MF_E(i0, k0 + t) : 0.0;
         }
@@ -880,10 +905,12 @@ mf_forward64_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict__
         }
         __syncthreads();
     }
-    for (int r = 0; r < NR; ++r) {
-        for (int k = tid; k < np; k += TS6) x[(size_t)r * ldx + I[k]] = y[r * m + k];
-        for (int i = np + tid; i < m; i += TS6) atomicAdd(x + (size_t)r * ldx + I[i], y[r * m + i]);
-    }
+    for (int r = 0; r < NR; ++r)
+        for (int k = tid, j = 0; k < m; k += TS6, ++j) {
+            const int ii = j == 0 ? ik0 : (j == 1 ? ik1 : I[k]);
+            if (k < np) x[(size_t)r * ldx + ii] = y[r * m + k];
+            else atomicAdd(x + (size_t)r * ldx + ii, y[r * m + k]);
+        }
 }
 
 // backward: x_P = U11^-1 (y_P - U12 x_U);   TR: x_P = L11^-T (y_P - L21^T x_U)
@@ -893,9 +920,13 @@ mf_backward64_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict_
     extern __shared__ double y[];          // NR x m, then (plain) the per-warp partial sums of the U12 mat-vec
     __shared__ double yb[NR][SB];
     __shared__ double part4[4][NR][SB];
+    pdl_launch_dependents();
     const int s = nodes[blockIdx.x];
     const int m = d.m[s], np = d.np[s], tid = threadIdx.x;
-    if (np == 0) return;
+    if (np == 0) {
+        pdl_wait();
+        return;
+    }
     const double *F = d.F + d.front_ptr[s];
     const int *I = d.idx + d.idx_ptr[s];
     // plain: U11^-1; transposed: (L11^-1)^T
@@ -903,8 +934,31 @@ mf_backward64_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict_
     const int nblk = (np + SB - 1) / SB;
     for (int off = tid * 16; off < nblk * 2 * SB * SB; off += TS6 * 16)
         asm volatile("prefetch.global.L1 [%0];" ::"l"(d.dinv64 + (size_t)d.dinv64_ptr[s] * (2 * SB * SB) + off));
+    // read-only prologue (ahead of the previous level's completion under PDL): the off-diagonal panel of the first
+    // mat-vec into L1 when it is small (plain: columns np.. = U12 and below; transposed: columns ..np = L21 and above),
+    // the thread's entries of the index list and the factor entries of its first row above the last pivot block
+    if ((size_t)(m - np) * m <= 12288 && !TR) {
+        for (size_t off = (size_t)tid * 16; off < (size_t)(m - np) * m; off += (size_t)TS6 * 16)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(F + (size_t)np * m + off));
+    } else if ((size_t)np * m <= 12288 && TR && m > np) {
+        for (size_t off = (size_t)tid * 16; off < (size_t)np * m; off += (size_t)TS6 * 16)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(F + off));
+    }
+    const int ik0 = tid < m ? I[tid] : 0, ik1 = tid + TS6 < m ? I[tid + TS6] : 0;
+    double e[SB];
+    {
+        const int k0 = (nblk - 1) * SB, kb = min(SB, np - k0);
+        if (tid < k0) {
+#pragma unroll
+            for (int t = 0; t < SB; ++t) e[t] = (t < kb) ? MF_E(tid, k0 + t) : 0.0;
+        }
+    }
+    pdl_wait();
     for (int r = 0; r < NR; ++r)
-        for (int k = tid; k < m; k += TS6) y[r * m + k] = x[(size_t)r * ldx + I[k]];
+        for (int k = tid, j = 0; k < m; k += TS6, ++j) {
+            const int ii = j == 0 ? ik0 : (j == 1 ? ik1 : I[k]);
+            y[r * m + k] = __ldcg(x + (size_t)r * ldx + ii);
+        }
     __syncthreads();
     // y_P -= U12 x_U (TR: L21^T x_U), shared by all 16 warps (see mf_backward_kernel)
     {
@@ -957,8 +1011,7 @@ mf_backward64_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict_
     for (int b = nblk - 1; b >= 0; --b) {
         const int k0 = b * SB, kb = min(SB, np - k0);
         // rows above the block: entries of this thread's first row, requested before the pivot-block product
-        double e[SB];
-        if (tid < k0) {
+        if (b < nblk - 1 && tid < k0) {
 #pragma unroll
             for (int t = 0; t < SB; ++t) e[t] = (t < kb) ? MF_E(tid, k0 + t) : 0.0;
         }
@@ -992,7 +1045,7 @@ mf_backward64_kernel(MFDev d, const int *__restrict__ nodes, double *__restrict_
         __syncthreads();
     }
     for (int r = 0; r < NR; ++r)
-        for (int k = tid; k < np; k += TS6) x[(size_t)r * ldx + I[k]] = y[r * m + k];
+        for (int k = tid, j = 0; k < np; k += TS6, ++j) x[(size_t)r * ldx + (j == 0 ? ik0 : (j == 1 ? ik1 : I[k]))] = y[r * m + k];
 }
 
 
@@ -1507,6 +1560,7 @@ struct MultifrontalLU::Impl {
     int *dinv64_ptr = nullptr, *block_node = nullptr;
     int nblocks64 = 0;
     bool solve64 = true;         // 64-row-block solve kernels for the small fronts (OCP_MF_SOLVE16=1: the 16-row ones)
+    bool pdl = true;             // programmatic dependent launches between the levels of a sweep (OCP_MF_PDL=0: plain)
     int4 *cta_map = nullptr;     // per CTA of every large-front launch: (front of the launch, rank in its group, group size)
     // CUDA graphs of the factor / solve launch sequences, keyed by the (fixed) device pointer they operate on
     std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs, solve_t_graphs, solve4_graphs;
@@ -1765,6 +1819,7 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
     {
         // 64-pivot blocks of the SMALL fronts (the large fronts keep the 16-row solve kernels)
         if (const char *e16 = getenv("OCP_MF_SOLVE16")) I.solve64 = atoi(e16) == 0;
+        if (const char *ep = getenv("OCP_MF_PDL")) I.pdl = atoi(ep) != 0;
         std::vector<int> dp(S.nnodes + 1, 0);
         for (int k = 0; k < S.nnodes; ++k) dp[k + 1] = dp[k] + (S.m[k] > big_limit ? 0 : (S.np[k] + SB - 1) / SB);
         std::vector<int> bn(dp[S.nnodes]);
@@ -1908,11 +1963,30 @@ bool MultifrontalLU::check(std::string &err) {
     return true;
 }
 
+// A level of the 64-row-block solve kernels; pdl: the previous launch on the stream is such a level of the same sweep,
+// so this one may start early (programmatic stream serialisation) and overlap its read-only prologue with it.
+template <class K>
+static void launch_solve64(K kernel, int nf, size_t smem, cudaStream_t s, bool pdl, const MFDev &dev, const int *nodes,
+                           double *d_x, int ldx) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nf);
+    cfg.blockDim = dim3(TS6);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, dev, nodes, d_x, ldx);
+}
+
 template <bool TR, int NR>
-static void launch_level_fwd(const MFDev &dev, const int *nodes, int nf, int max_m, double *d_x, int ldx, cudaStream_t s) {
+static void launch_level_fwd(const MFDev &dev, const int *nodes, int nf, int max_m, double *d_x, int ldx, cudaStream_t s,
+                             bool pdl = false) {
     if (nf <= 0) return;
     if (dev.dinv64) {
-        mf_forward64_kernel<TR, NR><<<nf, TS6, sizeof(double) * max_m * NR, s>>>(dev, nodes, d_x, ldx);
+        launch_solve64(mf_forward64_kernel<TR, NR>, nf, sizeof(double) * max_m * NR, s, pdl, dev, nodes, d_x, ldx);
         return;
     }
     if (max_m <= TS)
@@ -1923,13 +1997,13 @@ static void launch_level_fwd(const MFDev &dev, const int *nodes, int nf, int max
 
 template <bool TR, int NR>
 static void launch_level_bwd(const MFDev &dev, const int *nodes, int nf, int max_m, int max_np, double *d_x, int ldx,
-                             cudaStream_t s) {
+                             cudaStream_t s, bool pdl = false) {
     if (nf <= 0) return;
     // y (NR x m) plus, for the plain sweep, the per-warp partial sums of the U12 mat-vec (16 x NR x np)
     const size_t smem = sizeof(double) * NR * ((size_t)max_m + (TR ? 0 : (size_t)(TS / 32) * max_np));
     if (dev.dinv64) {
         const size_t smem6 = sizeof(double) * NR * ((size_t)max_m + (TR ? 0 : (size_t)(TS6 / 32) * max_np));
-        mf_backward64_kernel<TR, NR><<<nf, TS6, smem6, s>>>(dev, nodes, d_x, ldx);
+        launch_solve64(mf_backward64_kernel<TR, NR>, nf, smem6, s, pdl, dev, nodes, d_x, ldx);
         return;
     }
     if (max_m <= TS)
@@ -1965,17 +2039,27 @@ static void launch_big_bwd(const MFDev &dev, const int *nodes, int nf, int max_m
 bool MultifrontalLU::Impl::enqueue_solve(double *d_x, int variant, cudaStream_t s, std::string &err) {
     const MFSymbolic &S = this->S;
     const int ldx = S.n;
+    // chain: the previous launch on the stream was a 64-row-block level of THIS pass (factors and inverses are read-only
+    // from there on), so the next such level may be a programmatic dependent launch
+    bool chain = false;
+    auto link = [&](int nf, int nbg) {
+        const bool p = pdl && chain && dev.dinv64 && nf > 0;
+        if (nf > 0) chain = dev.dinv64 != nullptr;
+        if (nbg > 0) chain = false;
+        return p;
+    };
     for (int l = 0; l < S.nlevels; ++l) {
         const int nf = level_nsmall[l], nbg = level_nbig[l];
         const int *nodes = level_nodes + level_off[l], *big = nodes + nf;
+        const bool p = link(nf, nbg);
         if (variant == 1) {
-            launch_level_fwd<true, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+            launch_level_fwd<true, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s, p);
             launch_big_fwd<true>(dev, big, nbg, level_big_max_m[l], 1, d_x, ldx, s);
         } else if (variant == 2) {
-            launch_level_fwd<false, 4>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+            launch_level_fwd<false, 4>(dev, nodes, nf, level_max_m[l], d_x, ldx, s, p);
             launch_big_fwd<false>(dev, big, nbg, level_big_max_m[l], 4, d_x, ldx, s);
         } else {
-            launch_level_fwd<false, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s);
+            launch_level_fwd<false, 1>(dev, nodes, nf, level_max_m[l], d_x, ldx, s, p);
             launch_big_fwd<false>(dev, big, nbg, level_big_max_m[l], 1, d_x, ldx, s);
         }
     }
@@ -1983,18 +2067,21 @@ bool MultifrontalLU::Impl::enqueue_solve(double *d_x, int variant, cudaStream_t 
         const int nf = level_nsmall[l], nbg = level_nbig[l];
         const int *nodes = level_nodes + level_off[l], *big = nodes + nf;
         if (variant == 1) {
-            launch_level_bwd<true, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
+            launch_level_bwd<true, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s, link(nf, nbg));
             launch_big_bwd<true>(dev, big, nbg, level_big_max_m[l], 1, d_x, ldx, s);
         } else if (variant == 2) {
             // four right-hand sides at once unless their shared-memory footprint (y + per-warp partial sums) is too large
             if (sizeof(double) * 4 * ((size_t)level_max_m[l] + (size_t)(TS / 32) * level_max_np[l]) <= 200 * 1024)
-                launch_level_bwd<false, 4>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
-            else
+                launch_level_bwd<false, 4>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s, link(nf, nbg));
+            else {
                 for (int r = 0; r < 4; ++r)
-                    launch_level_bwd<false, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x + (size_t)r * ldx, ldx, s);
+                    launch_level_bwd<false, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x + (size_t)r * ldx, ldx, s,
+                                               link(nf, 0));
+                link(0, nbg);
+            }
             launch_big_bwd<false>(dev, big, nbg, level_big_max_m[l], 4, d_x, ldx, s);
         } else {
-            launch_level_bwd<false, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s);
+            launch_level_bwd<false, 1>(dev, nodes, nf, level_max_m[l], level_max_np[l], d_x, ldx, s, link(nf, nbg));
             launch_big_bwd<false>(dev, big, nbg, level_big_max_m[l], 1, d_x, ldx, s);
         }
     }
