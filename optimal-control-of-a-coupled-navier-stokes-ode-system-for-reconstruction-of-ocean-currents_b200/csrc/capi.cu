@@ -127,6 +127,12 @@ struct ocp_ctx {
     };
     std::vector<StepGraph> step_graphs;
     bool step_graph = true, capturing = false, step_graph_sharded = false;
+    // The adjoint operator only depends on the state, not on the buoys: inside a gradient evaluation it is assembled on
+    // a side stream (a parallel branch of the step graph) while the projection and the two buoy sweeps run
+    // (OCP_STEP_OVERLAP=0: one after the other).
+    bool step_overlap = true;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
     cudaStream_t cap_stream = nullptr;
     int warm_K = -1;              // a plain evaluation with this buoy count has run (work arrays sized, operators built)
     int n_step_graph = 0, n_step_plain = 0;
@@ -664,6 +670,7 @@ int ocp_create(const ocp_problem_desc *d, void *stream, ocp_ctx **out) {
     if (const char *ed = getenv("OCP_NEWTON_SPECULATE")) c->newton_speculate = atoi(ed) != 0;
     if (const char *ed = getenv("OCP_STEP_GRAPH")) c->step_graph = atoi(ed) != 0;
     if (const char *ed = getenv("OCP_STEP_GRAPH_SHARDED")) c->step_graph_sharded = atoi(ed) != 0;
+    if (const char *ed = getenv("OCP_STEP_OVERLAP")) c->step_overlap = atoi(ed) != 0;
     // staged (shared-memory / TMA) buoy kernels are opt-in: measured slower than the global-table kernels on B200
     if (const char *es = getenv("OCP_BUOY_STAGED"))
         c->buoy_staged = atoi(es) != 0 && buoy_tables_fit_shared(d->nc, d->nn, d->nv);
@@ -833,6 +840,9 @@ void ocp_destroy(ocp_ctx *c) {
     cudaFree(c->d_nhist);
     cudaFree(c->d_nstate);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_side) cudaEventDestroy(c->ev_side);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -1021,13 +1031,20 @@ int ocp_misfit(ocp_ctx *c, int K, const double *d_u, const double *d_ud, double 
     return OCP_OK;
 }
 
+// assembled: the adjoint operator (with its BC rows) already sits in c->d_vals (gradient evaluation: side stream)
+static int adjoint_solve_impl(ocp_ctx *c, const double *d_w, const double *d_bnode, double *d_z, bool assembled);
+
 int ocp_adjoint_solve(ocp_ctx *c, const double *d_w, const double *d_bnode, double *d_z) {
+    return adjoint_solve_impl(c, d_w, d_bnode, d_z, false);
+}
+
+static int adjoint_solve_impl(ocp_ctx *c, const double *d_w, const double *d_bnode, double *d_z, bool assembled) {
     if (!c || !d_w || !d_bnode || !d_z) return OCP_ERR_INVALID;
     cudaStream_t s = c->stream;
     const int n = c->ndofs;
     {
         PhaseTimer t(c, &c->stats.assemble_ms);
-        int rc = assemble_adjoint(c, d_w, c->d_vals, true);
+        int rc = assembled ? OCP_OK : assemble_adjoint(c, d_w, c->d_vals, true);
         if (rc != OCP_OK) return rc;
         launch_rhs_from_nodal(c->nn, c->nv, c->d_dof_ux, c->d_dof_uy, c->d_dof_p, d_bnode, c->d_rhs, s);
         launch_dirichlet(c->n_dir, c->d_dir, c->d_rowptr, c->d_col, nullptr, c->d_rhs, nullptr, nullptr, s);   // b[d] = 0
@@ -1239,14 +1256,45 @@ static int enqueue_gradient_step(ocp_ctx *c, const StepArgs &a, int *its) {
     CUDA_OK(c, cudaMemsetAsync(a.d_mask, 0, sizeof(double) * a.K, s));
     CUDA_OK(c, cudaMemsetAsync(a.d_acc, 0, sizeof(double) * nacc, s));
     if ((rc = ocp_forward_solve(c, a.d_f, a.d_w, 1, its, nullptr))) return rc;
-    if ((rc = ocp_project_grad(c, a.d_w, a.d_g))) return rc;
+    // fork: adjoint operator at the converged state on the side stream
+    bool forked = false;
+    if (c->step_overlap && !c->profile) {
+        if (!c->side && cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) c->side = nullptr;
+        if (c->side && !c->ev_fork && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) c->ev_fork = nullptr;
+        if (c->side && !c->ev_side && cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) != cudaSuccess) c->ev_side = nullptr;
+        if (c->side && c->ev_fork && c->ev_side) {
+            CUDA_OK(c, cudaEventRecord(c->ev_fork, s));
+            CUDA_OK(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+            c->stream = c->side;
+            rc = assemble_adjoint(c, a.d_w, c->d_vals, true);
+            c->stream = s;
+            cudaEventRecord(c->ev_side, c->side);
+            forked = true;
+            if (rc) {
+                cudaStreamWaitEvent(s, c->ev_side, 0);
+                return rc;
+            }
+        } else {
+            cudaGetLastError();
+            c->step_overlap = false;
+        }
+    }
+    auto join = [&]() {
+        if (forked) cudaStreamWaitEvent(s, c->ev_side, 0);
+        forked = false;
+    };
+    if ((rc = ocp_project_grad(c, a.d_w, a.d_g))) { join(); return rc; }
     launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, a.d_w, a.d_vel, s);
     run_buoy_forward(c, a.d_vel, a.d_x0, a.K, a.d_x, a.d_u, nullptr, a.d_mask, a.d_parked);
-    if ((rc = run_buoy_backward(c, a.d_vel, a.d_g, a.K, a.d_x, a.d_u, a.d_ud, a.d_mask, a.d_parked, nullptr, a.d_acc, true)))
+    if ((rc = run_buoy_backward(c, a.d_vel, a.d_g, a.K, a.d_x, a.d_u, a.d_ud, a.d_mask, a.d_parked, nullptr, a.d_acc, true))) {
+        join();
         return rc;
+    }
     // buoys sharded over ranks: the sum over buoys (OCP_dolfin.py:353-366) is completed across GPUs here
-    if (!c->comm.allreduce_sum(a.d_acc, nacc, s, c->err)) return OCP_ERR_COMM;
-    if ((rc = ocp_adjoint_solve(c, a.d_w, a.d_acc, a.d_z))) return rc;
+    if (!c->comm.allreduce_sum(a.d_acc, nacc, s, c->err)) { join(); return OCP_ERR_COMM; }
+    const bool assembled = forked;
+    join();
+    if ((rc = adjoint_solve_impl(c, a.d_w, a.d_acc, a.d_z, assembled))) return rc;
     if (a.d_znod && a.d_grad) {       // grad j = alpha f - z on the nodes (OCP_dolfin.py:379)
         launch_velocity_nodal(c->nn, c->d_dof_ux, c->d_dof_uy, a.d_z, a.d_znod, s);
         launch_axpby(2 * c->nn, a.alpha, a.d_f, -1.0, a.d_znod, a.d_grad, s);

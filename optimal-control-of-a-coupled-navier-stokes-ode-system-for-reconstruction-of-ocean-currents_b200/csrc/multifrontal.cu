@@ -41,6 +41,7 @@ struct MFDev {
     const int *dinv_ptr;       // per front: index of its first panel in dinv
     double *dinv64;            // per 64-pivot block of a SMALL front: [L11^-1 | U11^-1], each 64 x 64 row-major
     const int *dinv64_ptr;     // per front: index of its first 64-pivot block in dinv64 (small fronts only)
+    int ea_atomic;             // small fronts: extend-add with fp64 atomics (OCP_MF_EA_ATOMIC=1) instead of child-by-child
 };
 
 __global__ void scatter_values_kernel(int nnz, const long long *__restrict__ dest, const double *__restrict__ vals,
@@ -224,16 +225,49 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
     const bool worker = tid < TW;
     const int lane = tid & 31;
     double *F = d.F + d.front_ptr[s];
-    // ---- extend-add the children's update matrices (atomic: two children may hit the same entry)
+    // ---- extend-add the children's update matrices.  Two children may hit the same entry of the front, one child never
+    // hits an entry twice (its index map is injective): the children go one at a time with a cluster barrier in between,
+    // so every entry has a single writer and plain read-modify-writes do - eight independent ones in flight per thread,
+    // the (column, row) pairs of the CTA's columns flattened over its threads.  fp64 atomics (d.ea_atomic, the round-1
+    // form) top out near 50 G/s on this chip and cost the levels 1-4 of the 32 x 32 tree 15-40 us each; the plain
+    // form also fixes the summation order (A + child 1 + child 2): the factors are bit-reproducible.
     for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
         const int c = d.child[ci], mc = d.m[c], npc = d.np[c], nu = mc - npc;
         const double *Fc = d.F + d.front_ptr[c];
         const int *rel = d.rel + d.rel_ptr[c];
-        for (int j = rank; j < nu; j += C) {
-            const double *src = Fc + npc + (size_t)(npc + j) * mc;
-            double *dst = F + (size_t)__ldg(rel + j) * m;
-            for (int i = tid; i < nu; i += TF) atomicAdd(dst + __ldg(rel + i), __ldcg(src + i));
+        if (d.ea_atomic) {
+            for (int j = rank; j < nu; j += C) {
+                const double *src = Fc + npc + (size_t)(npc + j) * mc;
+                double *dst = F + (size_t)__ldg(rel + j) * m;
+                for (int i = tid; i < nu; i += TF) atomicAdd(dst + __ldg(rel + i), __ldcg(src + i));
+            }
+            continue;
         }
+        const int ncol = nu > rank ? (nu - rank + C - 1) / C : 0;     // columns rank, rank + C, ... of the update matrix
+        const int total = ncol * nu;
+        constexpr int EU = 8;
+        for (int e0 = tid; e0 < total; e0 += EU * TF) {
+            double *p[EU];
+            double v[EU];
+#pragma unroll
+            for (int u = 0; u < EU; ++u) {
+                const int e = e0 + u * TF;
+                p[u] = nullptr;
+                v[u] = 0.0;
+                if (e < total) {
+                    const int q = e / nu, i = e - q * nu, j = rank + q * C;
+                    p[u] = F + (size_t)__ldg(rel + j) * m + __ldg(rel + i);
+                    v[u] = __ldcg(Fc + npc + i + (size_t)(npc + j) * mc);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < EU; ++u)
+                if (p[u]) v[u] += __ldcg(p[u]);
+#pragma unroll
+            for (int u = 0; u < EU; ++u)
+                if (p[u]) __stcg(p[u], v[u]);
+        }
+        if (ci + 1 < d.child_ptr[s + 1]) cl.sync();     // the next child may hit entries another CTA has just written
     }
     cl.sync();
     if (np == 0) return;
@@ -765,10 +799,10 @@ constexpr int TS6 = 384;     // threads of the 64-row-block solve kernels: 168 r
 // block in shared memory and all of its 64 unknowns in registers (outer-product form: the 64 dependent steps each
 // update independent registers).  Rows / columns beyond a partial last block are identity padding.
 __global__ void __launch_bounds__(SB)
-mf_dinv64_kernel(MFDev d, const int *__restrict__ block_node, int nblocks) {
+mf_dinv64_kernel(MFDev d, const int *__restrict__ block_node, int first, int nblocks) {
     __shared__ double B[SB][SB + 1];
-    const int p = blockIdx.x >> 1, which = blockIdx.x & 1;      // which = 0: L11^-1, 1: U11^-1
-    if (p >= nblocks) return;
+    const int p = first + (blockIdx.x >> 1), which = blockIdx.x & 1;      // which = 0: L11^-1, 1: U11^-1
+    if (p >= first + nblocks) return;
     const int s = block_node[p];
     const int m = d.m[s], np = d.np[s];
     const int k0 = (p - d.dinv64_ptr[s]) * SB, kb = min(SB, np - k0);
@@ -1561,6 +1595,38 @@ struct MultifrontalLU::Impl {
     int nblocks64 = 0;
     bool solve64 = true;         // 64-row-block solve kernels for the small fronts (OCP_MF_SOLVE16=1: the 16-row ones)
     bool pdl = true;             // programmatic dependent launches between the levels of a sweep (OCP_MF_PDL=0: plain)
+    // diagonal-block inverses of a level formed on a side stream while the next levels are factored (OCP_MF_OVERLAP=1).
+    // Measured on B200 and NOT the default: the side kernels take SM time from the level kernels, 2 factorisations
+    // 1.73 -> 1.88 ms per GD iteration; the default forms all inverses in one launch behind the factorisation.
+    bool overlap_dinv = false;
+    std::vector<int> level_blk_off;
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> ev_level;
+    cudaEvent_t ev_join = nullptr;
+    bool ensure_side(int nlevels) {
+        if (side && (int)ev_level.size() >= nlevels) return true;
+        if (!side && cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            side = nullptr;
+            overlap_dinv = false;
+            return false;
+        }
+        if (!ev_join && cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            overlap_dinv = false;
+            return false;
+        }
+        while ((int)ev_level.size() < nlevels) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                overlap_dinv = false;
+                return false;
+            }
+            ev_level.push_back(e);
+        }
+        return true;
+    }
     int4 *cta_map = nullptr;     // per CTA of every large-front launch: (front of the launch, rank in its group, group size)
     // CUDA graphs of the factor / solve launch sequences, keyed by the (fixed) device pointer they operate on
     std::map<const void *, cudaGraphExec_t> factor_graphs, solve_graphs, solve_t_graphs, solve4_graphs;
@@ -1578,6 +1644,9 @@ struct MultifrontalLU::Impl {
         for (auto &kv : solve_t_graphs) cudaGraphExecDestroy(kv.second);
         for (auto &kv : solve4_graphs) cudaGraphExecDestroy(kv.second);
         if (cap_stream) cudaStreamDestroy(cap_stream);
+        for (cudaEvent_t e : ev_level) cudaEventDestroy(e);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side) cudaStreamDestroy(side);
         if (h_info) cudaFreeHost(h_info);
     }
     bool enqueue_factor(const double *d_vals, int nnz, cudaStream_t s, std::string &err);
@@ -1820,12 +1889,22 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
         // 64-pivot blocks of the SMALL fronts (the large fronts keep the 16-row solve kernels)
         if (const char *e16 = getenv("OCP_MF_SOLVE16")) I.solve64 = atoi(e16) == 0;
         if (const char *ep = getenv("OCP_MF_PDL")) I.pdl = atoi(ep) != 0;
-        std::vector<int> dp(S.nnodes + 1, 0);
-        for (int k = 0; k < S.nnodes; ++k) dp[k + 1] = dp[k] + (S.m[k] > big_limit ? 0 : (S.np[k] + SB - 1) / SB);
-        std::vector<int> bn(dp[S.nnodes]);
-        for (int k = 0; k < S.nnodes; ++k)
-            for (int q = dp[k]; q < dp[k + 1]; ++q) bn[q] = k;
-        I.nblocks64 = dp[S.nnodes];
+        if (const char *eo = getenv("OCP_MF_OVERLAP")) I.overlap_dinv = atoi(eo) != 0;
+        // blocks are numbered level by level (the order of the launch lists), so that the inverses of a level's blocks
+        // can be formed on the side stream while the next level is being factored (enqueue_factor)
+        std::vector<int> dp(S.nnodes + 1, 0), bn;
+        I.level_blk_off.assign(S.nlevels + 1, 0);
+        for (int l = 0; l < S.nlevels; ++l) {
+            I.level_blk_off[l] = (int)bn.size();
+            for (int k = S.level_ptr[l]; k < S.level_ptr[l + 1]; ++k) {
+                const int nd = ordered[k];
+                dp[nd] = (int)bn.size();
+                const int nb = S.m[nd] > big_limit ? 0 : (S.np[nd] + SB - 1) / SB;
+                for (int q = 0; q < nb; ++q) bn.push_back(nd);
+            }
+        }
+        I.level_blk_off[S.nlevels] = dp[S.nnodes] = (int)bn.size();
+        I.nblocks64 = (int)bn.size();
         if (!up(&I.dinv64_ptr, dp, err) || !up(&I.block_node, bn, err)) return false;
         if (I.solve64 &&
             cudaMalloc((void **)&I.dinv64, sizeof(double) * 2 * SB * SB * std::max(I.nblocks64, 1)) != cudaSuccess) {
@@ -1834,7 +1913,8 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
         }
     }
     I.dev = MFDev{I.m, I.np, I.first, I.idx_ptr, I.idx, I.child_ptr, I.child, I.rel_ptr, I.rel, I.front_ptr, I.F, I.piv,
-                  I.dinv, I.dinv_ptr, I.dinv64, I.dinv64_ptr};
+                  I.dinv, I.dinv_ptr, I.dinv64, I.dinv64_ptr, 0};
+    if (const char *ea = getenv("OCP_MF_EA_ATOMIC")) I.dev.ea_atomic = atoi(ea) != 0;
     factor_nnz_ = 0;
     for (int s = 0; s < S.nnodes; ++s)
         factor_nnz_ += (long long)S.m[s] * S.m[s] - (long long)(S.m[s] - S.np[s]) * (S.m[s] - S.np[s]);
@@ -1849,6 +1929,7 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
 
 bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStream_t s, std::string &err) {
     const MFSymbolic &S = this->S;
+    const bool side_on = overlap_dinv && !prof && ensure_side(S.nlevels);
     cudaMemsetAsync(F, 0, sizeof(double) * S.fsize, s);
     scatter_values_kernel<<<(nnz + 255) / 256, 256, 0, s>>>(nnz, a_dest, d_vals, F);
     for (int l = 0; l < S.nlevels; ++l) {
@@ -1900,9 +1981,22 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
                 return false;
             }
         }
+        if (side_on) {
+            // the level's factors are final: their 64 x 64 diagonal inverses go to the side stream (a parallel branch of
+            // the captured graph) and run on the SMs the next levels leave idle
+            cudaEventRecord(ev_level[l], s);
+            cudaStreamWaitEvent(side, ev_level[l], 0);
+            const int b0 = level_blk_off[l], nb = level_blk_off[l + 1] - b0;
+            if (solve64 && nb > 0) mf_dinv64_kernel<<<2 * nb, SB, 0, side>>>(dev, block_node, b0, nb);
+        }
     }
-    if (npanels > 0) mf_dinv_kernel<<<(2 * npanels * 32 + 255) / 256, 256, 0, s>>>(dev, panel_node, npanels, info);
-    if (solve64 && nblocks64 > 0) mf_dinv64_kernel<<<2 * nblocks64, SB, 0, s>>>(dev, block_node, nblocks64);
+    if (npanels > 0) mf_dinv_kernel<<<(2 * npanels * 32 + 255) / 256, 256, 0, side_on ? side : s>>>(dev, panel_node, npanels, info);
+    if (side_on) {
+        cudaEventRecord(ev_join, side);
+        cudaStreamWaitEvent(s, ev_join, 0);
+    } else if (solve64 && nblocks64 > 0) {
+        mf_dinv64_kernel<<<2 * nblocks64, SB, 0, s>>>(dev, block_node, 0, nblocks64);
+    }
     cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, s);
     return true;
 }
