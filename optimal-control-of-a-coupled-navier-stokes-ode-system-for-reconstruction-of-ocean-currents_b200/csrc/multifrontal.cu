@@ -502,6 +502,242 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small fronts whose pivot part fits ONE CTA's shared memory (the bottom levels of the tree: 224 of the 255 fronts of
+// the 32 x 32 mesh).  mf_factor_kernel walks such a front panel by panel through L2: per 16-column panel a load, a
+// 4 x 4-tile pass over the WHOLE trailing matrix (16 L2 loads + 16 stores per 256 FMAs) and barriers - the leaves ran
+// at ~10 % of an SM's fp64 rate.  Here the first np columns (Lp, m x np) and the first np rows (Up, np x (m - np))
+// of the front live in shared memory, the right-looking LU only updates that L-shaped region, and the Schur
+// complement - the bulk of the flops - is formed at the end in ONE pass, S -= L21 U12 with K = np (16 loads + 16 stores
+// per 16 np FMAs, loads issued ahead of the K loop).  Static pivoting and the 16 x 16 diagonal-block routine are those
+// of mf_factor_kernel; the summation order differs (one subtraction of the accumulated product), so the factors agree
+// to rounding, not bitwise.  Children (levels above the leaves) are extend-added first, one child at a time.
+constexpr int TL = 256;
+constexpr size_t kLeafSmemMax = 224 * 1024;   // dynamic shared memory the kernel may ask for (+ 2.5 KB static)
+__host__ __device__ inline int leaf_ld(int rows) { return (rows + 3) & ~3; }
+__host__ __device__ inline size_t leaf_smem_doubles(int m, int np) {
+    return (size_t)leaf_ld(m) * np + (size_t)leaf_ld(m - np) * np + (size_t)NB * leaf_ld(m);
+}
+
+__global__ void __launch_bounds__(TL, 1)
+mf_leaf_factor_kernel(MFDev d, const int *__restrict__ nodes, int *info) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double s_D[NB][NB + 1];            // factored diagonal block: L below, U on / above the diagonal
+    __shared__ double s_rd[NB];                   // reciprocals of its diagonal
+    __shared__ __align__(16) double s_prow[2][NB];
+    const int s = nodes[blockIdx.x];
+    const int m = d.m[s], np = d.np[s], tid = threadIdx.x, lane = tid & 31;
+    double *F = d.F + d.front_ptr[s];
+    // ---- extend-add, one child at a time (single writer per entry, see mf_factor_kernel)
+    for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
+        const int c = d.child[ci], mc = d.m[c], npc = d.np[c], nuc = mc - npc;
+        const double *Fc = d.F + d.front_ptr[c];
+        const int *rel = d.rel + d.rel_ptr[c];
+        const int total = nuc * nuc;
+        constexpr int EU = 8;
+        for (int e0 = tid; e0 < total; e0 += EU * TL) {
+            double *p[EU];
+            double v[EU];
+#pragma unroll
+            for (int u = 0; u < EU; ++u) {
+                const int e = e0 + u * TL;
+                p[u] = nullptr;
+                v[u] = 0.0;
+                if (e < total) {
+                    const int j = e / nuc, i = e - j * nuc;
+                    p[u] = F + (size_t)__ldg(rel + j) * m + __ldg(rel + i);
+                    v[u] = __ldcg(Fc + npc + i + (size_t)(npc + j) * mc);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < EU; ++u)
+                if (p[u]) v[u] += __ldcg(p[u]);
+#pragma unroll
+            for (int u = 0; u < EU; ++u)
+                if (p[u]) __stcg(p[u], v[u]);
+        }
+        __syncthreads();
+    }
+    if (np == 0) return;
+    const int nu = m - np;
+    const int ldL = leaf_ld(m), ldU = leaf_ld(nu), ldS = leaf_ld(m);
+    double *Lp = sm;                              // columns 0 .. np-1:            Lp[i + c * ldL]
+    double *Up = Lp + (size_t)ldL * np;           // rows 0 .. np-1 of columns np..: Up[t * ldU + (c - np)]
+    double *Us = Up + (size_t)ldU * np;           // U rows of the current panel:   Us[t * ldS + (c - k1)]
+    for (int e = tid; e < m * np; e += TL) {
+        const int c = e / m, i = e - c * m;
+        Lp[i + c * ldL] = __ldcg(F + i + (size_t)c * m);
+    }
+    for (int e = tid; e < np * nu; e += TL) {
+        const int c = e / np, t = e - c * np;
+        Up[t * ldU + c] = __ldcg(F + t + (size_t)(np + c) * m);
+    }
+    __syncthreads();
+    for (int k0 = 0; k0 < np; k0 += NB) {
+        const int kb = min(NB, np - k0), k1 = k0 + kb;
+        // (1) diagonal block, one warp
+        if (tid < 32) {
+            double r[NB];
+#pragma unroll
+            for (int jj = 0; jj < NB; ++jj)
+                r[jj] = (lane < kb && jj < kb) ? Lp[(k0 + lane) + (k0 + jj) * ldL] : ((jj == lane) ? 1.0 : 0.0);
+            diag16_factor(r, lane, kb, s_prow, s_rd, info, s);
+            if (lane < NB) {
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) s_D[lane][jj] = r[jj];
+            }
+            if (lane < kb) {
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj)
+                    if (jj < kb) Lp[(k0 + lane) + (k0 + jj) * ldL] = r[jj];
+            }
+        }
+        __syncthreads();
+        // (2) rows below the block: L = A U11^-1; columns right of it: U = L11^-1 A (one row / column per thread)
+        const int nrest = m - k1;
+        for (int task = tid; task < 2 * nrest; task += TL) {
+            if (task < nrest) {
+                const int i = k1 + task;
+                double a[NB];
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) a[jj] = jj < kb ? Lp[i + (k0 + jj) * ldL] : 0.0;
+#pragma unroll
+                for (int t = 0; t < NB; ++t) {
+                    if (t < kb) {
+                        const double l = a[t] * s_rd[t];
+                        a[t] = l;
+#pragma unroll
+                        for (int jj = 0; jj < NB; ++jj)
+                            if (jj > t && jj < kb) a[jj] = fma(-l, s_D[t][jj], a[jj]);
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj)
+                    if (jj < kb) Lp[i + (k0 + jj) * ldL] = a[jj];
+            } else {
+                const int c = k1 + (task - nrest);
+                double *col = c < np ? Lp + k0 + (size_t)c * ldL : Up + (size_t)k0 * ldU + (c - np);
+                const int st = c < np ? 1 : ldU;
+                double u[NB];
+#pragma unroll
+                for (int t = 0; t < NB; ++t) u[t] = t < kb ? col[t * st] : 0.0;
+#pragma unroll
+                for (int t = 0; t < NB; ++t) {
+                    if (t < kb) {
+#pragma unroll
+                        for (int tt = 0; tt < NB; ++tt)
+                            if (tt > t && tt < kb) u[tt] = fma(-s_D[tt][t], u[t], u[tt]);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < NB; ++t) {
+                    if (t < kb) {
+                        col[t * st] = u[t];
+                        Us[t * ldS + (c - k1)] = u[t];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // (3) rank-16 update of the L-shaped region only: rows [k1, m) x columns [k1, np) (in Lp) and rows [k1, np) x
+        // columns [np, m) (in Up); 4 x 4 tiles, a tile that straddles column / row np is predicated per element
+        if (k1 < np) {
+            const int tr = (m - k1 + 3) >> 2, tcA = (np - k1 + 3) >> 2, trB = tcA;
+            const int ntA = tr * tcA, ntB = trB * (tr - tcA);
+            for (int tile = tid; tile < ntA + ntB; tile += TL) {
+                int ti, tj;
+                if (tile < ntA) {
+                    ti = tile % tr;
+                    tj = tile / tr;
+                } else {
+                    const int q = tile - ntA;
+                    ti = q % trB;
+                    tj = tcA + q / trB;
+                }
+                const int i0 = k1 + 4 * ti, c0 = k1 + 4 * tj;
+                double acc[4][4];
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[aa][b] = 0.0;
+                for (int t = 0; t < NB; ++t) {
+                    const double2 la = *reinterpret_cast<const double2 *>(Lp + i0 + (k0 + t) * ldL);
+                    const double2 lb = *reinterpret_cast<const double2 *>(Lp + i0 + (k0 + t) * ldL + 2);
+                    const double2 ua = *reinterpret_cast<const double2 *>(Us + t * ldS + (c0 - k1));
+                    const double2 ub = *reinterpret_cast<const double2 *>(Us + t * ldS + (c0 - k1) + 2);
+                    const double l[4] = {la.x, la.y, lb.x, lb.y}, uu[4] = {ua.x, ua.y, ub.x, ub.y};
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[aa][b] = fma(l[aa], uu[b], acc[aa][b]);
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int c = c0 + b;
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) {
+                        const int i = i0 + aa;
+                        if (i < m && c < m && !(i >= np && c >= np)) {
+                            double *e = c < np ? Lp + i + (size_t)c * ldL : Up + (size_t)i * ldU + (c - np);
+                            *e -= acc[aa][b];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // (4) Schur complement in one pass: F[i, c] -= sum_t L[i, t] U[t, c], i, c >= np (tile rows aligned to 4)
+    {
+        const int rb = np & ~3;
+        const int trS = (m - rb + 3) >> 2, tcS = (nu + 3) >> 2;
+        for (int tile = tid; tile < trS * tcS; tile += TL) {
+            const int ti = tile % trS, tj = tile / trS;
+            const int i0 = rb + 4 * ti, cc0 = 4 * tj;
+            double f[4][4], acc[4][4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const double *colp = F + (size_t)(np + cc0 + b) * m;
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) {
+                    const int i = i0 + aa;
+                    f[aa][b] = (i >= np && i < m && cc0 + b < nu) ? __ldcg(colp + i) : 0.0;
+                    acc[aa][b] = 0.0;
+                }
+            }
+            for (int t = 0; t < np; ++t) {
+                const double2 la = *reinterpret_cast<const double2 *>(Lp + i0 + t * ldL);
+                const double2 lb = *reinterpret_cast<const double2 *>(Lp + i0 + t * ldL + 2);
+                const double2 ua = *reinterpret_cast<const double2 *>(Up + t * ldU + cc0);
+                const double2 ub = *reinterpret_cast<const double2 *>(Up + t * ldU + cc0 + 2);
+                const double l[4] = {la.x, la.y, lb.x, lb.y}, uu[4] = {ua.x, ua.y, ub.x, ub.y};
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[aa][b] = fma(l[aa], uu[b], acc[aa][b]);
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                double *colp = F + (size_t)(np + cc0 + b) * m;
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) {
+                    const int i = i0 + aa;
+                    if (i >= np && i < m && cc0 + b < nu) __stcg(colp + i, f[aa][b] - acc[aa][b]);
+                }
+            }
+        }
+    }
+    // (5) factors back to the front
+    for (int e = tid; e < m * np; e += TL) {
+        const int c = e / m, i = e - c * m;
+        __stcg(F + i + (size_t)c * m, Lp[i + c * ldL]);
+    }
+    for (int e = tid; e < np * nu; e += TL) {
+        const int c = e / np, t = e - c * np;
+        __stcg(F + t + (size_t)(np + c) * m, Up[t * ldU + c]);
+    }
+}
+
 // Triangular solves, one CTA per front and one launch per level.  Inside a front the pivot block is processed in
 // 16-row blocks: the block itself is a 16x16 mat-vec with the inverse stored by the factorisation (warp 0), the rows
 // outside the block are updated by all threads with the 16 block values; the matrix entries of the NEXT block are
@@ -1595,6 +1831,9 @@ struct MultifrontalLU::Impl {
     int nblocks64 = 0;
     bool solve64 = true;         // 64-row-block solve kernels for the small fronts (OCP_MF_SOLVE16=1: the 16-row ones)
     bool pdl = true;             // programmatic dependent launches between the levels of a sweep (OCP_MF_PDL=0: plain)
+    // bottom levels of the tree whose fronts take the shared-memory-resident single-CTA kernel (mf_leaf_factor_kernel)
+    std::vector<char> level_leaf;
+    std::vector<size_t> level_leaf_smem;
     // diagonal-block inverses of a level formed on a side stream while the next levels are factored (OCP_MF_OVERLAP=1).
     // Measured on B200 and NOT the default: the side kernels take SM time from the level kernels, 2 factorisations
     // 1.73 -> 1.88 ms per GD iteration; the default forms all inverses in one launch behind the factorisation.
@@ -1737,6 +1976,25 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
                 }
             }
     }
+    {
+        // OCP_MF_LEAF_LEVELS: how many bottom levels may take the shared-memory-resident kernel [1]; a level qualifies
+        // when it has no large front and every front's pivot columns / rows fit one CTA's shared memory
+        int leaf_levels = 1;
+        if (const char *el = getenv("OCP_MF_LEAF_LEVELS")) leaf_levels = std::max(0, atoi(el));
+        I.level_leaf.assign(S.nlevels, 0);
+        I.level_leaf_smem.assign(S.nlevels, 0);
+        for (int l = 0; l < S.nlevels && l < leaf_levels; ++l) {
+            if (I.level_nbig[l] > 0 || I.level_nsmall[l] == 0) break;
+            size_t need = 0;
+            for (int k = 0; k < I.level_nsmall[l]; ++k) {
+                const int nd = ordered[I.level_off[l] + k];
+                need = std::max(need, leaf_smem_doubles(S.m[nd], S.np[nd]) * sizeof(double));
+            }
+            if (need > kLeafSmemMax) break;
+            I.level_leaf[l] = 1;
+            I.level_leaf_smem[l] = need;
+        }
+    }
     if (S.max_front > 24000) {   // right-hand side of a large front must fit the solve kernels' shared memory
         err = "multifrontal: largest front (" + std::to_string(S.max_front) + ") exceeds the solve kernels' shared memory";
         return false;
@@ -1762,6 +2020,7 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
         e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(factor_kernel(v), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_leaf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLeafSmemMax);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_big_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_forward_big_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mf_forward_big_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1934,7 +2193,9 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
     scatter_values_kernel<<<(nnz + 255) / 256, 256, 0, s>>>(nnz, a_dest, d_vals, F);
     for (int l = 0; l < S.nlevels; ++l) {
         const int nf = level_nsmall[l];
-        if (nf > 0) {
+        if (nf > 0 && level_leaf[l] && !prof) {
+            mf_leaf_factor_kernel<<<nf, TL, level_leaf_smem[l], s>>>(dev, level_nodes + level_off[l], info);
+        } else if (nf > 0) {
             const int c = level_cluster[l];
             cudaLaunchConfig_t cfg = {};
             const int var = factor_variant(level_max_m[l]);
