@@ -503,8 +503,8 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Small fronts whose pivot part fits ONE CTA's shared memory (the bottom levels of the tree: 224 of the 255 fronts of
-// the 32 x 32 mesh).  mf_factor_kernel walks such a front panel by panel through L2: per 16-column panel a load, a
+// Small fronts whose pivot part fits ONE CTA's shared memory (the leaves of the tree: 128 of the 255 fronts of the
+// 32 x 32 mesh).  mf_factor_kernel walks such a front panel by panel through L2: per 16-column panel a load, a
 // 4 x 4-tile pass over the WHOLE trailing matrix (16 L2 loads + 16 stores per 256 FMAs) and barriers - the leaves ran
 // at ~10 % of an SM's fp64 rate.  Here the first np columns (Lp, m x np) and the first np rows (Up, np x (m - np))
 // of the front live in shared memory, the right-looking LU only updates that L-shaped region, and the Schur
@@ -512,21 +512,48 @@ mf_factor_kernel(MFDev d, const int *__restrict__ nodes, int max_m, int *info, l
 // per 16 np FMAs, loads issued ahead of the K loop).  Static pivoting and the 16 x 16 diagonal-block routine are those
 // of mf_factor_kernel; the summation order differs (one subtraction of the accumulated product), so the factors agree
 // to rounding, not bitwise.  Children (levels above the leaves) are extend-added first, one child at a time.
-constexpr int TL = 256;
-constexpr size_t kLeafSmemMax = 224 * 1024;   // dynamic shared memory the kernel may ask for (+ 2.5 KB static)
+//
+// TL threads = TLW workers + one LOOK-AHEAD warp (ncu of the first version, profiles/prof_r2_leaf_v1.summary.txt: 40 % of
+// all warp samples waited at the barriers behind the serial 16-step elimination of the diagonal block and behind a
+// second, nearly empty round of the row / column substitutions).  Per panel:
+//   phase 2  workers: rows below the block L = A U11^-1 and columns right of it U = L11^-1 A, one per thread, ONE round
+//            (<= 2 (m - 16) tasks <= TLW); the rows of D come as 16-byte loads from aligned copies (s_Dr, s_Dc)
+//   phase 3  workers: rank-16 update of the L-shaped region, 4 x 4 tiles, EXCEPT the next diagonal block;
+//            look-ahead warp: updates that block (same formula), factors it (diag16_factor) and publishes it
+// The first diagonal block is factored by the look-ahead warp straight from global memory while the workers load.
+constexpr int TL = 384, TLW = TL - 32;
+constexpr size_t kLeafSmemMax = 220 * 1024;   // dynamic shared memory the kernel may ask for (+ 6.6 KB static)
 __host__ __device__ inline int leaf_ld(int rows) { return (rows + 3) & ~3; }
 __host__ __device__ inline size_t leaf_smem_doubles(int m, int np) {
     return (size_t)leaf_ld(m) * np + (size_t)leaf_ld(m - np) * np + (size_t)NB * leaf_ld(m);
+}
+
+// look-ahead warp: factor the block held one row per lane, publish D (padded + aligned row / column copies) and 1/diag
+__device__ __forceinline__ void leaf_publish_block(double (&r)[NB], int lane, int kb, double (*s_D)[NB + 1],
+                                                   double (*s_Dr)[NB], double (*s_Dc)[NB], double (*s_prow)[NB],
+                                                   double *s_rd, int *info, int front) {
+    diag16_factor(r, lane, kb, s_prow, s_rd, info, front);
+    if (lane < NB) {
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj) {
+            s_D[lane][jj] = r[jj];
+            s_Dr[lane][jj] = r[jj];            // row `lane` of the block (U on / above the diagonal)
+            s_Dc[jj][lane] = r[jj];            // s_Dc[t][tt] = D[tt][t]: column t of the block (L below the diagonal)
+        }
+    }
 }
 
 __global__ void __launch_bounds__(TL, 1)
 mf_leaf_factor_kernel(MFDev d, const int *__restrict__ nodes, int *info) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double s_D[NB][NB + 1];            // factored diagonal block: L below, U on / above the diagonal
+    __shared__ __align__(16) double s_Dr[NB][NB]; // the same, rows 16-byte aligned
+    __shared__ __align__(16) double s_Dc[NB][NB]; // its transpose
     __shared__ double s_rd[NB];                   // reciprocals of its diagonal
     __shared__ __align__(16) double s_prow[2][NB];
     const int s = nodes[blockIdx.x];
     const int m = d.m[s], np = d.np[s], tid = threadIdx.x, lane = tid & 31;
+    const bool worker = tid < TLW;
     double *F = d.F + d.front_ptr[s];
     // ---- extend-add, one child at a time (single writer per entry, see mf_factor_kernel)
     for (int ci = d.child_ptr[s]; ci < d.child_ptr[s + 1]; ++ci) {
@@ -564,124 +591,194 @@ mf_leaf_factor_kernel(MFDev d, const int *__restrict__ nodes, int *info) {
     double *Lp = sm;                              // columns 0 .. np-1:            Lp[i + c * ldL]
     double *Up = Lp + (size_t)ldL * np;           // rows 0 .. np-1 of columns np..: Up[t * ldU + (c - np)]
     double *Us = Up + (size_t)ldU * np;           // U rows of the current panel:   Us[t * ldS + (c - k1)]
-    for (int e = tid; e < m * np; e += TL) {
-        const int c = e / m, i = e - c * m;
-        Lp[i + c * ldL] = __ldcg(F + i + (size_t)c * m);
-    }
-    for (int e = tid; e < np * nu; e += TL) {
-        const int c = e / np, t = e - c * np;
-        Up[t * ldU + c] = __ldcg(F + t + (size_t)(np + c) * m);
-    }
-    __syncthreads();
-    for (int k0 = 0; k0 < np; k0 += NB) {
-        const int kb = min(NB, np - k0), k1 = k0 + kb;
-        // (1) diagonal block, one warp
-        if (tid < 32) {
-            double r[NB];
+    if (worker) {
+        // ---- load the L-shaped region, eight independent loads in flight per thread
+        constexpr int LU8 = 8;
+        const int nL = m * np, nU = np * nu;
+        for (int e0 = tid; e0 < nL; e0 += LU8 * TLW) {
+            double v[LU8];
 #pragma unroll
-            for (int jj = 0; jj < NB; ++jj)
-                r[jj] = (lane < kb && jj < kb) ? Lp[(k0 + lane) + (k0 + jj) * ldL] : ((jj == lane) ? 1.0 : 0.0);
-            diag16_factor(r, lane, kb, s_prow, s_rd, info, s);
-            if (lane < NB) {
+            for (int u = 0; u < LU8; ++u) v[u] = (e0 + u * TLW < nL) ? __ldcg(F + e0 + u * TLW) : 0.0;
 #pragma unroll
-                for (int jj = 0; jj < NB; ++jj) s_D[lane][jj] = r[jj];
-            }
-            if (lane < kb) {
-#pragma unroll
-                for (int jj = 0; jj < NB; ++jj)
-                    if (jj < kb) Lp[(k0 + lane) + (k0 + jj) * ldL] = r[jj];
+            for (int u = 0; u < LU8; ++u) {
+                const int e = e0 + u * TLW;
+                if (e < nL) {
+                    const int c = e / m, i = e - c * m;
+                    Lp[i + c * ldL] = v[u];
+                }
             }
         }
-        __syncthreads();
-        // (2) rows below the block: L = A U11^-1; columns right of it: U = L11^-1 A (one row / column per thread)
+        for (int e0 = tid; e0 < nU; e0 += LU8 * TLW) {
+            double v[LU8];
+            int cc[LU8], tt[LU8];
+#pragma unroll
+            for (int u = 0; u < LU8; ++u) {
+                const int e = e0 + u * TLW;
+                cc[u] = e / np;
+                tt[u] = e - cc[u] * np;
+                v[u] = (e < nU) ? __ldcg(F + tt[u] + (size_t)(np + cc[u]) * m) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < LU8; ++u)
+                if (e0 + u * TLW < nU) Up[tt[u] * ldU + cc[u]] = v[u];
+        }
+    } else {
+        // ---- look-ahead warp: first diagonal block straight from the front
+        const int kb = min(NB, np);
+        double r[NB];
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj)
+            r[jj] = (lane < kb && jj < kb) ? __ldcg(F + lane + (size_t)jj * m) : ((jj == lane) ? 1.0 : 0.0);
+        leaf_publish_block(r, lane, kb, s_D, s_Dr, s_Dc, s_prow, s_rd, info, s);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (!worker && lane < min(NB, np)) {          // (the workers have stored the unfactored block: replace it)
+        const int kb = min(NB, np);
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj)
+            if (jj < kb) Lp[lane + jj * ldL] = s_D[lane][jj];
+    }
+    for (int k0 = 0; k0 < np; k0 += NB) {
+        const int kb = min(NB, np - k0), k1 = k0 + kb;
+        // (2) rows below the block: L = A U11^-1; columns right of it: U = L11^-1 A (one row / column per thread).
+        // Rows / columns >= kb of the block are identity padding, so all 16 steps run unconditionally.
         const int nrest = m - k1;
-        for (int task = tid; task < 2 * nrest; task += TL) {
-            if (task < nrest) {
-                const int i = k1 + task;
-                double a[NB];
+        if (worker) {
+            for (int task = tid; task < 2 * nrest; task += TLW) {
+                if (task < nrest) {
+                    const int i = k1 + task;
+                    double a[NB];
 #pragma unroll
-                for (int jj = 0; jj < NB; ++jj) a[jj] = jj < kb ? Lp[i + (k0 + jj) * ldL] : 0.0;
+                    for (int jj = 0; jj < NB; ++jj) a[jj] = jj < kb ? Lp[i + (k0 + jj) * ldL] : 0.0;
 #pragma unroll
-                for (int t = 0; t < NB; ++t) {
-                    if (t < kb) {
+                    for (int t = 0; t < NB; ++t) {
+                        // (keeps the compiler from hoisting all 120 entries of D into registers - it spilled 48 of them)
+                        if ((t & 1) == 0) asm volatile("" ::: "memory");
                         const double l = a[t] * s_rd[t];
                         a[t] = l;
+                        const double2 *dr = reinterpret_cast<const double2 *>(s_Dr[t]);
 #pragma unroll
-                        for (int jj = 0; jj < NB; ++jj)
-                            if (jj > t && jj < kb) a[jj] = fma(-l, s_D[t][jj], a[jj]);
+                        for (int j2 = 0; j2 < NB / 2; ++j2) {
+                            if (2 * j2 + 1 > t) {
+                                const double2 dd = dr[j2];
+                                if (2 * j2 > t) a[2 * j2] = fma(-l, dd.x, a[2 * j2]);
+                                a[2 * j2 + 1] = fma(-l, dd.y, a[2 * j2 + 1]);
+                            }
+                        }
                     }
-                }
 #pragma unroll
-                for (int jj = 0; jj < NB; ++jj)
-                    if (jj < kb) Lp[i + (k0 + jj) * ldL] = a[jj];
-            } else {
-                const int c = k1 + (task - nrest);
-                double *col = c < np ? Lp + k0 + (size_t)c * ldL : Up + (size_t)k0 * ldU + (c - np);
-                const int st = c < np ? 1 : ldU;
-                double u[NB];
+                    for (int jj = 0; jj < NB; ++jj)
+                        if (jj < kb) Lp[i + (k0 + jj) * ldL] = a[jj];
+                } else {
+                    const int c = k1 + (task - nrest);
+                    double *col = c < np ? Lp + k0 + (size_t)c * ldL : Up + (size_t)k0 * ldU + (c - np);
+                    const int st = c < np ? 1 : ldU;
+                    double u[NB];
 #pragma unroll
-                for (int t = 0; t < NB; ++t) u[t] = t < kb ? col[t * st] : 0.0;
+                    for (int t = 0; t < NB; ++t) u[t] = t < kb ? col[t * st] : 0.0;
 #pragma unroll
-                for (int t = 0; t < NB; ++t) {
-                    if (t < kb) {
+                    for (int t = 0; t < NB; ++t) {
+                        if ((t & 1) == 0) asm volatile("" ::: "memory");
+                        const double ut = u[t];
+                        const double2 *dc = reinterpret_cast<const double2 *>(s_Dc[t]);
 #pragma unroll
-                        for (int tt = 0; tt < NB; ++tt)
-                            if (tt > t && tt < kb) u[tt] = fma(-s_D[tt][t], u[t], u[tt]);
+                        for (int j2 = 0; j2 < NB / 2; ++j2) {
+                            if (2 * j2 + 1 > t) {
+                                const double2 dd = dc[j2];
+                                if (2 * j2 > t) u[2 * j2] = fma(-dd.x, ut, u[2 * j2]);
+                                u[2 * j2 + 1] = fma(-dd.y, ut, u[2 * j2 + 1]);
+                            }
+                        }
                     }
-                }
 #pragma unroll
-                for (int t = 0; t < NB; ++t) {
-                    if (t < kb) {
-                        col[t * st] = u[t];
-                        Us[t * ldS + (c - k1)] = u[t];
+                    for (int t = 0; t < NB; ++t) {
+                        if (t < kb) {
+                            col[t * st] = u[t];
+                            Us[t * ldS + (c - k1)] = u[t];
+                        }
                     }
                 }
             }
         }
         __syncthreads();
         // (3) rank-16 update of the L-shaped region only: rows [k1, m) x columns [k1, np) (in Lp) and rows [k1, np) x
-        // columns [np, m) (in Up); 4 x 4 tiles, a tile that straddles column / row np is predicated per element
+        // columns [np, m) (in Up); 4 x 4 tiles, a tile that straddles column / row np is predicated per element.  The
+        // next diagonal block [k1, k1 + kb2)^2 belongs to the look-ahead warp.
         if (k1 < np) {
-            const int tr = (m - k1 + 3) >> 2, tcA = (np - k1 + 3) >> 2, trB = tcA;
-            const int ntA = tr * tcA, ntB = trB * (tr - tcA);
-            for (int tile = tid; tile < ntA + ntB; tile += TL) {
-                int ti, tj;
-                if (tile < ntA) {
-                    ti = tile % tr;
-                    tj = tile / tr;
-                } else {
-                    const int q = tile - ntA;
-                    ti = q % trB;
-                    tj = tcA + q / trB;
-                }
-                const int i0 = k1 + 4 * ti, c0 = k1 + 4 * tj;
-                double acc[4][4];
-#pragma unroll
-                for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[aa][b] = 0.0;
-                for (int t = 0; t < NB; ++t) {
-                    const double2 la = *reinterpret_cast<const double2 *>(Lp + i0 + (k0 + t) * ldL);
-                    const double2 lb = *reinterpret_cast<const double2 *>(Lp + i0 + (k0 + t) * ldL + 2);
-                    const double2 ua = *reinterpret_cast<const double2 *>(Us + t * ldS + (c0 - k1));
-                    const double2 ub = *reinterpret_cast<const double2 *>(Us + t * ldS + (c0 - k1) + 2);
-                    const double l[4] = {la.x, la.y, lb.x, lb.y}, uu[4] = {ua.x, ua.y, ub.x, ub.y};
+            const int kb2 = min(NB, np - k1), kend = k1 + kb2;
+            if (worker) {
+                const int tr = (m - k1 + 3) >> 2, tcA = (np - k1 + 3) >> 2, trB = tcA;
+                const int ntA = tr * tcA, ntB = trB * (tr - tcA);
+                for (int tile = tid; tile < ntA + ntB; tile += TLW) {
+                    int ti, tj;
+                    if (tile < ntA) {
+                        ti = tile % tr;
+                        tj = tile / tr;
+                    } else {
+                        const int q = tile - ntA;
+                        ti = q % trB;
+                        tj = tcA + q / trB;
+                    }
+                    const int i0 = k1 + 4 * ti, c0 = k1 + 4 * tj;
+                    if (i0 + 3 < kend && c0 + 3 < kend) continue;          // entirely inside the look-ahead block
+                    double acc[4][4];
 #pragma unroll
                     for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[aa][b] = fma(l[aa], uu[b], acc[aa][b]);
-                }
+                        for (int b = 0; b < 4; ++b) acc[aa][b] = 0.0;
+#pragma unroll 4
+                    for (int t = 0; t < NB; ++t) {
+                        const double2 la = *reinterpret_cast<const double2 *>(Lp + i0 + (k0 + t) * ldL);
+                        const double2 lb = *reinterpret_cast<const double2 *>(Lp + i0 + (k0 + t) * ldL + 2);
+                        const double2 ua = *reinterpret_cast<const double2 *>(Us + t * ldS + (c0 - k1));
+                        const double2 ub = *reinterpret_cast<const double2 *>(Us + t * ldS + (c0 - k1) + 2);
+                        const double l[4] = {la.x, la.y, lb.x, lb.y}, uu[4] = {ua.x, ua.y, ub.x, ub.y};
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int c = c0 + b;
+                        for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
-                    for (int aa = 0; aa < 4; ++aa) {
-                        const int i = i0 + aa;
-                        if (i < m && c < m && !(i >= np && c >= np)) {
-                            double *e = c < np ? Lp + i + (size_t)c * ldL : Up + (size_t)i * ldU + (c - np);
-                            *e -= acc[aa][b];
+                            for (int b = 0; b < 4; ++b) acc[aa][b] = fma(l[aa], uu[b], acc[aa][b]);
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int c = c0 + b;
+#pragma unroll
+                        for (int aa = 0; aa < 4; ++aa) {
+                            const int i = i0 + aa;
+                            if (i < m && c < m && !(i >= np && c >= np) && !(i < kend && c < kend)) {
+                                double *e = c < np ? Lp + i + (size_t)c * ldL : Up + (size_t)i * ldU + (c - np);
+                                *e -= acc[aa][b];
+                            }
                         }
                     }
+                }
+            } else {
+                // look-ahead warp: row k1 + lane of the next diagonal block, updated by this panel and factored
+                double r[NB];
+                const int i = k1 + lane;
+                const bool live = lane < kb2;
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) r[jj] = 0.0;
+                if (live) {
+                    for (int t = 0; t < NB; ++t) {
+                        const double l = Lp[i + (k0 + t) * ldL];
+                        const double2 *ur = reinterpret_cast<const double2 *>(Us + t * ldS);
+#pragma unroll
+                        for (int j2 = 0; j2 < NB / 2; ++j2) {
+                            const double2 uu = ur[j2];
+                            r[2 * j2] = fma(l, uu.x, r[2 * j2]);
+                            r[2 * j2 + 1] = fma(l, uu.y, r[2 * j2 + 1]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj)
+                    r[jj] = (live && jj < kb2) ? Lp[i + (k1 + jj) * ldL] - r[jj] : ((jj == lane) ? 1.0 : 0.0);
+                leaf_publish_block(r, lane, kb2, s_D, s_Dr, s_Dc, s_prow, s_rd, info, s);
+                if (live) {
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj)
+                        if (jj < kb2) Lp[i + (k1 + jj) * ldL] = r[jj];
                 }
             }
             __syncthreads();
@@ -705,6 +802,7 @@ mf_leaf_factor_kernel(MFDev d, const int *__restrict__ nodes, int *info) {
                     acc[aa][b] = 0.0;
                 }
             }
+#pragma unroll 4
             for (int t = 0; t < np; ++t) {
                 const double2 la = *reinterpret_cast<const double2 *>(Lp + i0 + t * ldL);
                 const double2 lb = *reinterpret_cast<const double2 *>(Lp + i0 + t * ldL + 2);
@@ -730,7 +828,7 @@ mf_leaf_factor_kernel(MFDev d, const int *__restrict__ nodes, int *info) {
     // (5) factors back to the front
     for (int e = tid; e < m * np; e += TL) {
         const int c = e / m, i = e - c * m;
-        __stcg(F + i + (size_t)c * m, Lp[i + c * ldL]);
+        __stcg(F + e, Lp[i + c * ldL]);
     }
     for (int e = tid; e < np * nu; e += TL) {
         const int c = e / np, t = e - c * np;
