@@ -79,10 +79,13 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // by the blocked triangular solves.  One launch after the numeric factorisation, one warp per (block, factor): the
 // inversions are shuffle-heavy and used to sit on the critical path of every panel.
 __global__ void __launch_bounds__(256)
-mf_dinv_kernel(MFDev d, const int *__restrict__ panel_node, int npanels, int *info) {
+mf_dinv_kernel(MFDev d, const int *__restrict__ panel_node, int npanels, int *info, int check_only) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int p = w >> 1, which = w & 1;                 // which = 1: L11^{-1}, 0: U11^{-1}
     if (p >= npanels) return;
+    // check_only: every front is solved with the 64-row kernels (own inverses), so only the growth check below is
+    // wanted from this launch
+    if (check_only && which) return;
     const int s = panel_node[p];
     const int m = d.m[s], np = d.np[s];
     const int k0 = (p - d.dinv_ptr[s]) * NB, kb = min(NB, np - k0);
@@ -102,6 +105,7 @@ mf_dinv_kernel(MFDev d, const int *__restrict__ panel_node, int npanels, int *in
         }
         if (!(piv > 1e-11 * rowmax)) atomicExch(info, s + 1);
     }
+    if (check_only) return;
     double X[NB];
 #pragma unroll
     for (int c = 0; c < NB; ++c) X[c] = (c == lane) ? 1.0 : 0.0;
@@ -784,30 +788,38 @@ mf_leaf_factor_kernel(MFDev d, const int *__restrict__ nodes, int *info) {
             __syncthreads();
         }
     }
-    // (4) Schur complement in one pass: F[i, c] -= sum_t L[i, t] U[t, c], i, c >= np (tile rows aligned to 4)
+    // (4) Schur complement in one pass: F[i, c] -= sum_t L[i, t] U[t, c], i, c >= np.  A tile takes the row PAIRS ti and
+    // ti + H (pairs counted from the 4-aligned row rb): consecutive lanes then read consecutive 16-byte pieces of a
+    // column of L - conflict-free, where four consecutive rows per lane cost two wavefronts per quarter warp (ncu of the
+    // second version: the phase is bound by shared-memory wavefronts, 40 % of them excess).
     {
         const int rb = np & ~3;
-        const int trS = (m - rb + 3) >> 2, tcS = (nu + 3) >> 2;
-        for (int tile = tid; tile < trS * tcS; tile += TL) {
-            const int ti = tile % trS, tj = tile / trS;
-            const int i0 = rb + 4 * ti, cc0 = 4 * tj;
+        const int npair = (m - rb + 1) >> 1, H = (npair + 1) >> 1, tcS = (nu + 3) >> 2;
+        for (int tile = tid; tile < H * tcS; tile += TL) {
+            const int ti = tile % H, tj = tile / H;
+            const int rA = rb + 2 * ti, rB = rb + 2 * (ti + H), cc0 = 4 * tj;
+            const int ia[4] = {rA, rA + 1, rB, rB + 1};
             double f[4][4], acc[4][4];
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const double *colp = F + (size_t)(np + cc0 + b) * m;
 #pragma unroll
                 for (int aa = 0; aa < 4; ++aa) {
-                    const int i = i0 + aa;
+                    const int i = ia[aa];
                     f[aa][b] = (i >= np && i < m && cc0 + b < nu) ? __ldcg(colp + i) : 0.0;
                     acc[aa][b] = 0.0;
                 }
             }
+            const double *La = Lp + rA, *Lb = Lp + rB, *Uq = Up + cc0;
 #pragma unroll 4
             for (int t = 0; t < np; ++t) {
-                const double2 la = *reinterpret_cast<const double2 *>(Lp + i0 + t * ldL);
-                const double2 lb = *reinterpret_cast<const double2 *>(Lp + i0 + t * ldL + 2);
-                const double2 ua = *reinterpret_cast<const double2 *>(Up + t * ldU + cc0);
-                const double2 ub = *reinterpret_cast<const double2 *>(Up + t * ldU + cc0 + 2);
+                const double2 la = *reinterpret_cast<const double2 *>(La);
+                const double2 lb = *reinterpret_cast<const double2 *>(Lb);
+                const double2 ua = *reinterpret_cast<const double2 *>(Uq);
+                const double2 ub = *reinterpret_cast<const double2 *>(Uq + 2);
+                La += ldL;
+                Lb += ldL;
+                Uq += ldU;
                 const double l[4] = {la.x, la.y, lb.x, lb.y}, uu[4] = {ua.x, ua.y, ub.x, ub.y};
 #pragma unroll
                 for (int aa = 0; aa < 4; ++aa)
@@ -819,7 +831,7 @@ mf_leaf_factor_kernel(MFDev d, const int *__restrict__ nodes, int *info) {
                 double *colp = F + (size_t)(np + cc0 + b) * m;
 #pragma unroll
                 for (int aa = 0; aa < 4; ++aa) {
-                    const int i = i0 + aa;
+                    const int i = ia[aa];
                     if (i >= np && i < m && cc0 + b < nu) __stcg(colp + i, f[aa][b] - acc[aa][b]);
                 }
             }
@@ -1936,6 +1948,7 @@ struct MultifrontalLU::Impl {
     // Measured on B200 and NOT the default: the side kernels take SM time from the level kernels, 2 factorisations
     // 1.73 -> 1.88 ms per GD iteration; the default forms all inverses in one launch behind the factorisation.
     bool overlap_dinv = false;
+    bool dinv_pair = false;      // the 16- and 64-block inverse kernels behind the factorisation side by side (OCP_MF_DINV_PAIR=1; measured: no gain)
     std::vector<int> level_blk_off;
     cudaStream_t side = nullptr;
     std::vector<cudaEvent_t> ev_level;
@@ -2247,6 +2260,7 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
         if (const char *e16 = getenv("OCP_MF_SOLVE16")) I.solve64 = atoi(e16) == 0;
         if (const char *ep = getenv("OCP_MF_PDL")) I.pdl = atoi(ep) != 0;
         if (const char *eo = getenv("OCP_MF_OVERLAP")) I.overlap_dinv = atoi(eo) != 0;
+        if (const char *eo = getenv("OCP_MF_DINV_PAIR")) I.dinv_pair = atoi(eo) != 0;
         // blocks are numbered level by level (the order of the launch lists), so that the inverses of a level's blocks
         // can be formed on the side stream while the next level is being factored (enqueue_factor)
         std::vector<int> dp(S.nnodes + 1, 0), bn;
@@ -2349,12 +2363,20 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
             if (solve64 && nb > 0) mf_dinv64_kernel<<<2 * nb, SB, 0, side>>>(dev, block_node, b0, nb);
         }
     }
-    if (npanels > 0) mf_dinv_kernel<<<(2 * npanels * 32 + 255) / 256, 256, 0, side_on ? side : s>>>(dev, panel_node, npanels, info);
-    if (side_on) {
+    // the 16 x 16 inverses are only read by the 16-row solve kernels (large fronts, OCP_MF_SOLVE16=1)
+    const int check_only = (solve64 && big_launches.empty()) ? 1 : 0;
+    // opt-in: the two inverse kernels side by side (a two-branch fork of the captured graph)
+    const bool pair_on = !side_on && dinv_pair && !prof && npanels > 0 && solve64 && nblocks64 > 0 && ensure_side(S.nlevels);
+    if (pair_on) {
+        cudaEventRecord(ev_level[0], s);
+        cudaStreamWaitEvent(side, ev_level[0], 0);
+    }
+    if (npanels > 0)
+        mf_dinv_kernel<<<(2 * npanels * 32 + 255) / 256, 256, 0, (side_on || pair_on) ? side : s>>>(dev, panel_node, npanels, info, check_only);
+    if (!side_on && solve64 && nblocks64 > 0) mf_dinv64_kernel<<<2 * nblocks64, SB, 0, s>>>(dev, block_node, 0, nblocks64);
+    if (side_on || pair_on) {
         cudaEventRecord(ev_join, side);
         cudaStreamWaitEvent(s, ev_join, 0);
-    } else if (solve64 && nblocks64 > 0) {
-        mf_dinv64_kernel<<<2 * nblocks64, SB, 0, s>>>(dev, block_node, 0, nblocks64);
     }
     cudaMemcpyAsync(h_info, info, sizeof(int), cudaMemcpyDeviceToHost, s);
     return true;
