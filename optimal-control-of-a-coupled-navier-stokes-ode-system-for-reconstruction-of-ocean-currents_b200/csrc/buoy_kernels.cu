@@ -320,6 +320,102 @@ __device__ __forceinline__ void eval_p2_cell_g(const double2 *__restrict__ cellv
     uy = sy;
 }
 
+// Small launches (K ~ 10^4: one or two warps per SM walking 199 dependent Euler steps): a buoy stays ~60 steps in a
+// cell, so the cell's geometry (6 doubles) and velocity record (12 doubles) are kept in REGISTERS while it does - a
+// step inside the cell is then pure arithmetic (barycentrics, basis, 12 FMAs, Euler) instead of two dependent table
+// reads.  The fast test is exactly the first hop of locate_g (same bary(), same strict-inside margin) and the
+// velocity sum runs in the order of eval_p2_cell_g, so x, u and the cells stay bit-identical to the table kernel.
+__global__ void __launch_bounds__(kBuoyThreads)
+buoy_forward_cached_kernel(DeviceTables t, const double2 *__restrict__ vel /* per-cell records */, const double2 *__restrict__ x0, int K, int nt,
+                    double h, double cx, double cy, double2 *__restrict__ x, double2 *__restrict__ u,
+                    int *__restrict__ cell, double *__restrict__ mask, uint8_t *__restrict__ parked) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= K) return;
+    double2 p = x0[b];
+    int cur = -1, kfail = -1;
+    double cg[6];
+    double2 cv[6];
+    double l0, l1, l2;
+    auto locate = [&]() -> int {
+        if (cur >= 0) {
+            bary(cg, p.x, p.y, l0, l1, l2);
+            if (l0 > kLocateMargin && l1 > kLocateMargin && l2 > kLocateMargin) return cur;
+        }
+        const int c = locate_g(t, p.x, p.y, cur, l0, l1, l2);
+        if (c >= 0 && c != cur) {
+            load_geom_g(t, c, cg);
+            const double2 *r = vel + 6 * (size_t)c;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) cv[i] = __ldg(r + i);
+            cur = c;
+        }
+        return c;
+    };
+    auto eval = [&](double &ux, double &uy) {
+        double phi[6];
+        p2_basis(l0, l1, l2, phi);
+        double sx = OCP_MUL(phi[0], cv[0].x), sy = OCP_MUL(phi[0], cv[0].y);
+#pragma unroll
+        for (int i = 1; i < 6; ++i) {
+            sx = OCP_FMA(phi[i], cv[i].x, sx);
+            sy = OCP_FMA(phi[i], cv[i].y, sy);
+        }
+        ux = sx;
+        uy = sy;
+    };
+    for (int k = 0; k < nt - 1; ++k) {
+        const int c = locate();
+        if (c < 0) {
+            kfail = k;
+            break;
+        }
+        double ux, uy;
+        eval(ux, uy);
+        const size_t o = (size_t)k * K + b;
+        x[o] = p;
+        u[o] = make_double2(ux, uy);
+        if (cell) cell[o] = c;
+        p.x = OCP_ADD(p.x, OCP_MUL(h, ux));      // two roundings, as numpy at OCP_dolfin.py:212
+        p.y = OCP_ADD(p.y, OCP_MUL(h, uy));
+    }
+    if (kfail < 0) {
+        // trailing evaluation at the last sample, OCP_dolfin.py:223-229
+        const size_t o = (size_t)(nt - 1) * K + b;
+        const int c = locate();
+        if (c >= 0) {
+            double ux, uy;
+            eval(ux, uy);
+            x[o] = p;
+            u[o] = make_double2(ux, uy);
+            if (cell) cell[o] = c;
+            parked[b] = 0;
+        } else {
+            x[o] = make_double2(cx, cy);
+            u[o] = make_double2(0.0, 0.0);
+            if (cell) cell[o] = -1;
+            parked[b] = 1;
+        }
+        return;
+    }
+    // the `except` branch, OCP_dolfin.py:213-221 (see buoy_forward_global_kernel)
+    mask[b] = 1.0;
+    parked[b] = 0;
+    const int cc = locate_g(t, cx, cy, -1, l0, l1, l2);
+    double ucx = 0.0, ucy = 0.0;
+    if (cc >= 0) eval_p2_cell_g(vel, cc, l0, l1, l2, ucx, ucy);
+    for (int k = 0; k < nt; ++k) {
+        const size_t o = (size_t)k * K + b;
+        x[o] = make_double2(cx, cy);
+        if (k == kfail + 1) {
+            u[o] = make_double2(ucx, ucy);
+            if (cell) cell[o] = cc;
+        } else if (k >= kfail) {
+            u[o] = make_double2(0.0, 0.0);
+            if (cell) cell[o] = -1;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kBuoyThreads)
 buoy_forward_global_kernel(DeviceTables t, const double2 *__restrict__ vel /* per-cell records */, const double2 *__restrict__ x0, int K, int nt,
                     double h, double cx, double cy, double2 *__restrict__ x, double2 *__restrict__ u,
@@ -952,7 +1048,12 @@ buoy_adjoint_scatter_global_kernel(DeviceTables t, const double2 *__restrict__ v
 // The dependent chain shrinks from nt to 2 nt / T samples and T times as many warps are in flight.  mu at the chunk
 // boundaries is formed through the composed maps, i.e. with a different (equally valid) rounding sequence than the
 // serial sweep: mu and b agree with it to ~1e-15 relative (tests: 1e-12 against the oracle).
-template <int T, bool X>
+// CR (opt-in): the geometry and the projected-gradient record of the cell a lane is in stay in REGISTERS while it
+// stays there (~60 samples): the fast test is the first hop of locate_g (same bary(), same strict-inside margin), so
+// cells and barycentrics - hence mu and b - are bit-identical to the table path, and the nine table reads per sample
+// only happen on a cell change.  Measured on B200 and NOT the default: 154 instead of 96 registers, 12 instead of 20
+// warps per SM, in-step launch 0.132 vs 0.100 ms (4 lanes per buoy: 0.114, 16: 0.139).
+template <int T, bool X, bool CR>
 __global__ void __launch_bounds__(kBuoyThreads)
 buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /* per-cell records */,
                                const double2 *__restrict__ g /* per-cell vertex gradients */, int K, int nt, double h,
@@ -974,20 +1075,38 @@ buoy_adjoint_scatter_tp_kernel(DeviceTables t, const double2 *__restrict__ vel /
     long long *const dovf = X ? digits + 8 * (size_t)t.nn : nullptr;
     double misfit = 0.0, nmasked = (masked && j == 0) ? 1.0 : 0.0;
     // G(x_k)^T-step coefficients of one sample: returns false when the sample leaves mu unchanged
+    double cgeo[6];                                            // CR: geometry / gradient record of cell `hint`
+    double2 cgr[6];
     auto locate_sample = [&](int k, double2 &p, int &hint, double &l0, double &l1, double &l2, bool &lost) -> int {
+        if (CR && hint >= 0) {
+            bary(cgeo, p.x, p.y, l0, l1, l2);
+            if (l0 > kLocateMargin && l1 > kLocateMargin && l2 > kLocateMargin) {
+                lost = false;
+                return hint;
+            }
+        }
         int c = locate_g(t, p.x, p.y, hint, l0, l1, l2);
         lost = c < 0;
         if (lost) {                                            // `except` of OCP_dolfin.py:359-361: point = centre
             p = make_double2(cx, cy);
             c = locate_g(t, cx, cy, -1, l0, l1, l2);
         }
-        if (c >= 0) hint = c;
+        if (c >= 0) {
+            if (CR && c != hint) {
+                load_geom_g(t, c, cgeo);
+                const double2 *gr = g + 6 * (size_t)c;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) cgr[i] = __ldg(gr + i);
+            }
+            hint = c;
+        }
         return c;
     };
     auto grad_at = [&](int c, double l0, double l1, double l2, double &G0, double &G1, double &G2, double &G3) {
         const double2 *gr = g + 6 * (size_t)c;
-        const double2 a0 = __ldg(gr), a1 = __ldg(gr + 1), b0 = __ldg(gr + 2), b1 = __ldg(gr + 3), c0 = __ldg(gr + 4),
-                      c1 = __ldg(gr + 5);
+        // (CR: c is the cell the record in registers belongs to - locate_sample has just returned it)
+        const double2 a0 = CR ? cgr[0] : __ldg(gr), a1 = CR ? cgr[1] : __ldg(gr + 1), b0 = CR ? cgr[2] : __ldg(gr + 2),
+                      b1 = CR ? cgr[3] : __ldg(gr + 3), c0 = CR ? cgr[4] : __ldg(gr + 4), c1 = CR ? cgr[5] : __ldg(gr + 5);
         G0 = l0 * a0.x + l1 * b0.x + l2 * c0.x;
         G1 = l0 * a0.y + l1 * b0.y + l2 * c0.y;
         G2 = l0 * a1.x + l1 * b1.x + l2 * c1.x;
@@ -1242,7 +1361,10 @@ int time_parallel_lanes(int K, int nt, int nrep) {
     if (enabled < 0) {
         const char *e = getenv("OCP_BUOY_TP");
         enabled = (e && atoi(e) == 0) ? 0 : 1;
-        if (const char *l = getenv("OCP_BUOY_TP_LANES")) forced = atoi(l) == 32 ? 32 : (atoi(l) == 8 ? 8 : 0);
+        if (const char *l = getenv("OCP_BUOY_TP_LANES")) {
+            const int v = atoi(l);
+            forced = (v == 32 || v == 16 || v == 8 || v == 4) ? v : 0;
+        }
     }
     if (!enabled || nrep > 1 || nt < 64) return 1;
     if (K > 12000) return 1;
@@ -1277,8 +1399,16 @@ void launch_buoy_forward(const DeviceTables &t, bool staged, const double *field
         buoy_forward_kernel<true><<<sh.grid, sh.threads, smem, s>>>(t, f2, x02, K, sh.per_block, nt, h, cx, cy, x2, u2,
                                                                     cell, mask, parked);
     } else {
-        buoy_forward_global_kernel<<<(K + kBuoyThreads - 1) / kBuoyThreads, kBuoyThreads, 0, s>>>(
-            t, f2, x02, K, nt, h, cx, cy, x2, u2, cell, mask, parked);
+        // small launches: cell data in registers (0.075 -> 0.065 ms at K = 10^4); OCP_BUOY_FWD_BLOCK = 32 / 64 spreads the
+        // warps over all SMs and measured no faster than 128-thread CTAs
+        static const bool cached = !(getenv("OCP_BUOY_FWD_CACHE") && atoi(getenv("OCP_BUOY_FWD_CACHE")) == 0);
+        static const int small_block = getenv("OCP_BUOY_FWD_BLOCK") ? std::max(32, std::min(kBuoyThreads, atoi(getenv("OCP_BUOY_FWD_BLOCK")) & ~31)) : kBuoyThreads;
+        if (cached && K <= 12000)
+            buoy_forward_cached_kernel<<<(K + small_block - 1) / small_block, small_block, 0, s>>>(
+                t, f2, x02, K, nt, h, cx, cy, x2, u2, cell, mask, parked);
+        else
+            buoy_forward_global_kernel<<<(K + kBuoyThreads - 1) / kBuoyThreads, kBuoyThreads, 0, s>>>(
+                t, f2, x02, K, nt, h, cx, cy, x2, u2, cell, mask, parked);
     }
 }
 
@@ -1324,18 +1454,22 @@ void launch_buoy_adjoint_scatter(const DeviceTables &t, bool staged, const doubl
         const int T = time_parallel_lanes(K, nt, nrep);
         const long long threads = (long long)((K + (32 / T) - 1) / (32 / T)) * 32;
         const int grid = (int)((threads + kBuoyThreads - 1) / kBuoyThreads);
+        // (opt-in, OCP_BUOY_TP_CACHE=1: measured slower - 0.132 vs 0.100 ms at K = 10^4 - the 154 registers of the cached
+        // variant leave 12 instead of 20 warps per SM)
+        static const bool cached = getenv("OCP_BUOY_TP_CACHE") && atoi(getenv("OCP_BUOY_TP_CACHE")) != 0;
 #define OCP_TP_ARGS t, fv, fg, K, nt, h, cx, cy, x2, u2, d2, mask, parked, mu2, acc, scratch, counter, digits
-        if (T == 32) {
-            if (exact)
-                buoy_adjoint_scatter_tp_kernel<32, true><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
-            else
-                buoy_adjoint_scatter_tp_kernel<32, false><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
-        } else {
-            if (exact)
-                buoy_adjoint_scatter_tp_kernel<8, true><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
-            else
-                buoy_adjoint_scatter_tp_kernel<8, false><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);
-        }
+#define OCP_TP_LAUNCH(TT)                                                                                       \
+    do {                                                                                                        \
+        if (exact && cached) buoy_adjoint_scatter_tp_kernel<TT, true, true><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);    \
+        else if (exact) buoy_adjoint_scatter_tp_kernel<TT, true, false><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);        \
+        else if (cached) buoy_adjoint_scatter_tp_kernel<TT, false, true><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);       \
+        else buoy_adjoint_scatter_tp_kernel<TT, false, false><<<grid, kBuoyThreads, 0, s>>>(OCP_TP_ARGS);                  \
+    } while (0)
+        if (T == 32) OCP_TP_LAUNCH(32);
+        else if (T == 16) OCP_TP_LAUNCH(16);
+        else if (T == 4) OCP_TP_LAUNCH(4);
+        else OCP_TP_LAUNCH(8);
+#undef OCP_TP_LAUNCH
 #undef OCP_TP_ARGS
     } else {
         const int grid = (K + kBuoyThreads - 1) / kBuoyThreads;
