@@ -546,6 +546,47 @@ def test_refined_mesh_large_front_solver_matches_oracle(n, big, monkeypatch):
     ocp.close()
 
 
+def test_solver_variants_of_round_two_agree_with_the_oracle_and_with_each_other(monkeypatch):
+    """The factor / solve variants introduced in round 2, each against the oracle on the reference mesh and against
+    the default build: programmatic dependent launches between the solve levels, the side-stream assembly of the
+    adjoint operator, the inverse kernels on a side stream (same arithmetic, different launch mechanics), extend-add
+    child by child vs fp64 atomics, the shared-memory-resident leaf kernel on 0 / 1 / 3 bottom levels (a different
+    summation order of the Schur complement).  Everything agrees to rounding (measured on B200: w 1e-16 ... 7e-16,
+    z 8e-15 ... 1.6e-14 between the variants); the triangular solves still add the children's contributions to the
+    right-hand side with atomics, so not even two runs of one build are bitwise equal."""
+    V = H.square32()
+    rng = np.random.default_rng(11)
+    K = 48
+    x0 = np.stack([rng.uniform(0.2, 1.0, K), rng.uniform(0.3, 1.7, K)], 1)
+    f = initial_control(V, "PL")
+    P = H.OraclePipeline(V, 1.0, x0, np.zeros((K, 200, 2)), 1e-6 * K)
+    _, ud, _, _, _ = P.primal(P.O.newton_solve(1.3 * f))
+    P.ud = ud
+    s = P.gradient_step(f)
+
+    def run(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ocp = OCP(V, Parameters(), x0, ud, device=dev())
+        ocp.ctx.set_observations_host(x0, ud)
+        out = [ocp.ctx.gradient_host(f) for _ in range(3)]       # plain path, graph capture, graph replay
+        ocp.close()
+        for k in env:
+            monkeypatch.delenv(k)
+        for w, z, _, sc in out:
+            assert sc["newton_its"] == s["its"]
+            assert H.rel(w, s["w"]) < 1e-11 and H.rel(z, s["z"]) < 1e-9
+        return out
+
+    base = run({})
+    for w, z, _, _ in base[1:]:                                  # plain path, captured graph, replayed graph
+        assert H.rel(w, base[0][0]) < 1e-12 and H.rel(z, base[0][1]) < 1e-10
+    for env in ({"OCP_MF_PDL": "0"}, {"OCP_STEP_OVERLAP": "0"}, {"OCP_MF_DINV_PAIR": "1"}, {"OCP_MF_OVERLAP": "1"},
+                {"OCP_MF_EA_ATOMIC": "1"}, {"OCP_MF_LEAF_LEVELS": "0"}, {"OCP_MF_LEAF_LEVELS": "3"}):
+        out = run(env)
+        assert H.rel(out[0][0], base[0][0]) < 1e-12 and H.rel(out[0][1], base[0][1]) < 1e-10, env
+
+
 def test_ensemble_of_independent_cases_runs_concurrently_with_identical_results():
     """cfg4: independent cases on one GPU, one context / stream / host thread each (ocp_b200.ensemble).  The concurrent
     run must reproduce the one-after-the-other run and the oracle's cost of every case."""
