@@ -1948,6 +1948,11 @@ struct MultifrontalLU::Impl {
     // Measured on B200 and NOT the default: the side kernels take SM time from the level kernels, 2 factorisations
     // 1.73 -> 1.88 ms per GD iteration; the default forms all inverses in one launch behind the factorisation.
     bool overlap_dinv = false;
+    // ONE fork instead: the inverses of all blocks below the top `overlap_top` levels are formed on the side stream
+    // while those levels - which leave most SMs idle (4, 2, 1 fronts) - are factored (OCP_MF_OVERLAP_FROM = levels from
+    // the top that run beside the inverse kernel; 0 = off).  Measured on B200 and NOT the default either: 2
+    // factorisations 1.504 -> 1.538 / 1.549 / 1.544 ms for 1 / 2 / 3 levels (profiles/README.md).
+    int overlap_top = 0;
     bool dinv_pair = false;      // the 16- and 64-block inverse kernels behind the factorisation side by side (OCP_MF_DINV_PAIR=1; measured: no gain)
     std::vector<int> level_blk_off;
     cudaStream_t side = nullptr;
@@ -2261,6 +2266,7 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
         if (const char *ep = getenv("OCP_MF_PDL")) I.pdl = atoi(ep) != 0;
         if (const char *eo = getenv("OCP_MF_OVERLAP")) I.overlap_dinv = atoi(eo) != 0;
         if (const char *eo = getenv("OCP_MF_DINV_PAIR")) I.dinv_pair = atoi(eo) != 0;
+        if (const char *eo = getenv("OCP_MF_OVERLAP_FROM")) I.overlap_top = std::max(0, atoi(eo));
         // blocks are numbered level by level (the order of the launch lists), so that the inverses of a level's blocks
         // can be formed on the side stream while the next level is being factored (enqueue_factor)
         std::vector<int> dp(S.nnodes + 1, 0), bn;
@@ -2301,10 +2307,21 @@ bool MultifrontalLU::configure(int n, int nnz, const int *h_rowptr, const int *h
 bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStream_t s, std::string &err) {
     const MFSymbolic &S = this->S;
     const bool side_on = overlap_dinv && !prof && ensure_side(S.nlevels);
+    // single fork in front of level fork_level (none: -1); only when every block below belongs to a small front
+    int fork_level = -1;
+    if (!side_on && overlap_top > 0 && !prof && solve64 && nblocks64 > 0 && big_launches.empty() && S.nlevels > overlap_top &&
+        level_blk_off[S.nlevels - overlap_top] > 0 && ensure_side(S.nlevels))
+        fork_level = S.nlevels - overlap_top;
     cudaMemsetAsync(F, 0, sizeof(double) * S.fsize, s);
     scatter_values_kernel<<<(nnz + 255) / 256, 256, 0, s>>>(nnz, a_dest, d_vals, F);
     for (int l = 0; l < S.nlevels; ++l) {
         const int nf = level_nsmall[l];
+        if (l == fork_level) {
+            cudaEventRecord(ev_level[0], s);
+            cudaStreamWaitEvent(side, ev_level[0], 0);
+            mf_dinv64_kernel<<<2 * level_blk_off[l], SB, 0, side>>>(dev, block_node, 0, level_blk_off[l]);
+            g_launch_count.fetch_add(1, std::memory_order_relaxed);      // (one inverse launch more than factor() counts)
+        }
         if (nf > 0 && level_leaf[l] && !prof) {
             mf_leaf_factor_kernel<<<nf, TL, level_leaf_smem[l], s>>>(dev, level_nodes + level_off[l], info);
         } else if (nf > 0) {
@@ -2366,15 +2383,20 @@ bool MultifrontalLU::Impl::enqueue_factor(const double *d_vals, int nnz, cudaStr
     // the 16 x 16 inverses are only read by the 16-row solve kernels (large fronts, OCP_MF_SOLVE16=1)
     const int check_only = (solve64 && big_launches.empty()) ? 1 : 0;
     // opt-in: the two inverse kernels side by side (a two-branch fork of the captured graph)
-    const bool pair_on = !side_on && dinv_pair && !prof && npanels > 0 && solve64 && nblocks64 > 0 && ensure_side(S.nlevels);
+    const bool pair_on = !side_on && fork_level < 0 && dinv_pair && !prof && npanels > 0 && solve64 && nblocks64 > 0 && ensure_side(S.nlevels);
     if (pair_on) {
         cudaEventRecord(ev_level[0], s);
         cudaStreamWaitEvent(side, ev_level[0], 0);
     }
     if (npanels > 0)
         mf_dinv_kernel<<<(2 * npanels * 32 + 255) / 256, 256, 0, (side_on || pair_on) ? side : s>>>(dev, panel_node, npanels, info, check_only);
-    if (!side_on && solve64 && nblocks64 > 0) mf_dinv64_kernel<<<2 * nblocks64, SB, 0, s>>>(dev, block_node, 0, nblocks64);
-    if (side_on || pair_on) {
+    if (fork_level >= 0) {
+        const int b0 = level_blk_off[fork_level];
+        if (nblocks64 > b0) mf_dinv64_kernel<<<2 * (nblocks64 - b0), SB, 0, s>>>(dev, block_node, b0, nblocks64 - b0);
+    } else if (!side_on && solve64 && nblocks64 > 0) {
+        mf_dinv64_kernel<<<2 * nblocks64, SB, 0, s>>>(dev, block_node, 0, nblocks64);
+    }
+    if (side_on || pair_on || fork_level >= 0) {
         cudaEventRecord(ev_join, side);
         cudaStreamWaitEvent(s, ev_join, 0);
     }

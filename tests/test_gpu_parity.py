@@ -582,6 +582,7 @@ def test_solver_variants_of_round_two_agree_with_the_oracle_and_with_each_other(
     for w, z, _, _ in base[1:]:                                  # plain path, captured graph, replayed graph
         assert H.rel(w, base[0][0]) < 1e-12 and H.rel(z, base[0][1]) < 1e-10
     for env in ({"OCP_MF_PDL": "0"}, {"OCP_STEP_OVERLAP": "0"}, {"OCP_MF_DINV_PAIR": "1"}, {"OCP_MF_OVERLAP": "1"},
+                {"OCP_MF_OVERLAP_FROM": "0"}, {"OCP_MF_OVERLAP_FROM": "1"}, {"OCP_MF_OVERLAP_FROM": "3"},
                 {"OCP_MF_EA_ATOMIC": "1"}, {"OCP_MF_LEAF_LEVELS": "0"}, {"OCP_MF_LEAF_LEVELS": "3"}):
         out = run(env)
         assert H.rel(out[0][0], base[0][0]) < 1e-12 and H.rel(out[0][1], base[0][1]) < 1e-10, env
